@@ -1,0 +1,228 @@
+/*
+ * seedb200.h -- C ABI of libseedb200.so: the B200 (sm_100a) replacement for the
+ * SEED visual-tokenizer encode path and the llama_xformer forward path.
+ *
+ * The reference (AILab-CVC/SEED) has no FFI of its own: its "plugin interface"
+ * for this path is a set of Python methods.  Every entry
+ * point below names the reference function it replaces (file:line relative to
+ * /root/reference).  The Python mirror in seed_b200/ binds these with ctypes
+ * (see INTEGRATION.md for the exact stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; `stream` is a cudaStream_t passed as void*;
+ *   - unless a name ends in _host, every data pointer is a DEVICE pointer;
+ *   - fp16 tensors are IEEE binary16, row-major, innermost dimension contiguous;
+ *   - every call returns 0 on success, non-zero on failure, and never throws;
+ *     seedb200_last_error() returns a thread-local message for the last failure;
+ *   - all work is enqueued on the caller's stream, no hidden synchronisation and
+ *     no allocation after *_create (so an encode / forward call is CUDA-graph
+ *     capturable);
+ *   - handles are not thread-safe; distinct handles are independent.
+ */
+#ifndef SEEDB200_H
+#define SEEDB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEEDB200_VERSION 100
+
+enum seedb200_status {
+  SEEDB200_OK = 0,
+  SEEDB200_ERR_INVALID = 1,   /* bad argument / shape / missing weight            */
+  SEEDB200_ERR_CUDA = 2,      /* a CUDA runtime or driver call failed             */
+  SEEDB200_ERR_UNSUPPORTED = 3
+};
+
+enum seedb200_dtype { SEEDB200_F16 = 0, SEEDB200_F32 = 1, SEEDB200_I64 = 2, SEEDB200_I32 = 3 };
+
+enum seedb200_act { SEEDB200_ACT_NONE = 0, SEEDB200_ACT_GELU = 1, SEEDB200_ACT_TANH = 2, SEEDB200_ACT_RELU = 3 };
+
+/* VQ distance arithmetic (SURVEY 8a/a10 rounding contract):
+ *   FP16: every term rounded to binary16 exactly where torch rounds it when the
+ *         reference runs its fp16 GPU mode (configs/tokenizer/..._hf.yaml:3);
+ *   FP32: distances evaluated in binary32 (the reference's fp16=False mode).   */
+enum seedb200_vq_mode { SEEDB200_VQ_FP16 = 0, SEEDB200_VQ_FP32 = 1 };
+
+int seedb200_version(void);
+const char* seedb200_last_error(void);
+/* number of kernels launched by this library on the calling thread since the
+ * last reset (bench.py's "gpu_launches"). */
+int64_t seedb200_launch_count(void);
+void seedb200_reset_launch_count(void);
+
+/* A named tensor handed to *_create.  Pointers are borrowed DEVICE pointers to
+ * contiguous fp16 data; the caller keeps them alive for the handle's lifetime.
+ * Names are the reference state-dict keys (qformer_quantizer.py:366-374 for the
+ * tokenizer, HF LLaMA names for llama_xformer.py). */
+typedef struct seedb200_tensor {
+  const char* name;
+  const void* data;
+  int32_t dtype;      /* seedb200_dtype; weights must be SEEDB200_F16 */
+  int32_t ndim;
+  int64_t shape[4];
+} seedb200_tensor;
+
+/* ------------------------------------------------------------------------- */
+/* Per-op entry points (unit tests, ncu).  Each is one kernel launch.         */
+/* ------------------------------------------------------------------------- */
+
+/* out = epilogue(A[M,K] . W[N,K]^T): torch.nn.functional.linear as used at
+ * eva_vit.py:133-135/:157/:60-65, qformer_causual.py:176-181/:251-255/:320-337,
+ * llama_xformer.py:186/:223-225/:258/:718.  tcgen05 + TMA + TMEM kernel.     */
+typedef struct seedb200_gemm_desc {
+  int32_t M, N, K;
+  const void* A;  int64_t lda;        /* fp16 [M,K]                              */
+  const void* W;  int64_t ldw;        /* fp16 [N,K] (nn.Linear.weight layout)    */
+  void* out;      int64_t ldo;        /* fp16 [rows, N] (N/2 columns in mode 1)  */
+  const void* bias;                   /* fp16 [N] or NULL                        */
+  const void* residual; int64_t ldr;  /* fp16, added after bias/act, or NULL     */
+  int32_t act;                        /* seedb200_act                            */
+  int32_t mode;                       /* 0 linear; 1 SiLU-gate: W rows are blocks
+                                         of [128 gate | 128 up], out[m,j] =
+                                         silu(gate_j) * up_j (llama_xformer.py:186) */
+  /* optional output-row remap: out_row = (m / row_group) * row_stride +
+   * (m % row_group) + row_offset when row_group > 0, else out_row = m.
+   * residual row = (m % res_mod) + res_offset when res_mod > 0 else out_row.
+   * Used to write patch tokens behind the cls token and add pos_embed
+   * (eva_vit.py:373-377).                                                      */
+  int32_t row_group, row_stride, row_offset;
+  int32_t res_mod, res_offset;
+  int32_t bn;                         /* tile-N hint, 0 = auto                   */
+  int32_t ctas;                       /* 1 or 2 (cta_group::2 pair), 0 = auto    */
+} seedb200_gemm_desc;
+int seedb200_gemm(const seedb200_gemm_desc* d, void* stream);
+
+/* y = LayerNorm(x) * w + b, statistics in fp32 (eva_vit.py:201-202 norm1/norm2,
+ * blip2.py:179-184 ln_vision, qformer_causual.py:96/:254/:336).               */
+int seedb200_layernorm(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,
+                       int rows, int cols, float eps, void* stream);
+/* LlamaRMSNorm.forward (llama_xformer.py:105-113): fp32 normalise, round to
+ * fp16, multiply by the fp16 weight.                                           */
+int seedb200_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy,
+                     int rows, int cols, float eps, void* stream);
+
+/* softmax(scale * Q K^T [+ causal]) V for strided [batch, head, token, dim]
+ * views.  Replaces eva_vit.py:139-156, qformer_causual.py:189-236, vit.py:93-103
+ * and xops.memory_efficient_attention at llama_xformer.py:240-256.
+ * Strides are in elements; head_dim in {64, 88, 128}.  causal != 0 masks key j
+ * for query i when j > i + (nk - nq).                                          */
+typedef struct seedb200_attn_desc {
+  const void* q; const void* k; const void* v; void* o;
+  int64_t q_bs, q_hs, q_ts;   /* batch / head / token strides of q              */
+  int64_t k_bs, k_hs, k_ts;
+  int64_t v_bs, v_hs, v_ts;
+  int64_t o_bs, o_hs, o_ts;
+  int32_t batch, heads, nq, nk, head_dim;
+  int32_t causal;
+  float scale;
+} seedb200_attn_desc;
+int seedb200_attention(const seedb200_attn_desc* d, void* stream);
+
+/* VectorQuantizer2.forward (qformer_quantizer.py:94-98): nearest codebook row
+ * under squared L2, ties -> lowest index, int64 ids.  z [n,dim], codebook
+ * [n_codes,dim] fp16; dim must be 32.                                          */
+int seedb200_vq_argmin(const void* z, const void* codebook, int n, int n_codes, int dim,
+                       int mode, int64_t* ids, void* stream);
+
+/* PatchEmbed unfold (eva_vit.py:222,229 conv k14 s14 as a GEMM): images
+ * [B,3,224,224] fp16 -> rows [B*256, kpad] fp16 (column = c*196 + dy*14 + dx,
+ * zero padded to kpad), plus the cls rows of x: x[b,0,:] = cls + pos[0]
+ * (eva_vit.py:373-377).                                                        */
+int seedb200_patchify(const void* images, int B, void* cols, int kpad, void* stream);
+
+/* apply_rotary_pos_emb (llama_xformer.py:152-161) fused with the KV-cache append
+ * (llama_xformer.py:234-239).  qkv [T, 3*H*D] (q | k | v per token), positions
+ * [T] int64; writes q_out [T, H*D] and appends K (post-RoPE) and V at cache row
+ * past_len + t of caches laid out [B, H, max_seq, D].                          */
+int seedb200_rope_kv_append(const void* qkv, const int64_t* positions, int B, int S, int H, int D,
+                            int past_len, int max_seq, void* q_out, void* k_cache, void* v_cache,
+                            void* stream);
+
+/* embedding gather (llama_xformer.py:544; qformer_quantizer.py:133).           */
+int seedb200_embedding(const void* table, int64_t ld, const int64_t* ids, int n, int cols,
+                       void* out, int64_t ldo, int64_t n_rows, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Image tokenizer: Blip2QformerQuantizer (qformer_quantizer.py:143-338)       */
+/* ------------------------------------------------------------------------- */
+typedef struct seedb200_encoder seedb200_encoder;
+
+typedef struct seedb200_encoder_config {
+  int32_t vit_depth;        /* 39  (eva_vit.py:466)                              */
+  int32_t qformer_layers;   /* 12  (BertConfig default, blip2.py:54)             */
+  int32_t detok_depth;      /* 4   (qformer_quantizer.py:176), 0 = no de-tokenizer head */
+  int32_t n_codes;          /* 8192                                              */
+  int32_t max_batch;        /* workspace is sized for this many images per call  */
+  int32_t vq_mode;          /* seedb200_vq_mode                                  */
+  int32_t gemm_ctas;        /* 0 auto, 1, 2: cta_group used by the GEMMs         */
+} seedb200_encoder_config;
+
+int seedb200_encoder_create(const seedb200_encoder_config* cfg, const seedb200_tensor* weights, int n_weights,
+                            seedb200_encoder** out);
+void seedb200_encoder_destroy(seedb200_encoder* enc);
+
+/* Blip2QformerQuantizer.get_codebook_indices (qformer_quantizer.py:288-307) as
+ * called by ImageTokenizer.encode (seed_llama_tokenizer.py:75-90):
+ * images [B,3,224,224] fp16 -> ids [B,32] int64.  Optional outputs (NULL to
+ * skip): z [B*32,32] fp16 (encode_task_layer output, the VQ input) and
+ * query_up [B,32,768] fp16 (decode_task_layer(quant), the 2nd return value).   */
+int seedb200_encoder_encode(seedb200_encoder* enc, const void* images, int B, int64_t* ids,
+                            void* z_out, void* query_up_out, void* stream);
+/* Same, with pinned HOST buffers; copies ride the same stream (bench e2e).     */
+int seedb200_encoder_encode_host(seedb200_encoder* enc, const void* images_host, int B,
+                                 int64_t* ids_host, void* stream);
+/* Blip2QformerQuantizer.get_codebook_entry (qformer_quantizer.py:309-338):
+ * ids [B,32] int64 -> image_embeds [B,1024] fp16.                              */
+int seedb200_encoder_detokenize(seedb200_encoder* enc, const int64_t* ids, int B, void* embeds_out,
+                                void* stream);
+/* Debug / parity taps: copy an internal activation of the last encode call.
+ * what: 0 = ViT output before ln_vision [B*257,1408]; 1 = Q-Former output
+ * [B*32,768]; 2 = ln_vision output [B*257,1408].  Returns element count.       */
+int64_t seedb200_encoder_tap(seedb200_encoder* enc, int what, void* dst, int64_t max_elems, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* LLaMA: models/llama_xformer.py LlamaForCausalLM                              */
+/* ------------------------------------------------------------------------- */
+typedef struct seedb200_llama seedb200_llama;
+
+typedef struct seedb200_llama_config {
+  int32_t hidden, layers, heads, head_dim, ffn, vocab;
+  int32_t max_batch, max_seq;   /* KV cache [layers][2][max_batch, heads, max_seq, head_dim] */
+  float rms_eps;
+  float rope_base;              /* 10000 (llama_xformer.py:118)                  */
+  int32_t gemm_ctas;
+} seedb200_llama_config;
+
+int seedb200_llama_create(const seedb200_llama_config* cfg, const seedb200_tensor* weights, int n_weights,
+                          seedb200_llama** out);
+void seedb200_llama_destroy(seedb200_llama* llm);
+
+/* LlamaForCausalLM.forward (llama_xformer.py:661-743).  input_ids [B,S] int64
+ * (or inputs_embeds [B,S,hidden] fp16 when input_ids is NULL), position_ids
+ * [B,S] int64 (NULL = past_len + arange(S), llama_xformer.py:530-539).  The
+ * internal KV cache must already hold past_len tokens.  logits_out is
+ * [B,S,vocab] fp16 (logits_mode 0, the reference contract) or [B,1,vocab]
+ * (logits_mode 1: last position only, the generate() fast path).
+ * Attention is causal over past+new, except S == 1 where the reference passes
+ * attn_bias=None (llama_xformer.py:255).                                        */
+int seedb200_llama_forward(seedb200_llama* llm, const int64_t* input_ids, const void* inputs_embeds,
+                           const int64_t* position_ids, int B, int S, int past_len, int logits_mode,
+                           void* logits_out, void* stream);
+/* Views of the KV cache of one layer: [max_batch, heads, max_seq, head_dim]
+ * fp16; the first past_len+S rows per (batch, head) are valid.  Used to build
+ * the past_key_values tuple the reference returns (llama_xformer.py:239).      */
+int seedb200_llama_kv_ptrs(seedb200_llama* llm, int layer, void** k, void** v);
+/* Load an externally supplied past (past_key_values argument) into the cache:  */
+int seedb200_llama_kv_load(seedb200_llama* llm, int layer, const void* k, const void* v, int B, int past_len,
+                           void* stream);
+/* tap: final hidden states (after model.norm) of the last forward [B*S,hidden] */
+int64_t seedb200_llama_tap(seedb200_llama* llm, int what, void* dst, int64_t max_elems, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEEDB200_H */

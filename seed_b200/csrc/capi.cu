@@ -1,0 +1,82 @@
+// capi.cu -- C-ABI plumbing shared by every entry point: thread-local error text, launch counter,
+// device query, and the stand-alone RoPE entry (which owns a small cache of cos/sin tables).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <map>
+#include <mutex>
+
+#include "common.cuh"
+#include "ops.h"
+
+namespace sb {
+
+static thread_local char g_err[1024] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+struct RopeTables { void* cos_t; void* sin_t; int max_pos; };
+static std::mutex g_rope_mu;
+static std::map<long long, RopeTables> g_rope_cache;
+
+int get_rope_tables(int D, float base, int min_pos, const void** cos_t, const void** sin_t, int* max_pos,
+                    cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(g_rope_mu);
+  int dev = 0;
+  SB_CHECK_CUDA(cudaGetDevice(&dev));
+  const long long key = ((long long)dev << 48) | ((long long)D << 32) | (long long)(unsigned)(base);
+  auto it = g_rope_cache.find(key);
+  if (it != g_rope_cache.end() && it->second.max_pos >= min_pos) {
+    *cos_t = it->second.cos_t; *sin_t = it->second.sin_t; *max_pos = it->second.max_pos;
+    return 0;
+  }
+  int n = 4096;
+  while (n < min_pos) n *= 2;
+  RopeTables t;
+  t.max_pos = n;
+  SB_CHECK_CUDA(cudaMalloc(&t.cos_t, (size_t)n * (D / 2) * 2));
+  SB_CHECK_CUDA(cudaMalloc(&t.sin_t, (size_t)n * (D / 2) * 2));
+  SB_PROPAGATE(build_rope_tables(t.cos_t, t.sin_t, n, D, base, stream));
+  g_rope_cache[key] = t;   // an older, smaller table (if any) stays alive: in-flight kernels may still read it
+  *cos_t = t.cos_t; *sin_t = t.sin_t; *max_pos = n;
+  return 0;
+}
+
+}  // namespace sb
+
+extern "C" {
+
+int seedb200_version(void) { return SEEDB200_VERSION; }
+const char* seedb200_last_error(void) { return sb::g_err; }
+int64_t seedb200_launch_count(void) { return sb::g_launches; }
+void seedb200_reset_launch_count(void) { sb::g_launches = 0; }
+
+int seedb200_rope_kv_append(const void* qkv, const int64_t* positions, int B, int S, int H, int D, int past_len,
+                            int max_seq, void* q_out, void* k_cache, void* v_cache, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const void *cos_t, *sin_t;
+  int max_pos;
+  SB_PROPAGATE(sb::get_rope_tables(D, 10000.0f, max_seq, &cos_t, &sin_t, &max_pos, st));
+  return sb::rope_kv_append_tables(qkv, positions, B, S, H, D, past_len, max_seq, max_pos, cos_t, sin_t, q_out,
+                                   k_cache, v_cache, st);
+}
+
+}  // extern "C"

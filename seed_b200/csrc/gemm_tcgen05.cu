@@ -1,0 +1,476 @@
+// gemm_tcgen05.cu -- out = epilogue(A[M,K] . W[N,K]^T), fp16 operands, fp32 accumulate.
+//
+// This is the kernel that carries >97% of the encode FLOPs (SURVEY.md 2.4 rows E1,E4,E6,E7,
+// E10-E15) and all LLaMA linears (rows L4,L8,L9,L10).  It replaces the cuBLAS calls behind
+// torch.nn.functional.linear in the reference (eva_vit.py:133-135,157,60-65;
+// qformer_causual.py:176-181,251-255,320-337; llama_xformer.py:186,223-225,258,718).
+//
+// Design (B200 / sm_100a):
+//   * persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer
+//     (one elected thread), warp 2 = TMEM allocator, warps 4..11 = epilogue;
+//   * A and W tiles are fetched by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a
+//     multi-stage shared-memory ring guarded by full/empty mbarriers;
+//   * accumulators live in TMEM, double buffered (2 x BN columns) so the epilogue of tile i
+//     overlaps the MMAs of tile i+1;
+//   * CTAS == 2: a CTA pair (cluster of 2) runs one 256 x BN tcgen05.mma.cta_group::2 tile;
+//     each CTA loads its own 128 rows of A and half of the W tile, halving the shared-memory
+//     and L2 traffic per FLOP;
+//   * epilogue: tcgen05.ld -> registers -> bias / activation / residual with the reference's
+//     fp16 rounding points -> 16-byte global stores.  SiLU-gate mode reads the gate and up
+//     halves of the same accumulator tile (llama_xformer.py:186).
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace sb {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;
+constexpr int GEMM_THREADS = 384;      // 4 control warps + 8 epilogue warps
+constexpr int GEMM_EPI_WARP0 = 4;
+constexpr int GEMM_EPI_THREADS = 256;
+
+struct GemmParams {
+  int M, N, K;
+  int m_tiles, n_tiles;      // m_tiles counts CTAS*128-row tiles
+  const __half* bias;
+  const __half* residual;
+  long long ldr;
+  __half* out;
+  long long ldo;
+  int act;
+  int row_group, row_stride, row_offset;
+  int res_mod, res_offset;
+};
+
+template <int BN, int CTAS>
+struct GemmCfg {
+  static constexpr int LOAD_N = BN / CTAS;
+  static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+  static constexpr int B_BYTES = LOAD_N * GEMM_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int ACC_STRIDE = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + BAR_BYTES;
+  // keep one CTA per SM (TMEM is allocated per CTA): request more than half of the SM's smem
+  static constexpr int SMEM_REQUEST = SMEM_BYTES < 120 * 1024 ? 120 * 1024 : SMEM_BYTES;
+  static_assert(B_BYTES % 1024 == 0, "W stage must keep 1024-byte alignment for SWIZZLE_128B");
+  static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
+  static_assert(STAGES >= 3, "pipeline too shallow");
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  // 0.5 x (1 + erf(x / sqrt 2)), erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, below fp16 resolution)
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = 1.0f - p * __expf(-z * z);
+  const float erfv = copysignf(e, x);
+  return 0.5f * x * (1.0f + erfv);
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case SEEDB200_ACT_GELU: return gelu_erf(x);
+    case SEEDB200_ACT_TANH: return tanhf(x);
+    case SEEDB200_ACT_RELU: return fmaxf(x, 0.0f);
+    default: return x;
+  }
+}
+
+// One 16-column chunk of one output row: bias -> fp16 -> act -> fp16 -> (+residual) -> fp16 -> store.
+template <int MODE>
+__device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint32_t (&acc)[16],
+                                                 const uint32_t (&acc2)[16], int m, int n0, int n_limit) {
+  if (m >= p.M || n0 >= n_limit) return;
+  long long orow = m;
+  if (p.row_group > 0) orow = (long long)(m / p.row_group) * p.row_stride + (m % p.row_group) + p.row_offset;
+  long long rrow = orow;
+  if (p.res_mod > 0) rrow = (m % p.res_mod) + p.res_offset;
+
+  __half h[16];
+  if constexpr (MODE == 1) {
+    // SiLU-gate: silu(fp16(gate)) rounded to fp16, times fp16(up), rounded (llama_xformer.py:186)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float g = __half2float(__float2half_rn(__uint_as_float(acc[j])));
+      const float u = __half2float(__float2half_rn(__uint_as_float(acc2[j])));
+      const float s = __half2float(__float2half_rn(g / (1.0f + __expf(-g))));
+      h[j] = __float2half_rn(s * u);
+    }
+  } else {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+    if (p.bias != nullptr) {
+      if (n0 + 16 <= n_limit) {
+        const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
+        const uint4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+        const __half2* bh0 = reinterpret_cast<const __half2*>(&b0);
+        const __half2* bh1 = reinterpret_cast<const __half2*>(&b1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f0 = __half22float2(bh0[j]);
+          const float2 f1 = __half22float2(bh1[j]);
+          v[2 * j] += f0.x; v[2 * j + 1] += f0.y;
+          v[8 + 2 * j] += f1.x; v[8 + 2 * j + 1] += f1.y;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n0 + j < n_limit) v[j] += __half2float(p.bias[n0 + j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(v[j]);
+    if (p.act != SEEDB200_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(apply_act(__half2float(h[j]), p.act));
+    }
+  }
+
+  const bool full = (n0 + 16 <= n_limit);
+  if (p.residual != nullptr) {
+    const __half* rp = p.residual + rrow * p.ldr + n0;
+    if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+      const uint4 r0 = *reinterpret_cast<const uint4*>(rp);
+      const uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
+      const __half* rh0 = reinterpret_cast<const __half*>(&r0);
+      const __half* rh1 = reinterpret_cast<const __half*>(&r1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        h[j] = __float2half_rn(__half2float(h[j]) + __half2float(rh0[j]));
+        h[8 + j] = __float2half_rn(__half2float(h[8 + j]) + __half2float(rh1[j]));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n0 + j < n_limit) h[j] = __float2half_rn(__half2float(h[j]) + __half2float(rp[j]));
+    }
+  }
+
+  __half* op = p.out + orow * p.ldo + n0;
+  if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+    uint4 o0, o1;
+    __half* oh0 = reinterpret_cast<__half*>(&o0);
+    __half* oh1 = reinterpret_cast<__half*>(&o1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { oh0[j] = h[j]; oh1[j] = h[8 + j]; }
+    *reinterpret_cast<uint4*>(op) = o0;
+    *reinterpret_cast<uint4*>(op + 8) = o1;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (n0 + j < n_limit) op[j] = h[j];
+  }
+}
+
+template <int BN, int CTAS, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmParams p) {
+  using Cfg = GemmCfg<BN, CTAS>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned stage bases (same offset in both CTAs of a pair)
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + STAGES * Cfg::A_BYTES;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t full_bar = bar_base;                   // [STAGES]
+  const uint32_t empty_bar = bar_base + STAGES * 8;     // [STAGES]
+  const uint32_t tfull_bar = bar_base + 2 * STAGES * 8; // [2]
+  const uint32_t tempty_bar = tfull_bar + 16;           // [2]
+  const uint32_t tmem_slot = tempty_bar + 16;           // uint32
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (cta_rank == 0);
+
+  if constexpr (CTAS == 2) cluster_sync_all();  // both CTAs resident before the paired TMEM allocation
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, CTAS);   // one arrive per CTA's producer (leader's copy is the one waited on)
+      mbar_init(empty_bar + 8 * s, 1);     // one tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar + 8 * i, 1);
+      mbar_init(tempty_bar + 8 * i, CTAS * GEMM_EPI_THREADS);
+    }
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc<CTAS>(tmem_slot, Cfg::TMEM_COLS);
+  }
+  tc_fence_before();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int tile0 = (CTAS == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const int tile_step = (CTAS == 2) ? (gridDim.x >> 1) : gridDim.x;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+        const int m_idx = (mt * CTAS + (int)cta_rank) * GEMM_BLOCK_M;
+        const int n_idx = nt * BN + (int)cta_rank * Cfg::LOAD_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_a + stage * Cfg::A_BYTES;
+          const uint32_t sb_ = smem_b + stage * Cfg::B_BYTES;
+          if constexpr (CTAS == 1) {
+            mbar_arrive_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
+            tma_load_2d(sa, &tmap_a, full_bar + 8 * stage, kb * GEMM_BLOCK_K, m_idx);
+            tma_load_2d(sb_, &tmap_b, full_bar + 8 * stage, kb * GEMM_BLOCK_K, n_idx);
+          } else {
+            const uint32_t lead_bar = mapa_shared(full_bar + 8 * stage, 0);
+            if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_2cta(sa, &tmap_a, lead_bar, kb * GEMM_BLOCK_K, m_idx);
+            tma_load_2d_2cta(sb_, &tmap_b, lead_bar, kb * GEMM_BLOCK_K, n_idx);
+            if (!leader) mbar_arrive_cluster(lead_bar);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(GEMM_BLOCK_M * CTAS, BN);
+      int stage = 0; uint32_t phase = 0; int iter = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        mbar_wait(tempty_bar + 8 * as, aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(smem_a + stage * Cfg::A_BYTES);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_b + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            // advance 16 halves = 32 bytes inside the 128-byte swizzle atom: +2 in 16-byte units
+            umma_f16<CTAS>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit<CTAS>(empty_bar + 8 * stage);            // frees the smem slot (both CTAs)
+          if (kb == num_kb - 1) umma_commit<CTAS>(tfull_bar + 8 * as);  // accumulator ready
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      if constexpr (CTAS == 2) {
+        // drain: make sure every remote tmem-empty arrive has landed before teardown
+        for (int back = 1; back <= 2 && back <= iter; ++back) {
+          const int it = iter - back;
+          mbar_wait(tempty_bar + 8 * (it & 1), (it >> 1) & 1);
+        }
+      }
+    }
+  } else if (warp >= GEMM_EPI_WARP0) {
+    // ===================== epilogue =====================
+    const int ew = warp - GEMM_EPI_WARP0;      // 0..7
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+    const int half_id = ew >> 2;               // which half of the column chunks
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t lead_tempty0 = (CTAS == 2) ? mapa_shared(tempty_bar, 0) : tempty_bar;
+    constexpr int NCHUNK = (MODE == 1) ? (BN / 32) : (BN / 16);   // 16-column output chunks per tile
+    constexpr int CH0 = (NCHUNK + 1) / 2;
+    const int c_begin = half_id == 0 ? 0 : CH0;
+    const int c_end = half_id == 0 ? CH0 : NCHUNK;
+    const int n_limit = (MODE == 1) ? p.N / 2 : p.N;
+    int iter = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++iter) {
+      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      mbar_wait(tfull_bar + 8 * as, aphase);
+      tc_fence_after();
+      const int m = (mt * CTAS + (int)cta_rank) * GEMM_BLOCK_M + quarter * 32 + lane;
+      const uint32_t t_acc = tmem_base + as * Cfg::ACC_STRIDE + lane_addr;
+      for (int c = c_begin; c < c_end; ++c) {
+        uint32_t r0[16], r1[16];
+        tmem_ld16(t_acc + c * 16, r0);
+        if constexpr (MODE == 1) tmem_ld16(t_acc + BN / 2 + c * 16, r1);
+        tmem_ld_wait();
+        if (c == c_end - 1) {
+          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+          tc_fence_before();
+          if constexpr (CTAS == 2) mbar_arrive_cluster(lead_tempty0 + 8 * as);
+          else mbar_arrive(tempty_bar + 8 * as);
+        }
+        const int n0 = (MODE == 1) ? nt * (BN / 2) + c * 16 : nt * BN + c * 16;
+        epilogue_store16<MODE>(p, r0, r1, m, n0, n_limit);
+      }
+      if (c_begin >= c_end) {   // (never for the instantiated shapes; keeps the barrier count exact)
+        tc_fence_before();
+        if constexpr (CTAS == 2) mbar_arrive_cluster(lead_tempty0 + 8 * as);
+        else mbar_arrive(tempty_bar + 8 * as);
+      }
+    }
+  }
+
+  tc_fence_before();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CTAS>(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp16 [rows, cols] row-major with leading dimension ld (elements); box = box_rows x 64 columns, 128B swizzle
+static int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    return SEEDB200_ERR_CUDA;
+  }
+  SB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "gemm: operand pointer %p not 16-byte aligned", ptr);
+  SB_REQUIRE((ld * 2) % 16 == 0, "gemm: leading dimension %lld (elements) is not a multiple of 8", (long long)ld);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)GEMM_BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld box_rows=%d)", (int)r,
+              (long long)rows, (long long)cols, (long long)ld, box_rows);
+    return SEEDB200_ERR_CUDA;
+  }
+  return 0;
+}
+
+template <int BN, int CTAS, int MODE>
+static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CTAS>;
+  static bool attr_set = false;
+  auto kern = gemm_tcgen05_kernel<BN, CTAS, MODE>;
+  if (!attr_set) {
+    SB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_REQUEST));
+    attr_set = true;
+  }
+  CUtensorMap ta, tb;
+  SB_PROPAGATE(make_tmap(&ta, d.A, d.M, d.K, d.lda, GEMM_BLOCK_M));
+  SB_PROPAGATE(make_tmap(&tb, d.W, d.N, d.K, d.ldw, Cfg::LOAD_N));
+
+  GemmParams p;
+  p.M = d.M; p.N = d.N; p.K = d.K;
+  p.m_tiles = (d.M + GEMM_BLOCK_M * CTAS - 1) / (GEMM_BLOCK_M * CTAS);
+  p.n_tiles = (d.N + BN - 1) / BN;
+  p.bias = static_cast<const __half*>(d.bias);
+  p.residual = static_cast<const __half*>(d.residual);
+  p.ldr = d.ldr;
+  p.out = static_cast<__half*>(d.out);
+  p.ldo = d.ldo;
+  p.act = d.act;
+  p.row_group = d.row_group; p.row_stride = d.row_stride; p.row_offset = d.row_offset;
+  p.res_mod = d.res_mod; p.res_offset = d.res_offset;
+
+  const int sms = num_sms();
+  const int tiles = p.m_tiles * p.n_tiles;
+  int units = sms / CTAS;
+  if (units > tiles) units = tiles;
+  if (units < 1) units = 1;
+
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(units * CTAS);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_REQUEST;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  SB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  count_launch();
+  return 0;
+}
+
+static int pick_bn(int N, int mode) {
+  if (mode == 1) return 256;
+  if (N % 256 == 0) return 256;
+  if (N % 192 == 0) return 192;
+  if (N % 176 == 0) return 176;
+  if (N % 128 == 0) return 128;
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  return 256;
+}
+
+int gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
+  SB_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "gemm: non-positive shape M=%d N=%d K=%d", d.M, d.N, d.K);
+  SB_REQUIRE(d.A && d.W && d.out, "gemm: null operand");
+  SB_REQUIRE(d.mode == 0 || d.mode == 1, "gemm: unknown mode %d", d.mode);
+  SB_REQUIRE(d.K % 8 == 0, "gemm: K=%d must be a multiple of 8 (16-byte TMA rows)", d.K);
+  if (d.mode == 1) {
+    SB_REQUIRE(d.N % 256 == 0, "gemm: SiLU-gate mode needs N %% 256 == 0 (got %d)", d.N);
+    SB_REQUIRE(d.bias == nullptr && d.act == 0, "gemm: SiLU-gate mode takes no bias/activation");
+  }
+  int bn = d.bn > 0 ? d.bn : pick_bn(d.N, d.mode);
+  int ctas = d.ctas > 0 ? d.ctas : 1;
+  SB_REQUIRE(ctas == 1 || ctas == 2, "gemm: ctas must be 1 or 2 (got %d)", ctas);
+  if (ctas == 2 && (bn < 64 || d.M <= GEMM_BLOCK_M)) ctas = 1;   // pairs only pay off on big tiles
+
+#define SB_GEMM_CASE(BN_, CT_, MD_) \
+  if (bn == BN_ && ctas == CT_ && d.mode == MD_) return launch_gemm<BN_, CT_, MD_>(d, stream);
+  SB_GEMM_CASE(256, 1, 0) SB_GEMM_CASE(256, 2, 0)
+  SB_GEMM_CASE(192, 1, 0) SB_GEMM_CASE(192, 2, 0)
+  SB_GEMM_CASE(176, 1, 0) SB_GEMM_CASE(176, 2, 0)
+  SB_GEMM_CASE(128, 1, 0) SB_GEMM_CASE(128, 2, 0)
+  SB_GEMM_CASE(64, 1, 0)  SB_GEMM_CASE(64, 2, 0)
+  SB_GEMM_CASE(32, 1, 0)
+  SB_GEMM_CASE(256, 1, 1) SB_GEMM_CASE(256, 2, 1)
+#undef SB_GEMM_CASE
+  set_error("gemm: unsupported tile configuration bn=%d ctas=%d mode=%d", bn, ctas, d.mode);
+  return SEEDB200_ERR_UNSUPPORTED;
+}
+
+}  // namespace sb
+
+extern "C" int seedb200_gemm(const seedb200_gemm_desc* d, void* stream) {
+  if (d == nullptr) {
+    sb::set_error("seedb200_gemm: null descriptor");
+    return SEEDB200_ERR_INVALID;
+  }
+  return sb::gemm(*d, static_cast<cudaStream_t>(stream));
+}

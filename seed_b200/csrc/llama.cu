@@ -1,0 +1,273 @@
+// llama.cu -- seedb200_llama: models/llama_xformer.py LlamaForCausalLM.forward (:661-743) /
+// LlamaModel.forward (:496-627) / LlamaDecoderLayer.forward (:280-332) as a fixed launch sequence.
+//
+// What changes relative to the reference graph:
+//   * q/k/v projections run as ONE GEMM over a fused [3h, h] weight, gate/up as ONE GEMM whose epilogue
+//     applies SiLU(gate)*up (weights interleaved in 128-row blocks at create time);
+//   * the dense additive mask (:50-92, :552-557) and the per-layer `attention_mask.sum() == 0` host sync
+//     (:255) are gone: causality is a kernel flag;
+//   * the KV cache is preallocated [B, H, max_seq, D] and appended in place by the RoPE kernel instead of
+//     torch.cat per layer per step (:236-237);
+//   * batch-1 decode (S == 1) switches to the HBM-bound GEMV / split-KV kernels.
+// Weights named like the HF checkpoint (model.layers.N.self_attn.q_proj.weight ...).  o_proj, down_proj,
+// norms, embed_tokens and lm_head are borrowed; q/k/v and gate/up are copied into their fused layouts and
+// the originals are not referenced after create.
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "ops.h"
+
+namespace sb {
+struct LlamaLayerW {
+  const __half *in_ln, *post_ln, *qkv_w, *o_w, *gu_w, *down_w;
+  __half *k_cache, *v_cache;
+};
+}  // namespace sb
+
+struct seedb200_llama {
+  seedb200_llama_config cfg;
+  std::map<std::string, seedb200_tensor> w;
+  std::vector<void*> owned;
+  const __half *embed, *norm_w, *lm_head;
+  std::vector<sb::LlamaLayerW> layers;
+  const void *cos_t, *sin_t;
+  int max_pos;
+  __half *x, *nb, *qkv, *q, *att, *gu, *hn, *last;
+  float* da_ws;
+  int last_T;
+};
+
+namespace sb {
+
+static int llama_find(const seedb200_llama* m, const std::string& name, const __half** out, int64_t n_expected) {
+  auto it = m->w.find(name);
+  if (it == m->w.end()) {
+    set_error("llama_create: missing weight '%s'", name.c_str());
+    return SEEDB200_ERR_INVALID;
+  }
+  const seedb200_tensor& t = it->second;
+  int64_t n = 1;
+  for (int i = 0; i < t.ndim; ++i) n *= t.shape[i];
+  if (t.dtype != SEEDB200_F16 || n != n_expected || (reinterpret_cast<uintptr_t>(t.data) & 15) != 0) {
+    set_error("llama_create: weight '%s' must be fp16, 16-byte aligned, %lld elements (got %lld)", name.c_str(),
+              (long long)n_expected, (long long)n);
+    return SEEDB200_ERR_INVALID;
+  }
+  *out = static_cast<const __half*>(t.data);
+  return 0;
+}
+
+template <typename T>
+static int llama_alloc(seedb200_llama* m, T** p, size_t elems) {
+  void* q = nullptr;
+  size_t bytes = elems * sizeof(T);
+  SB_CHECK_CUDA(cudaMalloc(&q, bytes < 256 ? 256 : bytes));
+  m->owned.push_back(q);
+  *p = static_cast<T*>(q);
+  return 0;
+}
+
+static int llama_build(seedb200_llama* m) {
+  const seedb200_llama_config& c = m->cfg;
+  const int64_t h = c.hidden, ffn = c.ffn, V = c.vocab;
+  cudaStream_t st = 0;
+  char nm[256];
+  SB_PROPAGATE(llama_find(m, "model.embed_tokens.weight", &m->embed, V * h));
+  SB_PROPAGATE(llama_find(m, "model.norm.weight", &m->norm_w, h));
+  SB_PROPAGATE(llama_find(m, "lm_head.weight", &m->lm_head, V * h));
+  m->layers.resize(c.layers);
+  const size_t cache_elems = (size_t)c.max_batch * c.heads * c.max_seq * c.head_dim;
+  for (int l = 0; l < c.layers; ++l) {
+    LlamaLayerW& L = m->layers[l];
+    auto key = [&](const char* s) { snprintf(nm, sizeof(nm), "model.layers.%d.%s", l, s); return std::string(nm); };
+    const __half *wq, *wk, *wv, *wg, *wu;
+    SB_PROPAGATE(llama_find(m, key("input_layernorm.weight"), &L.in_ln, h));
+    SB_PROPAGATE(llama_find(m, key("post_attention_layernorm.weight"), &L.post_ln, h));
+    SB_PROPAGATE(llama_find(m, key("self_attn.q_proj.weight"), &wq, h * h));
+    SB_PROPAGATE(llama_find(m, key("self_attn.k_proj.weight"), &wk, h * h));
+    SB_PROPAGATE(llama_find(m, key("self_attn.v_proj.weight"), &wv, h * h));
+    SB_PROPAGATE(llama_find(m, key("self_attn.o_proj.weight"), &L.o_w, h * h));
+    SB_PROPAGATE(llama_find(m, key("mlp.gate_proj.weight"), &wg, ffn * h));
+    SB_PROPAGATE(llama_find(m, key("mlp.up_proj.weight"), &wu, ffn * h));
+    SB_PROPAGATE(llama_find(m, key("mlp.down_proj.weight"), &L.down_w, h * ffn));
+    __half *fq, *fg;
+    SB_PROPAGATE(llama_alloc(m, &fq, (size_t)3 * h * h));
+    SB_CHECK_CUDA(cudaMemcpyAsync(fq, wq, (size_t)h * h * 2, cudaMemcpyDeviceToDevice, st));
+    SB_CHECK_CUDA(cudaMemcpyAsync(fq + (size_t)h * h, wk, (size_t)h * h * 2, cudaMemcpyDeviceToDevice, st));
+    SB_CHECK_CUDA(cudaMemcpyAsync(fq + (size_t)2 * h * h, wv, (size_t)h * h * 2, cudaMemcpyDeviceToDevice, st));
+    L.qkv_w = fq;
+    // [ffn/128] blocks of [128 gate rows | 128 up rows]
+    SB_PROPAGATE(llama_alloc(m, &fg, (size_t)2 * ffn * h));
+    const size_t blk = (size_t)128 * h * 2;
+    SB_CHECK_CUDA(cudaMemcpy2DAsync(fg, 2 * blk, wg, blk, blk, ffn / 128, cudaMemcpyDeviceToDevice, st));
+    SB_CHECK_CUDA(cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(fg) + blk, 2 * blk, wu, blk, blk, ffn / 128,
+                                    cudaMemcpyDeviceToDevice, st));
+    L.gu_w = fg;
+    SB_PROPAGATE(llama_alloc(m, &L.k_cache, cache_elems));
+    SB_PROPAGATE(llama_alloc(m, &L.v_cache, cache_elems));
+  }
+  SB_PROPAGATE(get_rope_tables(c.head_dim, c.rope_base, c.max_seq, &m->cos_t, &m->sin_t, &m->max_pos, st));
+  const size_t T = (size_t)c.max_batch * c.max_seq;
+  SB_PROPAGATE(llama_alloc(m, &m->x, T * h));
+  SB_PROPAGATE(llama_alloc(m, &m->nb, T * h));
+  SB_PROPAGATE(llama_alloc(m, &m->qkv, T * 3 * h));
+  SB_PROPAGATE(llama_alloc(m, &m->q, T * h));
+  SB_PROPAGATE(llama_alloc(m, &m->att, T * h));
+  SB_PROPAGATE(llama_alloc(m, &m->gu, T * ffn));
+  SB_PROPAGATE(llama_alloc(m, &m->hn, T * h));
+  SB_PROPAGATE(llama_alloc(m, &m->last, (size_t)c.max_batch * h));
+  SB_PROPAGATE(llama_alloc(m, &m->da_ws, (size_t)c.max_batch * c.heads * 32 * (128 + 2)));
+  SB_CHECK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static int lin(cudaStream_t st, int ctas, int M, int N, int K, const void* A, const void* W, void* out, int64_t ldo,
+               const void* residual, int mode) {
+  if (M <= 4) return gemv(A, W, K, out, residual, M, N, K, mode, st);
+  seedb200_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.M = M; d.N = N; d.K = K; d.A = A; d.lda = K; d.W = W; d.ldw = K;
+  d.out = out; d.ldo = ldo; d.residual = residual; d.ldr = ldo; d.mode = mode; d.ctas = ctas;
+  return gemm(d, st);
+}
+
+static int llama_forward(seedb200_llama* m, const int64_t* input_ids, const void* inputs_embeds,
+                         const int64_t* position_ids, int B, int S, int past_len, int logits_mode, void* logits,
+                         cudaStream_t st) {
+  const seedb200_llama_config& c = m->cfg;
+  const int h = c.hidden, H = c.heads, D = c.head_dim, ffn = c.ffn, V = c.vocab, ct = c.gemm_ctas;
+  const int T = B * S;
+  if (input_ids)
+    SB_PROPAGATE(embedding(m->embed, h, input_ids, T, h, m->x, h, V, st));
+  else
+    SB_CHECK_CUDA(cudaMemcpyAsync(m->x, inputs_embeds, (size_t)T * h * 2, cudaMemcpyDeviceToDevice, st));
+  const float scale = 1.0f / sqrtf((float)D);   // xformers default scale
+  const int kv_len = past_len + S;
+  for (int l = 0; l < c.layers; ++l) {
+    const LlamaLayerW& L = m->layers[l];
+    SB_PROPAGATE(rmsnorm(m->x, h, L.in_ln, m->nb, h, T, h, c.rms_eps, st));
+    SB_PROPAGATE(lin(st, ct, T, 3 * h, h, m->nb, L.qkv_w, m->qkv, 3 * h, nullptr, 0));
+    // qkv rows are [q | k | v] per token, each [H, D]
+    SB_PROPAGATE(rope_kv_append_tables(m->qkv, position_ids, B, S, H, D, past_len, c.max_seq, m->max_pos, m->cos_t,
+                                       m->sin_t, m->q, L.k_cache, L.v_cache, st));
+    if (S == 1) {
+      SB_PROPAGATE(decode_attention(m->q, L.k_cache, L.v_cache, m->att, B, H, D, kv_len, c.max_seq, scale, m->da_ws, st));
+    } else {
+      seedb200_attn_desc a;
+      memset(&a, 0, sizeof(a));
+      a.q = m->q; a.k = L.k_cache; a.v = L.v_cache; a.o = m->att;
+      a.q_bs = (int64_t)S * h; a.q_hs = D; a.q_ts = h;
+      a.k_bs = (int64_t)H * c.max_seq * D; a.k_hs = (int64_t)c.max_seq * D; a.k_ts = D;
+      a.v_bs = a.k_bs; a.v_hs = a.k_hs; a.v_ts = a.k_ts;
+      a.o_bs = (int64_t)S * h; a.o_hs = D; a.o_ts = h;
+      a.batch = B; a.heads = H; a.nq = S; a.nk = kv_len; a.head_dim = D; a.causal = 1; a.scale = scale;
+      SB_PROPAGATE(attention(a, st));
+    }
+    SB_PROPAGATE(lin(st, ct, T, h, h, m->att, L.o_w, m->x, h, m->x, 0));
+    SB_PROPAGATE(rmsnorm(m->x, h, L.post_ln, m->nb, h, T, h, c.rms_eps, st));
+    SB_PROPAGATE(lin(st, ct, T, 2 * ffn, h, m->nb, L.gu_w, m->gu, ffn, nullptr, 1));
+    SB_PROPAGATE(lin(st, ct, T, h, ffn, m->gu, L.down_w, m->x, h, m->x, 0));
+  }
+  SB_PROPAGATE(rmsnorm(m->x, h, m->norm_w, m->hn, h, T, h, c.rms_eps, st));
+  m->last_T = T;
+  if (logits == nullptr) return 0;
+  if (logits_mode == 0) {
+    SB_PROPAGATE(lin(st, ct, T, V, h, m->hn, m->lm_head, logits, V, nullptr, 0));
+  } else {
+    const __half* src = m->hn;
+    if (S > 1) {   // gather the last position of every sequence
+      SB_CHECK_CUDA(cudaMemcpy2DAsync(m->last, (size_t)h * 2, m->hn + (size_t)(S - 1) * h, (size_t)S * h * 2,
+                                      (size_t)h * 2, B, cudaMemcpyDeviceToDevice, st));
+      src = m->last;
+    }
+    SB_PROPAGATE(lin(st, ct, B, V, h, src, m->lm_head, logits, V, nullptr, 0));
+  }
+  return 0;
+}
+
+}  // namespace sb
+
+extern "C" {
+
+int seedb200_llama_create(const seedb200_llama_config* cfg, const seedb200_tensor* weights, int n_weights,
+                          seedb200_llama** out) {
+  if (!cfg || !weights || !out) {
+    sb::set_error("llama_create: null argument");
+    return SEEDB200_ERR_INVALID;
+  }
+  SB_REQUIRE(cfg->head_dim == 128, "llama_create: head_dim must be 128 (got %d)", cfg->head_dim);
+  SB_REQUIRE(cfg->hidden == cfg->heads * cfg->head_dim, "llama_create: hidden != heads * head_dim");
+  SB_REQUIRE(cfg->ffn % 128 == 0, "llama_create: ffn %d must be a multiple of 128", cfg->ffn);
+  SB_REQUIRE(cfg->hidden % 8 == 0 && cfg->layers >= 0 && cfg->vocab > 0, "llama_create: bad dims");
+  SB_REQUIRE(cfg->max_batch >= 1 && cfg->max_seq >= 1, "llama_create: bad cache size");
+  seedb200_llama* m = new seedb200_llama();
+  m->cfg = *cfg;
+  if (m->cfg.rope_base <= 0.0f) m->cfg.rope_base = 10000.0f;
+  if (m->cfg.rms_eps <= 0.0f) m->cfg.rms_eps = 1e-6f;
+  m->last_T = 0;
+  for (int i = 0; i < n_weights; ++i) m->w[std::string(weights[i].name)] = weights[i];
+  int s = sb::llama_build(m);
+  if (s != 0) {
+    seedb200_llama_destroy(m);
+    return s;
+  }
+  m->w.clear();
+  *out = m;
+  return 0;
+}
+
+void seedb200_llama_destroy(seedb200_llama* llm) {
+  if (!llm) return;
+  for (void* p : llm->owned) cudaFree(p);
+  delete llm;
+}
+
+int seedb200_llama_forward(seedb200_llama* llm, const int64_t* input_ids, const void* inputs_embeds,
+                           const int64_t* position_ids, int B, int S, int past_len, int logits_mode, void* logits_out,
+                           void* stream) {
+  SB_REQUIRE(llm != nullptr, "llama_forward: null handle");
+  SB_REQUIRE((input_ids != nullptr) != (inputs_embeds != nullptr),
+             "llama_forward: specify exactly one of input_ids / inputs_embeds (llama_xformer.py:516-523)");
+  SB_REQUIRE(B >= 1 && B <= llm->cfg.max_batch, "llama_forward: batch %d outside [1,%d]", B, llm->cfg.max_batch);
+  SB_REQUIRE(S >= 1 && past_len >= 0 && past_len + S <= llm->cfg.max_seq,
+             "llama_forward: past_len %d + S %d exceeds max_seq %d", past_len, S, llm->cfg.max_seq);
+  SB_REQUIRE(logits_mode == 0 || logits_mode == 1, "llama_forward: logits_mode must be 0 or 1");
+  return sb::llama_forward(llm, input_ids, inputs_embeds, position_ids, B, S, past_len, logits_mode, logits_out,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int seedb200_llama_kv_ptrs(seedb200_llama* llm, int layer, void** k, void** v) {
+  SB_REQUIRE(llm && k && v && layer >= 0 && layer < (int)llm->layers.size(), "llama_kv_ptrs: bad arguments");
+  *k = llm->layers[layer].k_cache;
+  *v = llm->layers[layer].v_cache;
+  return 0;
+}
+
+int seedb200_llama_kv_load(seedb200_llama* llm, int layer, const void* k, const void* v, int B, int past_len,
+                           void* stream) {
+  SB_REQUIRE(llm && k && v && layer >= 0 && layer < (int)llm->layers.size(), "llama_kv_load: bad arguments");
+  SB_REQUIRE(B >= 1 && B <= llm->cfg.max_batch && past_len >= 0 && past_len <= llm->cfg.max_seq, "llama_kv_load: bad sizes");
+  if (past_len == 0) return 0;
+  const size_t D = llm->cfg.head_dim, H = llm->cfg.heads;
+  const size_t w = (size_t)past_len * D * 2, dp = (size_t)llm->cfg.max_seq * D * 2;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // source [B,H,past,D] contiguous; destination rows of max_seq*D per (b,h); batch stride H*max_seq*D matches
+  SB_CHECK_CUDA(cudaMemcpy2DAsync(llm->layers[layer].k_cache, dp, k, w, w, (size_t)B * H, cudaMemcpyDeviceToDevice, st));
+  SB_CHECK_CUDA(cudaMemcpy2DAsync(llm->layers[layer].v_cache, dp, v, w, w, (size_t)B * H, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int64_t seedb200_llama_tap(seedb200_llama* llm, int what, void* dst, int64_t max_elems, void* stream) {
+  if (!llm || !dst || llm->last_T <= 0 || what != 0) return -1;
+  int64_t n = (int64_t)llm->last_T * llm->cfg.hidden;
+  if (n > max_elems) n = max_elems;
+  if (cudaMemcpyAsync(dst, llm->hn, (size_t)n * 2, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+    return -1;
+  return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,38 @@
+// ops.h -- internal C++ entry points of the kernels (one launch each), used by the handle-level
+// orchestration in encoder.cu / llama.cu and re-exported 1:1 through the C ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/seedb200.h"
+
+namespace sb {
+
+int gemm(const seedb200_gemm_desc& d, cudaStream_t stream);
+int attention(const seedb200_attn_desc& d, cudaStream_t stream);
+int layernorm(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy, int rows, int cols,
+              float eps, cudaStream_t stream);
+int rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int cols, float eps,
+            cudaStream_t stream);
+int patchify(const void* images, int B, void* cols, int kpad, cudaStream_t stream);
+int broadcast_rows(const void* src, int src_rows, int cols, void* dst, int64_t ldd, int64_t group_stride_rows,
+                   int groups, cudaStream_t stream);
+int embedding(const void* table, int64_t ld, const int64_t* ids, int n, int cols, void* out, int64_t ldo,
+              int64_t n_rows, cudaStream_t stream);
+int vq_argmin(const void* z, const void* codebook, int n, int n_codes, int dim, int mode, int64_t* ids,
+              cudaStream_t stream);
+int rope_kv_append_tables(const void* qkv, const int64_t* positions, int B, int S, int H, int D, int past_len,
+                          int max_seq, int max_pos, const void* cos_t, const void* sin_t, void* q_out,
+                          void* k_cache, void* v_cache, cudaStream_t stream);
+int build_rope_tables(void* cos_t, void* sin_t, int max_pos, int D, float base, cudaStream_t stream);
+int get_rope_tables(int D, float base, int min_pos, const void** cos_t, const void** sin_t, int* max_pos,
+                    cudaStream_t stream);
+// elementwise helpers (misc.cu)
+int add_rows(const void* a, const void* b, void* out, int rows, int cols, int b_rows, cudaStream_t stream);
+int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* residual, int M, int N, int K, int mode,
+         cudaStream_t stream);
+int decode_attention(const void* q, const void* k_cache, const void* v_cache, void* out, int B, int H, int D,
+                     int kv_len, int max_seq, float scale, void* workspace, cudaStream_t stream);
+
+}  // namespace sb

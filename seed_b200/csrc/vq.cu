@@ -1,0 +1,132 @@
+// vq.cu -- VectorQuantizer2.forward nearest-neighbour search (qformer_quantizer.py:94-98):
+//     d = sum(z^2, dim=1, keepdim) + sum(e^2, dim=1) - 2 * einsum('bd,dn->bn', z, e^T);  ids = argmin(d, dim=1)
+//
+// Integer output => the arithmetic is pinned exactly (oracle/vq_oracle.c restates it in C and the parity
+// tests are bit-exact against that):
+//   * dot(z, e_j): ONE fp32 fma chain over d = 0..31 in index order (products of two fp16 values are exact
+//     in fp32, so only the accumulation order matters -- tensor cores would make it implementation
+//     defined, which is why this kernel stays on the CUDA cores; it is 0.003% of the encode FLOPs);
+//   * |z|^2, |e_j|^2: fp32 sums in index order; in FP16 mode each square is first rounded to fp16
+//     (torch materialises z**2 as an fp16 tensor) and the sum is rounded to fp16;
+//   * FP16 mode (the reference's fp16 GPU path): C16 = fp16(dot); t = fp16(A16 + B16_j);
+//     d = fp16(t - fp16(2*C16));  FP32 mode: d = (A + B_j) - 2*C in fp32, evaluated in that order;
+//   * argmin: smallest d, ties -> lowest index (torch.argmin), NaN never produced by finite inputs.
+//
+// Mapping: a CTA owns 32 z rows (lane <-> row, the row lives in 32 fp32 registers); its 8 warps split the
+// codebook into 8 contiguous slices read through the read-only path (all lanes read the same code ->
+// one broadcast transaction per 16 bytes); partial (d, id) pairs are merged in slice order.
+#include "common.cuh"
+
+namespace sb {
+
+constexpr int VQ_DIM = 32;
+constexpr int VQ_WARPS = 8;
+
+__device__ __forceinline__ float round16(float x) { return __half2float(__float2half_rn(x)); }
+
+template <int MODE>
+__global__ void __launch_bounds__(VQ_WARPS * 32)
+vq_argmin_kernel(const __half* __restrict__ z, const __half* __restrict__ codebook, int n, int n_codes,
+                 long long* __restrict__ ids) {
+  __shared__ float s_d[VQ_WARPS][32];
+  __shared__ int s_i[VQ_WARPS][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 32 + lane;
+  const int rrow = row < n ? row : n - 1;
+
+  float zr[VQ_DIM];
+  {
+    const uint4* zp = reinterpret_cast<const uint4*>(z + (long long)rrow * VQ_DIM);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 raw = zp[q];
+      const __half* h = reinterpret_cast<const __half*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) zr[q * 8 + j] = __half2float(h[j]);
+    }
+  }
+  float A = 0.0f;
+#pragma unroll
+  for (int d = 0; d < VQ_DIM; ++d) {
+    float sq = __fmul_rn(zr[d], zr[d]);          // intrinsics: never contracted into an fma
+    if (MODE == SEEDB200_VQ_FP16) sq = round16(sq);
+    A = __fadd_rn(A, sq);
+  }
+  if (MODE == SEEDB200_VQ_FP16) A = round16(A);
+
+  const int per_warp = (n_codes + VQ_WARPS - 1) / VQ_WARPS;
+  const int c_begin = warp * per_warp;
+  const int c_end = min(n_codes, c_begin + per_warp);
+  float best = INFINITY;
+  int best_i = 0x7fffffff;
+  for (int c = c_begin; c < c_end; ++c) {
+    const uint4* ep = reinterpret_cast<const uint4*>(codebook + (long long)c * VQ_DIM);
+    float e[VQ_DIM];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 raw = __ldg(ep + q);
+      const __half* h = reinterpret_cast<const __half*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) e[q * 8 + j] = __half2float(h[j]);
+    }
+    float Bn = 0.0f, C = 0.0f;
+#pragma unroll
+    for (int d = 0; d < VQ_DIM; ++d) {
+      float sq = __fmul_rn(e[d], e[d]);
+      if (MODE == SEEDB200_VQ_FP16) sq = round16(sq);
+      Bn = __fadd_rn(Bn, sq);
+      C = __fmaf_rn(zr[d], e[d], C);
+    }
+    float dist;
+    if (MODE == SEEDB200_VQ_FP16) {
+      Bn = round16(Bn);
+      const float C16 = round16(C);
+      const float t = round16(__fadd_rn(A, Bn));
+      dist = round16(__fsub_rn(t, round16(__fmul_rn(2.0f, C16))));
+    } else {
+      const float t = __fadd_rn(A, Bn);
+      dist = __fsub_rn(t, __fmul_rn(2.0f, C));
+    }
+    if (dist < best) { best = dist; best_i = c; }   // strict <: first (lowest) index wins ties
+  }
+  s_d[warp][lane] = best;
+  s_i[warp][lane] = best_i;
+  __syncthreads();
+  if (warp == 0 && row < n) {
+    float bd = s_d[0][lane];
+    int bi = s_i[0][lane];
+#pragma unroll
+    for (int w = 1; w < VQ_WARPS; ++w) {
+      const float dd = s_d[w][lane];
+      if (dd < bd) { bd = dd; bi = s_i[w][lane]; }   // slices are in ascending id order
+    }
+    if (bi == 0x7fffffff) bi = 0;                    // all distances NaN/inf: torch.argmin returns 0 for all-inf
+    ids[row] = (long long)bi;
+  }
+}
+
+int vq_argmin(const void* z, const void* codebook, int n, int n_codes, int dim, int mode, int64_t* ids,
+              cudaStream_t stream) {
+  SB_REQUIRE(z && codebook && ids, "vq_argmin: null operand");
+  SB_REQUIRE(dim == VQ_DIM, "vq_argmin: dim=%d unsupported (codebook_embed_dim is 32)", dim);
+  SB_REQUIRE(n > 0 && n_codes > 0, "vq_argmin: empty problem");
+  SB_REQUIRE(mode == SEEDB200_VQ_FP16 || mode == SEEDB200_VQ_FP32, "vq_argmin: unknown mode %d", mode);
+  const int blocks = (n + 31) / 32;
+  if (mode == SEEDB200_VQ_FP16)
+    vq_argmin_kernel<SEEDB200_VQ_FP16><<<blocks, VQ_WARPS * 32, 0, stream>>>(
+        static_cast<const __half*>(z), static_cast<const __half*>(codebook), n, n_codes,
+        reinterpret_cast<long long*>(ids));
+  else
+    vq_argmin_kernel<SEEDB200_VQ_FP32><<<blocks, VQ_WARPS * 32, 0, stream>>>(
+        static_cast<const __half*>(z), static_cast<const __half*>(codebook), n, n_codes,
+        reinterpret_cast<long long*>(ids));
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace sb
+
+extern "C" int seedb200_vq_argmin(const void* z, const void* codebook, int n, int n_codes, int dim, int mode,
+                                  int64_t* ids, void* stream) {
+  return sb::vq_argmin(z, codebook, n, n_codes, dim, mode, ids, static_cast<cudaStream_t>(stream));
+}

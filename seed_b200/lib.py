@@ -1,0 +1,420 @@
+"""ctypes binding of libseedb200.so (the C ABI declared in include/seedb200.h).
+
+This is the binding a reference maintainer would add under models/ (see INTEGRATION.md): tensors are
+passed as raw device pointers (`tensor.data_ptr()`) plus the current CUDA stream.  There is NO CPU or
+PyTorch fallback: if the library is missing, cannot be loaded, or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libseedb200.so")
+
+ACT_NONE, ACT_GELU, ACT_TANH, ACT_RELU = 0, 1, 2, 3
+VQ_FP16, VQ_FP32 = 0, 1
+
+# every symbol include/seedb200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "seedb200_version", "seedb200_last_error", "seedb200_launch_count", "seedb200_reset_launch_count",
+    "seedb200_gemm", "seedb200_layernorm", "seedb200_rmsnorm", "seedb200_attention", "seedb200_vq_argmin",
+    "seedb200_patchify", "seedb200_rope_kv_append", "seedb200_embedding",
+    "seedb200_encoder_create", "seedb200_encoder_destroy", "seedb200_encoder_encode",
+    "seedb200_encoder_encode_host", "seedb200_encoder_detokenize", "seedb200_encoder_tap",
+    "seedb200_llama_create", "seedb200_llama_destroy", "seedb200_llama_forward", "seedb200_llama_kv_ptrs",
+    "seedb200_llama_kv_load", "seedb200_llama_tap",
+]
+
+
+class Tensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("dtype", C.c_int32), ("ndim", C.c_int32),
+                ("shape", C.c_int64 * 4)]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+                ("A", C.c_void_p), ("lda", C.c_int64),
+                ("W", C.c_void_p), ("ldw", C.c_int64),
+                ("out", C.c_void_p), ("ldo", C.c_int64),
+                ("bias", C.c_void_p),
+                ("residual", C.c_void_p), ("ldr", C.c_int64),
+                ("act", C.c_int32), ("mode", C.c_int32),
+                ("row_group", C.c_int32), ("row_stride", C.c_int32), ("row_offset", C.c_int32),
+                ("res_mod", C.c_int32), ("res_offset", C.c_int32),
+                ("bn", C.c_int32), ("ctas", C.c_int32)]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
+                ("q_bs", C.c_int64), ("q_hs", C.c_int64), ("q_ts", C.c_int64),
+                ("k_bs", C.c_int64), ("k_hs", C.c_int64), ("k_ts", C.c_int64),
+                ("v_bs", C.c_int64), ("v_hs", C.c_int64), ("v_ts", C.c_int64),
+                ("o_bs", C.c_int64), ("o_hs", C.c_int64), ("o_ts", C.c_int64),
+                ("batch", C.c_int32), ("heads", C.c_int32), ("nq", C.c_int32), ("nk", C.c_int32),
+                ("head_dim", C.c_int32), ("causal", C.c_int32), ("scale", C.c_float)]
+
+
+class EncoderConfig(C.Structure):
+    _fields_ = [("vit_depth", C.c_int32), ("qformer_layers", C.c_int32), ("detok_depth", C.c_int32),
+                ("n_codes", C.c_int32), ("max_batch", C.c_int32), ("vq_mode", C.c_int32),
+                ("gemm_ctas", C.c_int32)]
+
+
+class LlamaConfig(C.Structure):
+    _fields_ = [("hidden", C.c_int32), ("layers", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
+                ("ffn", C.c_int32), ("vocab", C.c_int32), ("max_batch", C.c_int32), ("max_seq", C.c_int32),
+                ("rms_eps", C.c_float), ("rope_base", C.c_float), ("gemm_ctas", C.c_int32)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m seed_b200.build` (needs nvcc, sm_100a). "
+            "seed_b200 has no CPU or PyTorch fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    lib.seedb200_version.restype = C.c_int
+    lib.seedb200_last_error.restype = C.c_char_p
+    lib.seedb200_launch_count.restype = C.c_int64
+    lib.seedb200_reset_launch_count.restype = None
+    lib.seedb200_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
+    lib.seedb200_layernorm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_int, C.c_int, C.c_float, C.c_void_p]
+    lib.seedb200_rmsnorm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                     C.c_float, C.c_void_p]
+    lib.seedb200_attention.argtypes = [C.POINTER(AttnDesc), C.c_void_p]
+    lib.seedb200_vq_argmin.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p]
+    lib.seedb200_patchify.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.seedb200_rope_kv_append.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.seedb200_embedding.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                       C.c_int64, C.c_void_p]
+    lib.seedb200_encoder_create.argtypes = [C.POINTER(EncoderConfig), C.POINTER(Tensor), C.c_int,
+                                            C.POINTER(C.c_void_p)]
+    lib.seedb200_encoder_destroy.argtypes = [C.c_void_p]
+    lib.seedb200_encoder_destroy.restype = None
+    lib.seedb200_encoder_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p]
+    lib.seedb200_encoder_encode_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.seedb200_encoder_detokenize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.seedb200_encoder_tap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.seedb200_encoder_tap.restype = C.c_int64
+    lib.seedb200_llama_create.argtypes = [C.POINTER(LlamaConfig), C.POINTER(Tensor), C.c_int,
+                                          C.POINTER(C.c_void_p)]
+    lib.seedb200_llama_destroy.argtypes = [C.c_void_p]
+    lib.seedb200_llama_destroy.restype = None
+    lib.seedb200_llama_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.seedb200_llama_kv_ptrs.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.seedb200_llama_kv_load.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_void_p]
+    lib.seedb200_llama_tap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.seedb200_llama_tap.restype = C.c_int64
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().seedb200_last_error()
+        raise RuntimeError(f"{what} failed (status {status}): {msg.decode() if msg else '?'}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda_f16(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor; seed_b200 has no CPU path (got device {t.device})")
+    if t.dtype != torch.float16:
+        raise RuntimeError(f"{name}: expected float16, got {t.dtype}")
+
+
+def launch_count() -> int:
+    return int(load().seedb200_launch_count())
+
+
+def reset_launch_count() -> None:
+    load().seedb200_reset_launch_count()
+
+
+# --------------------------------------------------------------------------------------------------
+# per-op wrappers (used by the tests and by ncu runs)
+# --------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+         residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, mode: int = 0,
+         bn: int = 0, ctas: int = 0, row_group: int = 0, row_stride: int = 0, row_offset: int = 0,
+         res_mod: int = 0, res_offset: int = 0) -> torch.Tensor:
+    """out = epilogue(a @ w.T); a [M,K], w [N,K] fp16 (nn.Linear layout)."""
+    _need_cuda_f16(a, "gemm.a"); _need_cuda_f16(w, "gemm.w")
+    M, K = a.shape
+    N = w.shape[0]
+    n_out = N // 2 if mode == 1 else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.float16, device=a.device)
+    d = GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.A, d.lda = a.data_ptr(), a.stride(0)
+    d.W, d.ldw = w.data_ptr(), w.stride(0)
+    d.out, d.ldo = out.data_ptr(), out.stride(0)
+    d.bias = _p(bias)
+    d.residual = _p(residual)
+    d.ldr = residual.stride(0) if residual is not None else 0
+    d.act, d.mode = act, mode
+    d.row_group, d.row_stride, d.row_offset = row_group, row_stride, row_offset
+    d.res_mod, d.res_offset = res_mod, res_offset
+    d.bn, d.ctas = bn, ctas
+    check(load().seedb200_gemm(C.byref(d), stream_ptr()), "seedb200_gemm")
+    return out
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float) -> torch.Tensor:
+    _need_cuda_f16(x, "layernorm.x")
+    y = torch.empty_like(x)
+    rows, cols = x.shape
+    check(load().seedb200_layernorm(x.data_ptr(), x.stride(0), w.data_ptr(), b.data_ptr(), y.data_ptr(),
+                                    y.stride(0), rows, cols, eps, stream_ptr()), "seedb200_layernorm")
+    return y
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
+    _need_cuda_f16(x, "rmsnorm.x")
+    y = torch.empty_like(x)
+    rows, cols = x.shape
+    check(load().seedb200_rmsnorm(x.data_ptr(), x.stride(0), w.data_ptr(), y.data_ptr(), y.stride(0), rows, cols,
+                                  eps, stream_ptr()), "seedb200_rmsnorm")
+    return y
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, causal: bool = False) -> torch.Tensor:
+    """q [B,H,Nq,D], k/v [B,H,Nk,D] (any strides with contiguous D) -> o [B,Nq,H,D] contiguous."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _need_cuda_f16(t, "attention." + n)
+        if t.stride(3) != 1:
+            raise RuntimeError("attention: head_dim must be contiguous")
+    B, H, Nq, D = q.shape
+    Nk = k.shape[2]
+    o = torch.empty((B, Nq, H, D), dtype=torch.float16, device=q.device)
+    d = AttnDesc()
+    d.q, d.k, d.v, d.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+    d.q_bs, d.q_hs, d.q_ts = q.stride(0), q.stride(1), q.stride(2)
+    d.k_bs, d.k_hs, d.k_ts = k.stride(0), k.stride(1), k.stride(2)
+    d.v_bs, d.v_hs, d.v_ts = v.stride(0), v.stride(1), v.stride(2)
+    d.o_bs, d.o_hs, d.o_ts = o.stride(0), o.stride(2), o.stride(1)
+    d.batch, d.heads, d.nq, d.nk, d.head_dim = B, H, Nq, Nk, D
+    d.causal, d.scale = int(causal), scale
+    check(load().seedb200_attention(C.byref(d), stream_ptr()), "seedb200_attention")
+    return o
+
+
+def vq_argmin(z: torch.Tensor, codebook: torch.Tensor, mode: int = VQ_FP16) -> torch.Tensor:
+    _need_cuda_f16(z, "vq.z"); _need_cuda_f16(codebook, "vq.codebook")
+    z2 = z.reshape(-1, z.shape[-1]).contiguous()
+    ids = torch.empty((z2.shape[0],), dtype=torch.int64, device=z.device)
+    check(load().seedb200_vq_argmin(z2.data_ptr(), codebook.data_ptr(), z2.shape[0], codebook.shape[0],
+                                    z2.shape[1], mode, ids.data_ptr(), stream_ptr()), "seedb200_vq_argmin")
+    return ids
+
+
+def patchify(images: torch.Tensor, kpad: int = 592) -> torch.Tensor:
+    _need_cuda_f16(images, "patchify.images")
+    B = images.shape[0]
+    cols = torch.empty((B * 256, kpad), dtype=torch.float16, device=images.device)
+    check(load().seedb200_patchify(images.contiguous().data_ptr(), B, cols.data_ptr(), kpad, stream_ptr()),
+          "seedb200_patchify")
+    return cols
+
+
+def rope_kv_append(qkv: torch.Tensor, positions: Optional[torch.Tensor], B: int, S: int, H: int, D: int,
+                   past_len: int, k_cache: torch.Tensor, v_cache: torch.Tensor) -> torch.Tensor:
+    _need_cuda_f16(qkv, "rope.qkv")
+    max_seq = k_cache.shape[2]
+    q_out = torch.empty((B * S, H * D), dtype=torch.float16, device=qkv.device)
+    check(load().seedb200_rope_kv_append(qkv.data_ptr(), _p(positions), B, S, H, D, past_len, max_seq,
+                                         q_out.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), stream_ptr()),
+          "seedb200_rope_kv_append")
+    return q_out
+
+
+def embedding(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    _need_cuda_f16(table, "embedding.table")
+    flat = ids.reshape(-1).contiguous()
+    out = torch.empty((flat.numel(), table.shape[1]), dtype=torch.float16, device=table.device)
+    check(load().seedb200_embedding(table.data_ptr(), table.stride(0), flat.data_ptr(), flat.numel(),
+                                    table.shape[1], out.data_ptr(), out.stride(0), table.shape[0], stream_ptr()),
+          "seedb200_embedding")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# handles
+# --------------------------------------------------------------------------------------------------
+def _tensor_array(weights: Dict[str, torch.Tensor]):
+    arr = (Tensor * len(weights))()
+    keep = []
+    for i, (name, t) in enumerate(weights.items()):
+        if not t.is_cuda or t.dtype != torch.float16 or not t.is_contiguous():
+            raise RuntimeError(f"weight {name}: expected contiguous CUDA float16, got {t.dtype} on {t.device}")
+        b = name.encode()
+        keep.append(b)
+        arr[i].name = b
+        arr[i].data = t.data_ptr()
+        arr[i].dtype = 0
+        arr[i].ndim = min(t.dim(), 4)
+        shp = list(t.shape)
+        if len(shp) > 4:   # fold leading dims (conv weight [1408,3,14,14] has exactly 4)
+            lead = 1
+            for s in shp[:-3]:
+                lead *= s
+            shp = [lead] + shp[-3:]
+        for j in range(4):
+            arr[i].shape[j] = shp[j] if j < len(shp) else 1
+    return arr, keep
+
+
+class Encoder:
+    """Owns a seedb200_encoder handle.  `weights` maps reference state-dict names to CUDA fp16 tensors."""
+
+    def __init__(self, weights: Dict[str, torch.Tensor], vit_depth: int = 39, qformer_layers: int = 12,
+                 detok_depth: int = 4, n_codes: int = 8192, max_batch: int = 256, vq_mode: int = VQ_FP16,
+                 gemm_ctas: int = 0):
+        lib = load()
+        self._weights = dict(weights)   # keep the borrowed tensors alive
+        arr, keep = _tensor_array(self._weights)
+        cfg = EncoderConfig(vit_depth, qformer_layers, detok_depth, n_codes, max_batch, vq_mode, gemm_ctas)
+        h = C.c_void_p()
+        check(lib.seedb200_encoder_create(C.byref(cfg), arr, len(self._weights), C.byref(h)),
+              "seedb200_encoder_create")
+        self._h = h
+        self.max_batch = max_batch
+        self.device = next(iter(self._weights.values())).device
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            load().seedb200_encoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def encode(self, images: torch.Tensor, return_z: bool = False, return_query_up: bool = False):
+        _need_cuda_f16(images, "encode.images")
+        images = images.contiguous()
+        B = images.shape[0]
+        ids = torch.empty((B, 32), dtype=torch.int64, device=images.device)
+        z = torch.empty((B * 32, 32), dtype=torch.float16, device=images.device) if return_z else None
+        qup = torch.empty((B, 32, 768), dtype=torch.float16, device=images.device) if return_query_up else None
+        check(load().seedb200_encoder_encode(self._h, images.data_ptr(), B, ids.data_ptr(), _p(z), _p(qup),
+                                             stream_ptr()), "seedb200_encoder_encode")
+        return ids, z, qup
+
+    def encode_host(self, images_pinned: torch.Tensor, ids_pinned: torch.Tensor) -> None:
+        """Host (pinned) fp16 images -> host int64 ids; copies are enqueued on the current stream."""
+        if images_pinned.is_cuda or ids_pinned.is_cuda:
+            raise RuntimeError("encode_host takes host tensors")
+        check(load().seedb200_encoder_encode_host(self._h, images_pinned.data_ptr(), images_pinned.shape[0],
+                                                  ids_pinned.data_ptr(), stream_ptr()),
+              "seedb200_encoder_encode_host")
+
+    def detokenize(self, ids: torch.Tensor) -> torch.Tensor:
+        if not ids.is_cuda or ids.dtype != torch.int64:
+            raise RuntimeError("detokenize: ids must be a CUDA int64 tensor")
+        ids = ids.reshape(-1, 32).contiguous()
+        B = ids.shape[0]
+        out = torch.empty((B, 1024), dtype=torch.float16, device=ids.device)
+        check(load().seedb200_encoder_detokenize(self._h, ids.data_ptr(), B, out.data_ptr(), stream_ptr()),
+              "seedb200_encoder_detokenize")
+        return out
+
+    def tap(self, what: int, B: int) -> torch.Tensor:
+        shape = {0: (B * 257, 1408), 1: (B * 32, 768), 2: (B * 257, 1408)}[what]
+        out = torch.empty(shape, dtype=torch.float16, device=self.device)
+        n = load().seedb200_encoder_tap(self._h, what, out.data_ptr(), out.numel(), stream_ptr())
+        if n != out.numel():
+            raise RuntimeError(f"seedb200_encoder_tap({what}) returned {n}, expected {out.numel()}")
+        return out
+
+
+class Llama:
+    """Owns a seedb200_llama handle.  `weights` uses the HF LLaMA state-dict names."""
+
+    def __init__(self, weights: Dict[str, torch.Tensor], hidden: int, layers: int, heads: int, ffn: int, vocab: int,
+                 max_batch: int = 1, max_seq: int = 4096, rms_eps: float = 1e-6, rope_base: float = 10000.0,
+                 gemm_ctas: int = 0):
+        lib = load()
+        self._weights = dict(weights)
+        arr, keep = _tensor_array(self._weights)
+        cfg = LlamaConfig(hidden, layers, heads, hidden // heads, ffn, vocab, max_batch, max_seq, rms_eps,
+                          rope_base, gemm_ctas)
+        h = C.c_void_p()
+        check(lib.seedb200_llama_create(C.byref(cfg), arr, len(self._weights), C.byref(h)), "seedb200_llama_create")
+        self._h = h
+        self.hidden, self.layers, self.heads, self.head_dim = hidden, layers, heads, hidden // heads
+        self.ffn, self.vocab, self.max_batch, self.max_seq = ffn, vocab, max_batch, max_seq
+        self.device = next(iter(self._weights.values())).device
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            load().seedb200_llama_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def forward(self, input_ids: Optional[torch.Tensor] = None, inputs_embeds: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.Tensor] = None, past_len: int = 0, last_only: bool = False,
+                want_logits: bool = True) -> Optional[torch.Tensor]:
+        if input_ids is not None:
+            B, S = input_ids.shape
+            input_ids = input_ids.contiguous()
+        else:
+            B, S = inputs_embeds.shape[:2]
+            inputs_embeds = inputs_embeds.contiguous()
+        if position_ids is not None:
+            position_ids = position_ids.reshape(-1, S).expand(B, S).contiguous().long()
+        logits = None
+        if want_logits:
+            logits = torch.empty((B, 1 if last_only else S, self.vocab), dtype=torch.float16, device=self.device)
+        check(load().seedb200_llama_forward(self._h, _p(input_ids), _p(inputs_embeds), _p(position_ids), B, S,
+                                            past_len, 1 if last_only else 0, _p(logits), stream_ptr()),
+              "seedb200_llama_forward")
+        return logits
+
+    def kv_views(self, layer: int):
+        k, v = C.c_void_p(), C.c_void_p()
+        check(load().seedb200_llama_kv_ptrs(self._h, layer, C.byref(k), C.byref(v)), "seedb200_llama_kv_ptrs")
+        return k.value, v.value
+
+    def kv_load(self, layer: int, k: torch.Tensor, v: torch.Tensor) -> None:
+        B, H, P, D = k.shape
+        check(load().seedb200_llama_kv_load(self._h, layer, k.contiguous().data_ptr(), v.contiguous().data_ptr(), B,
+                                            P, stream_ptr()), "seedb200_llama_kv_load")
+
+    def tap_hidden(self, T: int) -> torch.Tensor:
+        out = torch.empty((T, self.hidden), dtype=torch.float16, device=self.device)
+        n = load().seedb200_llama_tap(self._h, 0, out.data_ptr(), out.numel(), stream_ptr())
+        if n != out.numel():
+            raise RuntimeError(f"seedb200_llama_tap returned {n}, expected {out.numel()}")
+        return out

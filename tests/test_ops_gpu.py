@@ -1,0 +1,302 @@
+"""GPU parity tests of every per-op C-ABI entry point against the oracle restatements (oracle/ops_ref.py,
+oracle/vq_oracle.c).  Integer outputs are bit-exact; fp16 outputs are compared with the tolerance written
+next to each test (a few fp16 ulps: the accumulation order inside a tensor-core tile is not the oracle's)."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops_ref as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def max_ulp_err(a, b):
+    """max |a-b| in units of the fp16 spacing at |b| (floor at 2^-14)."""
+    a, b = a.float(), b.float()
+    ulp = torch.pow(2.0, torch.floor(torch.log2(b.abs().clamp_min(2.0 ** -14))) - 10)
+    return ((a - b).abs() / ulp).max().item()
+
+
+def rand16(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.float16).to(DEV)
+
+
+# ----------------------------------------------------------------------------------------------
+# GEMM (tcgen05): every tile shape x cta_group, tails in M/N/K, persistent multi-tile schedules
+# ----------------------------------------------------------------------------------------------
+GEMM_SHAPES = [
+    # M, N, K, bn, ctas
+    (128, 256, 64, 256, 1),       # one tile, one k-block
+    (128, 256, 256, 256, 1),      # k loop within one pipeline round
+    (300, 256, 1408, 256, 1),     # M tail, pipeline wraps (22 k-blocks)
+    (512, 512, 592, 256, 1),      # K tail (592 = 9*64 + 16)
+    (257, 1408, 1408, 176, 1),    # BN=176 (proj / fc2)
+    (257, 4224, 1408, 192, 1),    # BN=192 (ViT qkv)
+    (1000, 768, 768, 128, 1),
+    (96, 96, 768, 64, 1),         # N tail inside a 64-wide tile (scalar store path)
+    (64, 32, 768, 32, 1),         # z projection
+    (4096, 1024, 256, 32, 1),     # 1024 tiles over 148 CTAs: >= 6 accumulator hand-offs per CTA
+    (2048, 40194, 512, 256, 1),   # lm_head-like: odd ldo -> unaligned rows, N tail
+    (512, 512, 1408, 256, 2),     # cta_group::2
+    (300, 256, 592, 256, 2),
+    (1028, 4224, 1408, 192, 2),
+    (1028, 1408, 1408, 176, 2),
+    (1000, 768, 768, 128, 2),
+    (4096, 1024, 256, 64, 2),
+]
+
+
+@pytest.mark.parametrize("M,N,K,bn,ctas", GEMM_SHAPES)
+def test_gemm_plain(lib, M, N, K, bn, ctas):
+    a = rand16(M, K, seed=1)
+    w = rand16(N, K, scale=K ** -0.5, seed=2)
+    out = lib.gemm(a, w, bn=bn, ctas=ctas)
+    torch.cuda.synchronize()
+    ref = R.linear_ref(a, w)
+    # tolerance: 2 fp16 ulps of the output (fp32 accumulation order differs from the oracle's)
+    assert rel_err(out, ref) < 1e-3
+    assert max_ulp_err(out, ref) <= 2.0, f"max ulp {max_ulp_err(out, ref)}"
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+@pytest.mark.parametrize("ctas", [1, 2])
+def test_gemm_bias_act_residual(lib, act, ctas):
+    M, N, K = 515, 768, 320
+    a = rand16(M, K, seed=3)
+    w = rand16(N, K, scale=K ** -0.5, seed=4)
+    bias = rand16(N, scale=0.5, seed=5)
+    res = rand16(M, N, seed=6)
+    out = lib.gemm(a, w, bias=bias, act=act, residual=res, ctas=ctas)
+    torch.cuda.synchronize()
+    ref = R.linear_ref(a, w, bias, act, res)
+    # activation evaluated on an fp16-rounded pre-activation: a 1-ulp pre-activation difference can move
+    # the result by ~1 ulp more -> 4 ulps, plus an absolute floor for outputs near zero
+    diff = (out.float() - ref.float()).abs()
+    tol = 4 * torch.pow(2.0, torch.floor(torch.log2(ref.float().abs().clamp_min(2.0 ** -6))) - 10)
+    assert (diff <= tol).all(), f"max diff {diff.max().item()}"
+
+
+def test_gemm_inplace_residual(lib):
+    M, N, K = 514, 1408, 1408
+    a = rand16(M, K, seed=7)
+    w = rand16(N, K, scale=K ** -0.5, seed=8)
+    bias = rand16(N, scale=0.1, seed=9)
+    x = rand16(M, N, seed=10)
+    ref = R.linear_ref(a, w, bias, 0, x)
+    out = lib.gemm(a, w, bias=bias, residual=x, out=x)
+    torch.cuda.synchronize()
+    assert out.data_ptr() == x.data_ptr()
+    assert max_ulp_err(out, ref) <= 2.0
+
+
+def test_gemm_row_remap_patch_embed(lib):
+    """patch rows land behind each image's cls row and pick up pos_embed[1 + patch] (eva_vit.py:373-377)."""
+    B = 3
+    a = rand16(B * 256, 592, seed=11)
+    a[:, 588:] = 0
+    w = rand16(1408, 592, scale=588 ** -0.5, seed=12)
+    bias = rand16(1408, scale=0.1, seed=13)
+    pos = rand16(257, 1408, scale=0.1, seed=14)
+    x = torch.zeros((B * 257, 1408), dtype=torch.float16, device=DEV)
+    lib.gemm(a, w, bias=bias, residual=pos, out=x, row_group=256, row_stride=257, row_offset=1, res_mod=256,
+             res_offset=1)
+    torch.cuda.synchronize()
+    y = R.linear_ref(a, w, bias).float().reshape(B, 256, 1408)
+    ref = R.r16(y + pos[1:].float()[None])
+    got = x.reshape(B, 257, 1408)
+    assert (got[:, 0] == 0).all()                      # cls rows untouched
+    assert max_ulp_err(got[:, 1:], ref) <= 2.0
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("M,ffn,h", [(300, 1408, 512), (2048, 11008, 256)])
+def test_gemm_silu_gate(lib, M, ffn, h, ctas):
+    a = rand16(M, h, seed=15)
+    wg = rand16(ffn, h, scale=h ** -0.5, seed=16)
+    wu = rand16(ffn, h, scale=h ** -0.5, seed=17)
+    wgu = R.interleave_gate_up(wg, wu)
+    out = lib.gemm(a, wgu, mode=1, ctas=ctas)
+    torch.cuda.synchronize()
+    ref = R.silu_gate_ref(a, wg, wu)
+    assert out.shape == (M, ffn)
+    diff = (out.float() - ref.float()).abs()
+    tol = 4 * torch.pow(2.0, torch.floor(torch.log2(ref.float().abs().clamp_min(2.0 ** -6))) - 10)
+    assert (diff <= tol).all(), f"max diff {diff.max().item()}"
+
+
+def test_gemm_rejects_bad_args(lib):
+    a = rand16(64, 100, seed=1)          # K not a multiple of 8
+    w = rand16(32, 100, seed=2)
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        lib.gemm(a, w)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        lib.gemm(a.cpu(), w.cpu())
+
+
+# ----------------------------------------------------------------------------------------------
+# norms
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,cols,eps", [(257, 1408, 1e-6), (1028, 1408, 1e-5), (64, 768, 1e-12), (1, 768, 1e-6),
+                                           (33, 256, 1e-6), (7, 4096, 1e-5)])
+def test_layernorm(lib, rows, cols, eps):
+    x = rand16(rows, cols, scale=2.0, seed=20) + 0.5
+    w = (1.0 + 0.1 * torch.randn(cols)).to(torch.float16).to(DEV)
+    b = (0.1 * torch.randn(cols)).to(torch.float16).to(DEV)
+    y = lib.layernorm(x, w, b, eps)
+    torch.cuda.synchronize()
+    ref = R.layernorm_ref(x, w, b, eps)
+    # fp32 statistics on both sides: 1 fp16 ulp (+ floor near zero)
+    diff = (y.float() - ref.float()).abs()
+    tol = 1.0 * torch.pow(2.0, torch.floor(torch.log2(ref.float().abs().clamp_min(2.0 ** -8))) - 10)
+    assert (diff <= tol).all(), f"max diff {diff.max().item()}"
+
+
+@pytest.mark.parametrize("rows,cols", [(2048, 4096), (5, 5120), (1, 4096), (300, 512)])
+def test_rmsnorm(lib, rows, cols):
+    x = rand16(rows, cols, scale=1.5, seed=21)
+    w = (1.0 + 0.1 * torch.randn(cols)).to(torch.float16).to(DEV)
+    y = lib.rmsnorm(x, w, 1e-6)
+    torch.cuda.synchronize()
+    ref = R.rmsnorm_ref(x, w, 1e-6)
+    diff = (y.float() - ref.float()).abs()
+    tol = 2.0 * torch.pow(2.0, torch.floor(torch.log2(ref.float().abs().clamp_min(2.0 ** -8))) - 10)
+    assert (diff <= tol).all(), f"max diff {diff.max().item()}"
+
+
+# ----------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------
+ATTN_CASES = [
+    # B, H, Nq, Nk, D, causal
+    (2, 16, 257, 257, 88, False),     # ViT-g
+    (3, 12, 32, 32, 64, True),        # Q-Former self (causal)
+    (3, 12, 32, 257, 64, False),      # Q-Former cross
+    (2, 12, 32, 32, 64, False),       # de-tokenizer blocks
+    (1, 4, 300, 300, 128, True),      # LLaMA prefill
+    (2, 2, 2048, 2048, 128, True),
+    (1, 2, 5, 133, 128, True),        # chunked prefill with past: bottom-right aligned causal
+    (1, 3, 1, 77, 128, False),        # single query through the prefill kernel
+    (1, 2, 100, 100, 64, False),
+]
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,D,causal", ATTN_CASES)
+def test_attention(lib, B, H, Nq, Nk, D, causal):
+    q = rand16(B, H, Nq, D, seed=30)
+    k = rand16(B, H, Nk, D, seed=31)
+    v = rand16(B, H, Nk, D, seed=32)
+    scale = D ** -0.5
+    o = lib.attention(q, k, v, scale, causal)
+    torch.cuda.synchronize()
+    ref = R.attention_ref(q, k, v, scale, causal)
+    # probabilities are rounded to fp16 before P.V (as the reference does): relative Frobenius 2e-3
+    assert rel_err(o, ref) < 2e-3, rel_err(o, ref)
+    assert (o.float() - ref.float()).abs().max().item() < 1e-2
+
+
+def test_attention_strided_qkv_layout(lib):
+    """the ViT layout: q/k/v are column slices of one [B*257, 4224] GEMM output."""
+    B, H, N, D = 2, 16, 257, 88
+    qkv = rand16(B * N, 3 * H * D, seed=33)
+    v4 = qkv.view(B, N, 3, H, D)
+    q, k, v = (v4[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    o = lib.attention(q, k, v, D ** -0.5, False)
+    torch.cuda.synchronize()
+    ref = R.attention_ref(q, k, v, D ** -0.5, False)
+    assert rel_err(o, ref) < 2e-3
+
+
+# ----------------------------------------------------------------------------------------------
+# VQ argmin: bit-exact against the C oracle, both arithmetic modes
+# ----------------------------------------------------------------------------------------------
+def _oracle_vq(z, cb, mode):
+    from seed_b200.build import ORACLE_LIB, build_oracle
+
+    if not os.path.exists(ORACLE_LIB):
+        build_oracle()
+    o = C.CDLL(ORACLE_LIB)
+    zn = z.cpu().contiguous().view(torch.int16).numpy().view(np.uint16)
+    cn = cb.cpu().contiguous().view(torch.int16).numpy().view(np.uint16)
+    ids = np.zeros(zn.shape[0], dtype=np.int64)
+    margin = np.zeros(zn.shape[0], dtype=np.float32)
+    rc = o.vq_oracle_argmin(zn.ctypes.data_as(C.c_void_p), cn.ctypes.data_as(C.c_void_p), zn.shape[0], cn.shape[0],
+                            zn.shape[1], mode, ids.ctypes.data_as(C.c_void_p), margin.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return ids, margin
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n,n_codes,scale", [(64, 8192, 0.26), (1000, 8192, 0.26), (33, 1000, 1.0), (256, 8192, 1.0 / 8192)])
+def test_vq_bit_exact_vs_c_oracle(lib, mode, n, n_codes, scale):
+    z = rand16(n, 32, scale=0.26, seed=40)
+    cb = rand16(n_codes, 32, scale=scale, seed=41)
+    if scale < 1e-3:   # the reference's default init U(+-1/8192): every distance collapses, ties everywhere
+        cb = ((torch.rand(n_codes, 32) * 2 - 1) / 8192).to(torch.float16).to(DEV)
+    ids = lib.vq_argmin(z, cb, mode)
+    torch.cuda.synchronize()
+    ref, _ = _oracle_vq(z, cb, mode)
+    assert ids.dtype == torch.int64
+    assert np.array_equal(ids.cpu().numpy(), ref)
+
+
+def test_vq_duplicate_codes_pick_lowest_index(lib):
+    z = rand16(128, 32, scale=0.3, seed=42)
+    cb = rand16(512, 32, scale=0.3, seed=43)
+    cb = torch.cat([cb, cb, cb], dim=0).contiguous()      # every code three times
+    for mode in (0, 1):
+        ids = lib.vq_argmin(z, cb, mode)
+        assert (ids < 512).all()
+
+
+# ----------------------------------------------------------------------------------------------
+# patchify, embedding, RoPE + KV append
+# ----------------------------------------------------------------------------------------------
+def test_patchify_exact(lib):
+    img = rand16(3, 3, 224, 224, seed=50)
+    cols = lib.patchify(img, 592)
+    torch.cuda.synchronize()
+    assert torch.equal(cols, R.patchify_ref(img, 592))
+
+
+def test_embedding_exact(lib):
+    table = rand16(1000, 4096, seed=51)
+    ids = torch.randint(0, 1000, (3, 77), device=DEV)
+    out = lib.embedding(table, ids)
+    torch.cuda.synchronize()
+    assert torch.equal(out, table[ids.reshape(-1)])
+
+
+@pytest.mark.parametrize("B,S,H,past", [(1, 64, 4, 0), (2, 17, 3, 5), (1, 1, 8, 300)])
+def test_rope_kv_append(lib, B, S, H, past):
+    D, max_seq = 128, 512
+    qkv = rand16(B * S, 3 * H * D, seed=52)
+    pos = (past + torch.arange(S, device=DEV))[None].expand(B, S).contiguous()
+    kc = torch.zeros((B, H, max_seq, D), dtype=torch.float16, device=DEV)
+    vc = torch.zeros_like(kc)
+    q_out = lib.rope_kv_append(qkv, pos, B, S, H, D, past, kc, vc)
+    torch.cuda.synchronize()
+    v5 = qkv.view(B, S, 3, H, D)
+    q, k, v = (v5[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    q_ref = R.rope_ref(q, pos).permute(0, 2, 1, 3).reshape(B * S, H * D)
+    k_ref = R.rope_ref(k, pos)
+    # cos/sin come from the device's cosf/sinf instead of torch's: allow 2 fp16 ulps
+    assert (q_out.float() - q_ref.float()).abs().max().item() < 1e-2
+    assert max_ulp_err(q_out, q_ref) <= 4.0 or rel_err(q_out, q_ref) < 1e-3
+    assert rel_err(kc[:, :, past:past + S], k_ref) < 1e-3
+    assert torch.equal(vc[:, :, past:past + S], v)
+    assert (kc[:, :, past + S:] == 0).all() and (kc[:, :, :past] == 0).all()
+    # positions=None means past_len + arange(S) (llama_xformer.py:530-539)
+    kc2 = torch.zeros_like(kc); vc2 = torch.zeros_like(vc)
+    q2 = lib.rope_kv_append(qkv, None, B, S, H, D, past, kc2, vc2)
+    assert torch.equal(q2, q_out) and torch.equal(kc2, kc)
