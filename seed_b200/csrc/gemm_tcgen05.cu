@@ -62,18 +62,30 @@ struct GemmCfg {
   static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {
-  // 0.5 x (1 + erf(x / sqrt 2)), erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, below fp16 resolution)
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  // 0.5 x (1 + erf(x / sqrt 2)) = 0.5 (x + |x| erf(|x| / sqrt 2)); erf by Abramowitz-Stegun 7.1.26
+  // (|err| < 1.5e-7, far below fp16 resolution); ~15 issue slots per element, 2 of them MUFU
+  const float ax = fabsf(x);
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  const float e = 1.0f - p * __expf(-z * z);
-  const float erfv = copysignf(e, x);
-  return 0.5f * x * (1.0f + erfv);
+  const float e = ex2_approx(ax * ax * (-0.5f * 1.4426950408889634f));   // exp(-(|x|/sqrt2)^2)
+  const float erf_abs = fmaf(-p, e, 1.0f);
+  return 0.5f * fmaf(ax, erf_abs, x);
 }
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -130,7 +142,10 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(v[j]);
-    if (p.act != SEEDB200_ACT_NONE) {
+    if (p.act == SEEDB200_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(gelu_erf(__half2float(h[j])));
+    } else if (p.act != SEEDB200_ACT_NONE) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(apply_act(__half2float(h[j]), p.act));
     }
@@ -211,7 +226,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + 8 * i, 1);
-      mbar_init(tempty_bar + 8 * i, CTAS * GEMM_EPI_THREADS);
+      mbar_init(tempty_bar + 8 * i, CTAS * (GEMM_EPI_THREADS / 32));   // one arrive per epilogue warp
     }
     fence_mbar_init();
   } else if (warp == 2) {
@@ -315,16 +330,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if constexpr (MODE == 1) tmem_ld16(t_acc + BN / 2 + c * 16, r1);
         tmem_ld_wait();
         if (c == c_end - 1) {
-          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+          // all TMEM reads of this accumulator stage are done (tcgen05.wait::ld is warp-collective):
+          // one lane per warp hands the stage back to the MMA warp
           tc_fence_before();
-          if constexpr (CTAS == 2) mbar_arrive_cluster(lead_tempty0 + 8 * as);
-          else mbar_arrive(tempty_bar + 8 * as);
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CTAS == 2) mbar_arrive_cluster(lead_tempty0 + 8 * as);
+            else mbar_arrive(tempty_bar + 8 * as);
+          }
         }
         const int n0 = (MODE == 1) ? nt * (BN / 2) + c * 16 : nt * BN + c * 16;
         epilogue_store16<MODE>(p, r0, r1, m, n0, n_limit);
       }
-      if (c_begin >= c_end) {   // (never for the instantiated shapes; keeps the barrier count exact)
-        tc_fence_before();
+      if (c_begin >= c_end && lane == 0) {   // (never for the instantiated shapes; keeps the barrier count exact)
         if constexpr (CTAS == 2) mbar_arrive_cluster(lead_tempty0 + 8 * as);
         else mbar_arrive(tempty_bar + 8 * as);
       }

@@ -27,6 +27,22 @@ def max_ulp_err(a, b):
     return ((a - b).abs() / ulp).max().item()
 
 
+def assert_close16(out, ref, mags=(), ulps=2.0, atol=3e-5, what=""):
+    """|out-ref| <= ulps * 2^-10 * max(|ref|, |m| for m in mags) + atol, elementwise.  `mags` lists the
+    intermediates that were rounded to fp16 on the way (a 1-ulp flip of an intermediate survives a
+    cancelling add), `atol` covers the fp32 accumulation-order noise on near-zero outputs."""
+    o, r = out.float(), ref.float()
+    mag = r.abs()
+    for m in mags:
+        mag = torch.maximum(mag, m.float().abs())
+    tol = ulps * mag * 2.0 ** -10 + atol
+    diff = (o - r).abs()
+    bad = diff > tol
+    assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} elements outside tolerance; max diff "
+                           f"{diff.max().item():.3e}, rel fro {rel_err(out, ref):.3e}, worst idx "
+                           f"{int(torch.argmax(diff - tol))}")
+
+
 def rand16(*shape, scale=1.0, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     return (torch.randn(*shape, generator=g) * scale).to(torch.float16).to(DEV)
@@ -65,8 +81,8 @@ def test_gemm_plain(lib, M, N, K, bn, ctas):
     torch.cuda.synchronize()
     ref = R.linear_ref(a, w)
     # tolerance: 2 fp16 ulps of the output (fp32 accumulation order differs from the oracle's)
-    assert rel_err(out, ref) < 1e-3
-    assert max_ulp_err(out, ref) <= 2.0, f"max ulp {max_ulp_err(out, ref)}"
+    assert rel_err(out, ref) < 1e-3, rel_err(out, ref)
+    assert_close16(out, ref, what="gemm")
 
 
 @pytest.mark.parametrize("act", [0, 1, 2, 3])
@@ -80,11 +96,10 @@ def test_gemm_bias_act_residual(lib, act, ctas):
     out = lib.gemm(a, w, bias=bias, act=act, residual=res, ctas=ctas)
     torch.cuda.synchronize()
     ref = R.linear_ref(a, w, bias, act, res)
-    # activation evaluated on an fp16-rounded pre-activation: a 1-ulp pre-activation difference can move
-    # the result by ~1 ulp more -> 4 ulps, plus an absolute floor for outputs near zero
-    diff = (out.float() - ref.float()).abs()
-    tol = 4 * torch.pow(2.0, torch.floor(torch.log2(ref.float().abs().clamp_min(2.0 ** -6))) - 10)
-    assert (diff <= tol).all(), f"max diff {diff.max().item()}"
+    pre = R.linear_ref(a, w, bias)            # fp16-rounded pre-activation
+    post = R.linear_ref(a, w, bias, act)      # fp16-rounded activation output (before the residual add)
+    # a 1-ulp flip of an fp16-rounded intermediate survives into the result: 4 ulps of the largest magnitude
+    assert_close16(out, ref, mags=(pre, post, res), ulps=4.0, what=f"gemm act={act}")
 
 
 def test_gemm_inplace_residual(lib):
@@ -97,7 +112,7 @@ def test_gemm_inplace_residual(lib):
     out = lib.gemm(a, w, bias=bias, residual=x, out=x)
     torch.cuda.synchronize()
     assert out.data_ptr() == x.data_ptr()
-    assert max_ulp_err(out, ref) <= 2.0
+    assert_close16(out, ref, mags=(R.linear_ref(a, w, bias),), ulps=3.0, what="inplace residual")
 
 
 def test_gemm_row_remap_patch_embed(lib):
@@ -116,7 +131,7 @@ def test_gemm_row_remap_patch_embed(lib):
     ref = R.r16(y + pos[1:].float()[None])
     got = x.reshape(B, 257, 1408)
     assert (got[:, 0] == 0).all()                      # cls rows untouched
-    assert max_ulp_err(got[:, 1:], ref) <= 2.0
+    assert_close16(got[:, 1:], ref, mags=(y,), ulps=3.0, what="patch embed")
 
 
 @pytest.mark.parametrize("ctas", [1, 2])
@@ -130,9 +145,9 @@ def test_gemm_silu_gate(lib, M, ffn, h, ctas):
     torch.cuda.synchronize()
     ref = R.silu_gate_ref(a, wg, wu)
     assert out.shape == (M, ffn)
-    diff = (out.float() - ref.float()).abs()
-    tol = 4 * torch.pow(2.0, torch.floor(torch.log2(ref.float().abs().clamp_min(2.0 ** -6))) - 10)
-    assert (diff <= tol).all(), f"max diff {diff.max().item()}"
+    g = R.linear_ref(a, wg); u = R.linear_ref(a, wu)
+    # out = silu(g)*u: a 1-ulp flip of g or u moves the product by |u| or |g| ulps -> bound by |g*u| + |u| + |g|
+    assert_close16(out, ref, mags=(g.float() * u.float(), 0.5 * u.float(), 0.5 * g.float()), ulps=4.0, what="silu gate")
 
 
 def test_gemm_rejects_bad_args(lib):
@@ -157,9 +172,7 @@ def test_layernorm(lib, rows, cols, eps):
     torch.cuda.synchronize()
     ref = R.layernorm_ref(x, w, b, eps)
     # fp32 statistics on both sides: 1 fp16 ulp (+ floor near zero)
-    diff = (y.float() - ref.float()).abs()
-    tol = 1.0 * torch.pow(2.0, torch.floor(torch.log2(ref.float().abs().clamp_min(2.0 ** -8))) - 10)
-    assert (diff <= tol).all(), f"max diff {diff.max().item()}"
+    assert_close16(y, ref, ulps=1.5, atol=1e-4, what="layernorm")
 
 
 @pytest.mark.parametrize("rows,cols", [(2048, 4096), (5, 5120), (1, 4096), (300, 512)])
@@ -169,9 +182,7 @@ def test_rmsnorm(lib, rows, cols):
     y = lib.rmsnorm(x, w, 1e-6)
     torch.cuda.synchronize()
     ref = R.rmsnorm_ref(x, w, 1e-6)
-    diff = (y.float() - ref.float()).abs()
-    tol = 2.0 * torch.pow(2.0, torch.floor(torch.log2(ref.float().abs().clamp_min(2.0 ** -8))) - 10)
-    assert (diff <= tol).all(), f"max diff {diff.max().item()}"
+    assert_close16(y, ref, ulps=2.5, atol=1e-4, what="rmsnorm")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -291,8 +302,8 @@ def test_rope_kv_append(lib, B, S, H, past):
     q_ref = R.rope_ref(q, pos).permute(0, 2, 1, 3).reshape(B * S, H * D)
     k_ref = R.rope_ref(k, pos)
     # cos/sin come from the device's cosf/sinf instead of torch's: allow 2 fp16 ulps
-    assert (q_out.float() - q_ref.float()).abs().max().item() < 1e-2
-    assert max_ulp_err(q_out, q_ref) <= 4.0 or rel_err(q_out, q_ref) < 1e-3
+    assert (q_out.float() - q_ref.float()).abs().max().item() < 2e-2
+    assert rel_err(q_out, q_ref) < 1e-3, rel_err(q_out, q_ref)
     assert rel_err(kc[:, :, past:past + S], k_ref) < 1e-3
     assert torch.equal(vc[:, :, past:past + S], v)
     assert (kc[:, :, past + S:] == 0).all() and (kc[:, :, :past] == 0).all()
