@@ -75,17 +75,19 @@ def encoder_state_dict(vit_depth: int = 39, qformer_layers: int = 12, detok_dept
         p = f"Qformer.bert.encoder.layer.{l}."
         for n in ("query", "key", "value"):
             lin(p + "attention.self." + n, H, H)
-        lin(p + "attention.output.dense", H, H)
+        # small residual branches (std 0.005) keep the 32 post-LN query states from collapsing onto one
+        # direction over 12 random layers, so the synthetic ids differ per query token
+        lin(p + "attention.output.dense", H, H, std=0.005)
         ln(p + "attention.output.LayerNorm", H)
         if l % 2 == 0:
             lin(p + "crossattention.self.query", H, H)
             lin(p + "crossattention.self.key", H, D)
-            # 3x the default std: makes the query outputs (hence the ids) depend visibly on the image
-            lin(p + "crossattention.self.value", H, D, std=0.06)
-            lin(p + "crossattention.output.dense", H, H, std=0.06)
+            # 1.5x the default std: makes the query outputs (hence the ids) depend visibly on the image
+            lin(p + "crossattention.self.value", H, D, std=0.03)
+            lin(p + "crossattention.output.dense", H, H, std=0.03)
             ln(p + "crossattention.output.LayerNorm", H)
         lin(p + "intermediate_query.dense", QFF, H)
-        lin(p + "output_query.dense", H, QFF)
+        lin(p + "output_query.dense", H, QFF, std=0.005)
         ln(p + "output_query.LayerNorm", H)
     lin("encode_task_layer.0", H, H)
     lin("encode_task_layer.2", 32, H)

@@ -53,7 +53,7 @@ struct GemmCfg {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16 + 2 * 256 * 2;   // barriers, tmem slot, bias stage
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + BAR_BYTES;
   // keep one CTA per SM (TMEM is allocated per CTA): request more than half of the SM's smem
   static constexpr int SMEM_REQUEST = SMEM_BYTES < 120 * 1024 ? 120 * 1024 : SMEM_BYTES;
@@ -98,15 +98,14 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 }
 
 // One 16-column chunk of one output row: bias -> fp16 -> act -> fp16 -> (+residual) -> fp16 -> store.
+// `bias_s` points at this chunk's 16 bias values in shared memory (nullptr: no bias); `res` holds the
+// chunk's 16 residual values when `res_loaded` (prefetched one chunk ahead by the caller).
 template <int MODE>
 __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint32_t (&acc)[16],
-                                                 const uint32_t (&acc2)[16], int m, int n0, int n_limit) {
-  if (m >= p.M || n0 >= n_limit) return;
-  long long orow = m;
-  if (p.row_group > 0) orow = (long long)(m / p.row_group) * p.row_stride + (m % p.row_group) + p.row_offset;
-  long long rrow = orow;
-  if (p.res_mod > 0) rrow = (m % p.res_mod) + p.res_offset;
-
+                                                 const uint32_t (&acc2)[16], const __half* bias_s,
+                                                 const __half* res_row, __half* out_row, bool res_loaded,
+                                                 const uint4& res0, const uint4& res1, int n0, int n_limit) {
+  if (n0 >= n_limit) return;
   __half h[16];
   if constexpr (MODE == 1) {
     // SiLU-gate: silu(fp16(gate)) rounded to fp16, times fp16(up), rounded (llama_xformer.py:186)
@@ -114,30 +113,24 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
     for (int j = 0; j < 16; ++j) {
       const float g = __half2float(__float2half_rn(__uint_as_float(acc[j])));
       const float u = __half2float(__float2half_rn(__uint_as_float(acc2[j])));
-      const float s = __half2float(__float2half_rn(g / (1.0f + __expf(-g))));
+      const float s = __half2float(__float2half_rn(g * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * g))));
       h[j] = __float2half_rn(s * u);
     }
   } else {
     float v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
-    if (p.bias != nullptr) {
-      if (n0 + 16 <= n_limit) {
-        const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
-        const uint4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
-        const __half2* bh0 = reinterpret_cast<const __half2*>(&b0);
-        const __half2* bh1 = reinterpret_cast<const __half2*>(&b1);
+    if (bias_s != nullptr) {
+      const uint4 b0 = *reinterpret_cast<const uint4*>(bias_s);
+      const uint4 b1 = *reinterpret_cast<const uint4*>(bias_s + 8);
+      const __half2* bh0 = reinterpret_cast<const __half2*>(&b0);
+      const __half2* bh1 = reinterpret_cast<const __half2*>(&b1);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f0 = __half22float2(bh0[j]);
-          const float2 f1 = __half22float2(bh1[j]);
-          v[2 * j] += f0.x; v[2 * j + 1] += f0.y;
-          v[8 + 2 * j] += f1.x; v[8 + 2 * j + 1] += f1.y;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (n0 + j < n_limit) v[j] += __half2float(p.bias[n0 + j]);
+      for (int j = 0; j < 4; ++j) {
+        const float2 f0 = __half22float2(bh0[j]);
+        const float2 f1 = __half22float2(bh1[j]);
+        v[2 * j] += f0.x; v[2 * j + 1] += f0.y;
+        v[8 + 2 * j] += f1.x; v[8 + 2 * j + 1] += f1.y;
       }
     }
 #pragma unroll
@@ -151,14 +144,10 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
     }
   }
 
-  const bool full = (n0 + 16 <= n_limit);
-  if (p.residual != nullptr) {
-    const __half* rp = p.residual + rrow * p.ldr + n0;
-    if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-      const uint4 r0 = *reinterpret_cast<const uint4*>(rp);
-      const uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
-      const __half* rh0 = reinterpret_cast<const __half*>(&r0);
-      const __half* rh1 = reinterpret_cast<const __half*>(&r1);
+  if (res_row != nullptr) {
+    if (res_loaded) {
+      const __half* rh0 = reinterpret_cast<const __half*>(&res0);
+      const __half* rh1 = reinterpret_cast<const __half*>(&res1);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         h[j] = __float2half_rn(__half2float(h[j]) + __half2float(rh0[j]));
@@ -167,12 +156,12 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        if (n0 + j < n_limit) h[j] = __float2half_rn(__half2float(h[j]) + __half2float(rp[j]));
+        if (n0 + j < n_limit) h[j] = __float2half_rn(__half2float(h[j]) + __half2float(res_row[n0 + j]));
     }
   }
 
-  __half* op = p.out + orow * p.ldo + n0;
-  if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+  __half* op = out_row + n0;
+  if ((n0 + 16 <= n_limit) && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
     uint4 o0, o1;
     __half* oh0 = reinterpret_cast<__half*>(&o0);
     __half* oh1 = reinterpret_cast<__half*>(&o1);
@@ -205,6 +194,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t tfull_bar = bar_base + 2 * STAGES * 8; // [2]
   const uint32_t tempty_bar = tfull_bar + 16;           // [2]
   const uint32_t tmem_slot = tempty_bar + 16;           // uint32
+  const uint32_t bias_off = tmem_slot + 16;             // [2][256] halves
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -308,26 +298,70 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int ew = warp - GEMM_EPI_WARP0;      // 0..7
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int half_id = ew >> 2;               // which half of the column chunks
+    const int etid = threadIdx.x - GEMM_EPI_WARP0 * 32;   // 0..255
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const uint32_t lead_tempty0 = (CTAS == 2) ? mapa_shared(tempty_bar, 0) : tempty_bar;
+    __half* bias_smem = reinterpret_cast<__half*>(smem_gen + (bias_off - smem_base));
     constexpr int NCHUNK = (MODE == 1) ? (BN / 32) : (BN / 16);   // 16-column output chunks per tile
     constexpr int CH0 = (NCHUNK + 1) / 2;
     const int c_begin = half_id == 0 ? 0 : CH0;
     const int c_end = half_id == 0 ? CH0 : NCHUNK;
     const int n_limit = (MODE == 1) ? p.N / 2 : p.N;
+    const bool has_bias = (MODE == 0) && (p.bias != nullptr);
     int iter = 0;
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++iter) {
       const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
+      const int n_tile0 = (MODE == 1) ? nt * (BN / 2) : nt * BN;
+      const int m = (mt * CTAS + (int)cta_rank) * GEMM_BLOCK_M + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      // per-row pointers (output row remap / periodic residual rows, see seedb200_gemm_desc)
+      long long orow = m;
+      if (p.row_group > 0) orow = (long long)(m / p.row_group) * p.row_stride + (m % p.row_group) + p.row_offset;
+      long long rrow = orow;
+      if (p.res_mod > 0) rrow = (m % p.res_mod) + p.res_offset;
+      __half* out_row = p.out + orow * p.ldo;
+      const __half* res_row = (p.residual != nullptr && row_ok) ? p.residual + rrow * p.ldr : nullptr;
+      const bool res_vec = (res_row != nullptr) && ((reinterpret_cast<uintptr_t>(res_row) & 15) == 0);
+
+      // stage this tile's bias in shared memory and prefetch the first residual chunk while the MMAs of
+      // the tile are still running (both are global-memory latencies that used to sit in the chunk loop)
+      if (has_bias) {
+        if (etid < BN) {
+          const int n = n_tile0 + etid;
+          bias_smem[as * 256 + etid] = (n < p.N) ? p.bias[n] : __float2half(0.0f);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      uint4 rn0 = make_uint4(0, 0, 0, 0), rn1 = rn0;
+      bool rn_ok = false;
+      {
+        const int n0 = n_tile0 + c_begin * 16;
+        rn_ok = res_vec && (n0 + 16 <= n_limit);
+        if (rn_ok) {
+          rn0 = *reinterpret_cast<const uint4*>(res_row + n0);
+          rn1 = *reinterpret_cast<const uint4*>(res_row + n0 + 8);
+        }
+      }
+
       mbar_wait(tfull_bar + 8 * as, aphase);
       tc_fence_after();
-      const int m = (mt * CTAS + (int)cta_rank) * GEMM_BLOCK_M + quarter * 32 + lane;
       const uint32_t t_acc = tmem_base + as * Cfg::ACC_STRIDE + lane_addr;
       for (int c = c_begin; c < c_end; ++c) {
         uint32_t r0[16], r1[16];
         tmem_ld16(t_acc + c * 16, r0);
         if constexpr (MODE == 1) tmem_ld16(t_acc + BN / 2 + c * 16, r1);
+        const uint4 rc0 = rn0, rc1 = rn1;
+        const bool rc_ok = rn_ok;
+        if (c + 1 < c_end) {   // prefetch the next chunk's residual
+          const int n1 = n_tile0 + (c + 1) * 16;
+          rn_ok = res_vec && (n1 + 16 <= n_limit);
+          if (rn_ok) {
+            rn0 = *reinterpret_cast<const uint4*>(res_row + n1);
+            rn1 = *reinterpret_cast<const uint4*>(res_row + n1 + 8);
+          }
+        }
         tmem_ld_wait();
         if (c == c_end - 1) {
           // all TMEM reads of this accumulator stage are done (tcgen05.wait::ld is warp-collective):
@@ -339,12 +373,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             else mbar_arrive(tempty_bar + 8 * as);
           }
         }
-        const int n0 = (MODE == 1) ? nt * (BN / 2) + c * 16 : nt * BN + c * 16;
-        epilogue_store16<MODE>(p, r0, r1, m, n0, n_limit);
-      }
-      if (c_begin >= c_end && lane == 0) {   // (never for the instantiated shapes; keeps the barrier count exact)
-        if constexpr (CTAS == 2) mbar_arrive_cluster(lead_tempty0 + 8 * as);
-        else mbar_arrive(tempty_bar + 8 * as);
+        if (row_ok)
+          epilogue_store16<MODE>(p, r0, r1, has_bias ? bias_smem + as * 256 + c * 16 : nullptr, res_row, out_row,
+                                 rc_ok, rc0, rc1, n_tile0 + c * 16, n_limit);
       }
     }
   }

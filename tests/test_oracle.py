@@ -1,0 +1,158 @@
+"""CPU tests (-m "not gpu") that PIN the oracle:
+  * oracle/restatement.py (plain-torch restatement) and oracle/vq_oracle.c (C restatement of the VQ search)
+    against tests/golden/*.pt, which oracle/make_golden.py produced by running the unmodified reference;
+  * and, when /root/reference is mounted (build container only), against the live reference itself.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shim, restatement as R, synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=False)
+
+
+def _check_sample(t, s, rtol=2e-5):
+    flat = t.reshape(-1)
+    assert list(t.shape) == s["shape"]
+    got = flat[:: s["step"]]
+    assert torch.allclose(got, s["values"], rtol=rtol, atol=rtol * float(s["values"].abs().max()))
+    assert abs(flat.double().norm().item() - s["norm"]) <= rtol * s["norm"]
+
+
+@pytest.fixture(scope="module")
+def vq_lib():
+    from seed_b200.build import ORACLE_LIB, build_oracle
+
+    build_oracle()
+    lib = C.CDLL(ORACLE_LIB)
+    lib.vq_oracle_argmin.restype = C.c_int
+    return lib
+
+
+def c_oracle(lib, z16, cb16, mode):
+    zn = z16.contiguous().view(torch.int16).numpy().view(np.uint16)
+    cn = cb16.contiguous().view(torch.int16).numpy().view(np.uint16)
+    ids = np.zeros(zn.shape[0], dtype=np.int64)
+    margin = np.zeros(zn.shape[0], dtype=np.float32)
+    rc = lib.vq_oracle_argmin(zn.ctypes.data_as(C.c_void_p), cn.ctypes.data_as(C.c_void_p), zn.shape[0], cn.shape[0],
+                              zn.shape[1], mode, ids.ctypes.data_as(C.c_void_p), margin.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return torch.from_numpy(ids), torch.from_numpy(margin)
+
+
+# ---------------------------------------------------------------------------------------------
+# VQ: C oracle vs the reference's VectorQuantizer2.forward outputs (golden) in both dtypes
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["spread", "default_init"])
+def test_c_vq_oracle_matches_reference_vectors(vq_lib, tag):
+    g = _load("vq_reference_expr.pt")[tag]
+    ids32, m32 = c_oracle(vq_lib, g["z"], g["codebook"], 1)
+    ids16, m16 = c_oracle(vq_lib, g["z"], g["codebook"], 0)
+    # exact wherever the oracle's own top-2 margin is not a floating-point tie; report would-be flips
+    neq32 = ids32 != g["ids_fp32"]
+    neq16 = ids16 != g["ids_fp16"]
+    assert int(neq32.sum()) == 0, f"fp32 mode: {int(neq32.sum())} ids differ, margins {m32[neq32][:8]}"
+    assert int(neq16.sum()) == 0, f"fp16 mode: {int(neq16.sum())} ids differ, margins {m16[neq16][:8]}"
+    if tag == "default_init":
+        # the degenerate case SURVEY.md section 7 describes: in half precision every distance collapses to |z|^2
+        assert (g["ids_fp16"] == 0).float().mean() > 0.5
+
+
+def test_c_vq_oracle_rejects_bad_args(vq_lib):
+    assert vq_lib.vq_oracle_argmin(None, None, 1, 1, 32, 0, None, None) == -1
+
+
+def test_torch_vq_expression_equals_c_oracle_on_random_rows(vq_lib):
+    g = torch.Generator().manual_seed(5)
+    z = (torch.randn(300, 32, generator=g) * 0.3).half()
+    cb = (torch.randn(2048, 32, generator=g) * 0.3).half()
+    ids32, _ = c_oracle(vq_lib, z, cb, 1)
+    ref32, margin = R.vq_forward(z.float(), cb.float())
+    safe = margin > 1e-5
+    assert torch.equal(ids32[safe], ref32[safe])
+
+
+# ---------------------------------------------------------------------------------------------
+# encoder restatement vs golden (reference outputs)
+# ---------------------------------------------------------------------------------------------
+def _encoder_vs_golden(name):
+    g = _load(name)
+    c = g["config"]
+    sd = synth.encoder_state_dict(c["vit_depth"], c["qformer_layers"], c["detok_depth"])
+    x = synth.images(c["batch"])
+    with torch.no_grad():
+        out = R.encode(x, sd, c["vit_depth"], c["qformer_layers"])
+        emb = R.detokenize(g["ids"], sd, c["detok_depth"])
+    assert torch.equal(out["ids"], g["ids"])
+    assert torch.allclose(out["z"].reshape(-1, 32), g["z"], atol=2e-5)
+    _check_sample(out["vit"], g["vit"])
+    _check_sample(out["image_embeds"], g["image_embeds"])
+    _check_sample(out["query_output_up"], g["query_output_up"])
+    if isinstance(g["qformer"], dict):
+        _check_sample(out["qformer"], g["qformer"])
+    else:
+        assert torch.allclose(out["qformer"], g["qformer"], atol=5e-5)
+    assert torch.allclose(emb, g["image_embeds_out"], atol=5e-5, rtol=1e-4)
+
+
+def test_encoder_restatement_matches_golden_reduced():
+    _encoder_vs_golden("encoder_d2_q2.pt")
+
+
+def test_encoder_restatement_matches_golden_full_depth():
+    """full 39-block ViT-g + 12-layer Q-Former + 4 de-tokenizer blocks, 2 images (about a minute on 8 cores)."""
+    _encoder_vs_golden("encoder_full.pt")
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not mounted (GPU box)")
+def test_encoder_restatement_matches_live_reference():
+    vd, ql, dd = 1, 2, 1
+    model = ref_shim.build_reference_quantizer(vd, ql, dd)
+    sd = synth.encoder_state_dict(vd, ql, dd, seed=77)
+    model.load_state_dict(sd, strict=False)
+    x = synth.images(2, seed=78)
+    with torch.no_grad():
+        ids, up = model.get_codebook_indices(x)
+        emb = model.get_codebook_entry(ids)
+        out = R.encode(x, sd, vd, ql)
+        emb2 = R.detokenize(ids, sd, dd)
+    assert torch.equal(ids, out["ids"])
+    assert torch.allclose(up, out["query_output_up"], atol=1e-5)
+    assert torch.allclose(emb, emb2, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# LLaMA restatement vs golden (reference llama_xformer outputs, prefill + one cached decode step)
+# ---------------------------------------------------------------------------------------------
+def test_llama_restatement_matches_golden():
+    g = _load("llama_tiny.pt")
+    c = g["config"]
+    sd = synth.llama_state_dict(c["hidden"], c["layers"], c["ffn"], c["vocab"])
+    with torch.no_grad():
+        logits, hidden, past = R.llama_forward(sd, g["input_ids"], c["heads"], c["layers"])
+        assert torch.allclose(logits, g["logits"], atol=2e-5, rtol=1e-4)
+        assert torch.allclose(past[0][0], g["k0"], atol=1e-5)
+        assert torch.allclose(past[1][1], g["v1"], atol=1e-5)
+        nxt = logits[:, -1].argmax(-1, keepdim=True)
+        assert torch.equal(nxt, g["next_ids"])
+        logits2, _, _ = R.llama_forward(sd, nxt, c["heads"], c["layers"], past=past)
+        assert torch.allclose(logits2, g["decode_logits"], atol=2e-5, rtol=1e-4)
+
+
+def test_synth_is_deterministic_and_fp16_representable():
+    a = synth.encoder_state_dict(1, 1, 0)
+    b = synth.encoder_state_dict(1, 1, 0)
+    for k in a:
+        assert torch.equal(a[k], b[k])
+        assert torch.equal(a[k], a[k].half().float()), k
+    ids = synth.prompt_ids(2, 64, n_image_spans=1)
+    assert ids[0, 1] == 32000 + 8192 and ids[0, 34] == 32000 + 8193
+    assert ((ids[0, 2:34] >= 32000) & (ids[0, 2:34] < 32000 + 8192)).all()
