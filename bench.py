@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on the B200 path.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                      # images/s, ViT-g/14 + Q-Former + VQ, B=256
+    python bench.py --workload llama_prefill --steps 10 --warmup 3      # tokens/s, LLaMA-7B prefill, S=2048
+    python bench.py --impl reference ...                                 # the reference algorithm on the host CPU
+    torchrun --nproc-per-node N ... bench.py --gpus N ...                # one rank per GPU, weak scaling
+
+One "step" is one pass of the hot path over one batch of synthetic input:
+  encode        : 256 images/GPU -> [256,32] ids (config #2 of BASELINE.json); at N > 1 every rank encodes its own
+                  shard and one NCCL all-gather returns all ids to every rank (config #4's data-parallel pattern);
+  llama_prefill : one S=2048 prompt (with a 34-token image span) through random-init LLaMA-7B (config #3).
+`value` is timed with CUDA events with the inputs already resident in HBM; `e2e` is the same metric through the
+reference-facing Python API (models.seed_llama_tokenizer.ImageTokenizer.encode / models.llama_xformer
+.LlamaForCausalLM.forward) starting from PINNED HOST buffers and ending with the ids / last-token logits on
+the host, copies inside the timed region.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+VIT_DEPTH, QF_LAYERS = 39, 12
+# algorithmic work per image (2 FLOP per MAC), SURVEY.md section 8d / DESIGN.md
+T_TOK, D, FF = 257, 1408, 6144
+GEMM_FLOPS_PER_IMAGE = (
+    2 * 256 * 588 * D                                                   # patch embed
+    + VIT_DEPTH * 2 * T_TOK * (D * 3 * D + D * D + 2 * D * FF)         # qkv, proj, fc1, fc2
+    + 6 * 2 * T_TOK * D * 1536                                          # cross-attention K|V of 6 layers
+    + QF_LAYERS * 2 * 32 * (768 * 2304 + 768 * 768 + 2 * 768 * 3072)   # self qkv, out, FFN
+    + 6 * 2 * 32 * (2 * 768 * 768)                                      # cross q, out
+    + 2 * 32 * (768 * 768 + 768 * 32)                                   # encode_task_layer
+)
+ATTN_FLOPS_PER_IMAGE = (VIT_DEPTH * 4 * 16 * T_TOK * T_TOK * 88 + QF_LAYERS * 4 * 12 * 32 * 32 * 64
+                        + 6 * 4 * 12 * 32 * T_TOK * 64)
+ENCODE_FLOPS_PER_IMAGE = GEMM_FLOPS_PER_IMAGE + ATTN_FLOPS_PER_IMAGE + 2 * 32 * 8192 * 32
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops_burst": d.get("bf16_tflops"), "tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "MEASURED_PEAKS.json (of measured)"}
+    return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def barrier_sync(world):
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms: float, world: int) -> float:
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed(fn, steps, warmup, world):
+    """W untimed + K timed calls bracketed by barrier + synchronize; CUDA events; max over ranks (ms)."""
+    for _ in range(warmup):
+        fn()
+    barrier_sync(world)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        fn()
+    e.record()
+    barrier_sync(world)
+    return max_over_ranks(s.elapsed_time(e), world)
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU legs: the oracle port of the reference algorithm (the only place bench.py executes oracle/)
+# --------------------------------------------------------------------------------------------------
+def cpu_encode_images_per_s(sd, n_images: int):
+    from oracle import restatement as R
+    from seed_b200 import synth
+
+    torch.set_num_threads(os.cpu_count())
+    x = synth.images(max(n_images, 1), seed=4242)
+    with torch.no_grad():
+        R.encode(x[:1], sd, VIT_DEPTH, QF_LAYERS)          # warm-up
+        t0 = time.perf_counter()
+        R.encode(x, sd, VIT_DEPTH, QF_LAYERS)
+        dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
+def reference_arm(args, world, rank):
+    """--impl reference: the reference algorithm (oracle port: /root/reference is Python and does not travel to
+    the GPU box; oracle/restatement.py is pinned to it by tests/golden) on the host cores, same metric/config."""
+    if rank != 0:
+        return None
+    from seed_b200 import synth
+
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    if args.workload == "encode":
+        from oracle import restatement as R
+
+        sd = synth.encoder_state_dict(VIT_DEPTH, QF_LAYERS, 0)
+        x = synth.images(2, seed=1)
+        with torch.no_grad():
+            t0 = time.perf_counter(); R.encode(x, sd, VIT_DEPTH, QF_LAYERS); probe = (time.perf_counter() - t0) / 2
+        budget = 150.0 / max(1, args.steps + args.warmup)
+        nb = max(1, min(args.batch, int(budget / max(probe, 1e-3))))
+        x = synth.images(nb, seed=1234)
+        with torch.no_grad():
+            for _ in range(args.warmup):
+                R.encode(x, sd, VIT_DEPTH, QF_LAYERS)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                R.encode(x, sd, VIT_DEPTH, QF_LAYERS)
+            dt = time.perf_counter() - t0
+        value = nb * args.steps / dt
+        sample = f"{nb} images/step (of the {args.batch}-image batch), fp32, torch {torch.get_num_threads()} threads"
+        return dict(metric="images/sec SEED encode+VQ", value=value, unit="images/s", ms_per_step=1e3 * dt / args.steps,
+                    sample=sample, cores=cores, workload=f"encode_b{args.batch}")
+    else:
+        from oracle import restatement as R
+
+        layers = 2       # layer-truncated 7B (fp32 7B = 26.6 GB of weights and minutes per prompt on the host)
+        sd = synth.llama_state_dict(4096, layers, 11008, 40194)
+        ids = synth.prompt_ids(1, args.seq, 1)
+        with torch.no_grad():
+            for _ in range(max(1, min(args.warmup, 1))):
+                R.llama_forward(sd, ids, 32, layers)
+            t0 = time.perf_counter()
+            n = max(1, min(args.steps, 3))
+            for _ in range(n):
+                R.llama_forward(sd, ids, 32, layers)
+            dt = (time.perf_counter() - t0) / n
+        # scale the per-layer time to 32 layers (+ embedding / lm_head measured as part of the 2-layer run)
+        per_layer = dt / (layers + 0.8)
+        full = per_layer * (32 + 0.8)
+        value = args.seq / full
+        sample = (f"{layers}-layer slice of LLaMA-7B, S={args.seq}, fp32, scaled to 32 layers by measured time per layer "
+                  f"(lm_head+embedding counted as 0.8 layer)")
+        return dict(metric="tokens/sec LLaMA-7B prefill", value=value, unit="tokens/s", ms_per_step=1e3 * full,
+                    sample=sample, cores=cores, workload=f"llama7b_prefill_s{args.seq}")
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arms
+# --------------------------------------------------------------------------------------------------
+def encode_arm(args, world, rank, local):
+    from models.seed_llama_tokenizer import ImageTokenizer, all_gather_ids
+    from seed_b200 import lib as L, synth
+
+    B = args.batch
+    dev = torch.device("cuda", local)
+    sd = synth.encoder_state_dict(VIT_DEPTH, QF_LAYERS, 0)
+    tok = ImageTokenizer(model_path=sd, device=dev, fp16=True, max_batch=B, gemm_ctas=args.ctas,
+                         vq_mode=L.VQ_FP32 if args.vq == "fp32" else L.VQ_FP16)
+    # id parity against the reference's own output (tests/golden/encoder_full.pt), same weights
+    parity = None
+    gpath = os.path.join(REPO, "tests", "golden", "encoder_full.pt")
+    if rank == 0 and os.path.exists(gpath):
+        g = torch.load(gpath, map_location="cpu", weights_only=False)
+        ids = tok.encode(synth.images(g["config"]["batch"]).to(dev)).cpu()
+        neq = ids != g["ids"]
+        parity = {"tokens": int(ids.numel()), "equal": int((~neq).sum()),
+                  "differ_above_margin_0.02": int((neq.reshape(-1) & (g["margin"] > 0.02)).sum()),
+                  "vq_mode": args.vq, "against": "reference fp32 ids (tests/golden/encoder_full.pt)"}
+    host = synth.images(B, seed=1000 + rank).half().pin_memory()
+    x = host.to(dev)
+    out = {}
+
+    def step_device():
+        ids = tok.encode(x)
+        if world > 1:
+            ids = all_gather_ids(ids)
+        out["ids"] = ids
+
+    def step_e2e():
+        xi = host.to(dev, non_blocking=True)
+        ids = tok.encode(xi)
+        if world > 1:
+            ids = all_gather_ids(ids)
+        out["ids_host"] = ids.cpu()
+
+    step_device(); torch.cuda.synchronize()
+    L.reset_launch_count()
+    with ClockSampler(local) as cs:
+        ms = timed(step_device, args.steps, args.warmup, world)
+    launches = L.launch_count() // (args.steps + args.warmup)
+    clocks = cs.summary()
+    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup), world)
+    # roofline of the dominant kernel (tcgen05 GEMM): one more identical step with every GEMM launch bracketed
+    # by CUDA events on its stream
+    torch.cuda.synchronize()
+    L.profile_begin()
+    tok.encode(x)
+    prof = L.profile_end()
+    peaks = measured_peaks()
+    gemm_ms, gemm_n = prof["gemm"]["ms"], prof["gemm"]["launches"]
+    gemm_flops = GEMM_FLOPS_PER_IMAGE * B
+    ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(REPO, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch_avg")
+    roofline = {"kernel": "sb::gemm_tcgen05_kernel", "bound": "tensor", "achieved": round(ach, 1),
+                "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / peaks["tflops_sustained"], 4),
+                "traffic": traffic, "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                "launches_per_step": gemm_n, "gemm_ms_per_step": round(gemm_ms, 3),
+                "algorithmic_gflop_per_launch": round(gemm_flops / gemm_n / 1e9, 2),
+                "avg_launch_ms": round(gemm_ms / gemm_n, 4), "share_of_step": round(gemm_ms / (ms / args.steps), 3),
+                "attention_ms_per_step": round(prof["attention"]["ms"], 3),
+                "whole_step_tflops": round(ENCODE_FLOPS_PER_IMAGE * B / (ms / args.steps * 1e-3) / 1e12, 1)}
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        n_cpu = args.cpu_images
+        v, dt = cpu_encode_images_per_s(sd, n_cpu)
+        cpu = {"value": round(v, 3), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{n_cpu} of the {B} images, full depth, fp32, oracle/restatement.py, {dt:.1f} s"}
+    total = B * world * args.steps
+    res = {
+        "metric": "images/sec SEED encode+VQ", "value": round(total / (ms * 1e-3), 2), "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"encode_b{B}_per_gpu: 224x224 -> ViT-g/14 (39 blocks) + causal Q-Former (12 layers) + "
+                               f"8192-way VQ -> 32 ids/image", "global_batch": B * world, "vq_arithmetic": args.vq,
+                   "weights": "seeded synthetic (seed_b200/synth.py; codebook N(0,0.28) instead of U(+-1/8192))",
+                   "parallelism": f"dp{world}" + (" + NCCL all-gather of ids" if world > 1 else ""),
+                   "l2": "inputs not flushed explicitly: each step streams ~2 GB of activations, 16x the 126 MB L2",
+                   "gemm_cta_group": args.ctas or 1},
+        "clocks": clocks,
+        "e2e": {"value": round(total / (ms_e2e * 1e-3), 2), "unit": "images/s",
+                "h2d_bytes_per_step": B * 3 * 224 * 224 * 2, "d2h_bytes_per_step": B * world * 32 * 8,
+                "api": "models.seed_llama_tokenizer.ImageTokenizer.encode(pinned.to(cuda)) -> ids.cpu()"},
+        "gpu_launches": int(launches) * args.steps,
+        "roofline": roofline, "cpu_baseline": cpu, "id_parity": parity,
+    }
+    return res
+
+
+def llama_arm(args, world, rank, local):
+    from transformers.models.llama.configuration_llama import LlamaConfig
+
+    from models.llama_xformer import LlamaForCausalLM
+    from seed_b200 import lib as L, synth
+
+    dev = torch.device("cuda", local)
+    h, nl, nh, ffn, V, S = 4096, 32, 32, 11008, 40194, args.seq
+    cfg = LlamaConfig(vocab_size=V, hidden_size=h, intermediate_size=ffn, num_hidden_layers=nl,
+                      num_attention_heads=nh, num_key_value_heads=nh, rms_norm_eps=1e-6, max_position_embeddings=4096)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    def rnd(*shape, std=0.02, mean=0.0):
+        return (torch.randn(*shape, device=dev, generator=g, dtype=torch.float32) * std + mean).half()
+
+    sd = {"model.embed_tokens.weight": rnd(V, h), "model.norm.weight": rnd(h, std=0.05, mean=1.0),
+          "lm_head.weight": rnd(V, h)}
+    for l in range(nl):
+        p = f"model.layers.{l}."
+        for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            sd[p + f"self_attn.{n}.weight"] = rnd(h, h)
+        sd[p + "mlp.gate_proj.weight"] = rnd(ffn, h)
+        sd[p + "mlp.up_proj.weight"] = rnd(ffn, h)
+        sd[p + "mlp.down_proj.weight"] = rnd(h, ffn)
+        sd[p + "input_layernorm.weight"] = rnd(h, std=0.05, mean=1.0)
+        sd[p + "post_attention_layernorm.weight"] = rnd(h, std=0.05, mean=1.0)
+    model = LlamaForCausalLM(cfg, sd, device=dev, max_batch=1, max_seq=S, gemm_ctas=args.ctas)
+    del sd
+    torch.cuda.empty_cache()
+    ids_host = synth.prompt_ids(1, S, 1, seed=77 + rank).pin_memory()
+    ids = ids_host.to(dev)
+    out = {}
+
+    def step_device():
+        out["o"] = model.forward(input_ids=ids, use_cache=False)          # full [1,S,V] logits: the reference contract
+
+    def step_e2e():
+        o = model.forward(input_ids=ids_host.to(dev, non_blocking=True), use_cache=False)
+        out["last"] = o.logits[:, -1].float().cpu()
+
+    step_device(); torch.cuda.synchronize()
+    L.reset_launch_count()
+    with ClockSampler(local) as cs:
+        ms = timed(step_device, args.steps, args.warmup, world)
+    launches = L.launch_count() // (args.steps + args.warmup)
+    clocks = cs.summary()
+    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup), world)
+    L.profile_begin(); model.forward(input_ids=ids, use_cache=False); prof = L.profile_end()
+    peaks = measured_peaks()
+    lin_flops = 2.0 * S * (nl * (4 * h * h + 3 * h * ffn) + h * V)
+    attn_flops = nl * 4.0 * nh * S * S * 128 * 0.5
+    ach = lin_flops / (prof["gemm"]["ms"] * 1e-3) / 1e12
+    total_tok = S * world * args.steps
+    return {
+        "metric": "tokens/sec LLaMA-7B prefill", "value": round(total_tok / (ms * 1e-3), 1), "unit": "tokens/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"llama7b_prefill: random-init h4096/L32/H32/FFN11008/V40194, B=1, S={S} incl. one "
+                               f"34-token image span, logits for all positions", "global_batch": world, "seq_len": S,
+                   "parallelism": f"dp{world} (independent replicas, no collective)",
+                   "l2": "13.5 GB of weights stream through L2 every step", "gemm_cta_group": args.ctas or 1},
+        "clocks": clocks,
+        "e2e": {"value": round(total_tok / (ms_e2e * 1e-3), 1), "unit": "tokens/s", "h2d_bytes_per_step": S * 8,
+                "d2h_bytes_per_step": V * 4,
+                "api": "models.llama_xformer.LlamaForCausalLM.forward(pinned ids.to(cuda)) -> logits[:, -1].cpu()"},
+        "gpu_launches": int(launches) * args.steps,
+        "roofline": {"kernel": "sb::gemm_tcgen05_kernel", "bound": "tensor", "achieved": round(ach, 1),
+                     "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": round(ach / peaks["tflops_sustained"], 4), "traffic": None,
+                     "peak_source": peaks["source"], "launches_per_step": prof["gemm"]["launches"],
+                     "gemm_ms_per_step": round(prof["gemm"]["ms"], 3),
+                     "attention_ms_per_step": round(prof["attention"]["ms"], 3),
+                     "whole_step_tflops": round((lin_flops + attn_flops) / (ms / args.steps * 1e-3) / 1e12, 1)},
+        "cpu_baseline": None,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="seedb200", choices=["seedb200", "reference"])
+    ap.add_argument("--workload", default="encode", choices=["encode", "llama_prefill"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (encode)")
+    ap.add_argument("--seq", type=int, default=2048, help="prompt length (llama_prefill)")
+    ap.add_argument("--ctas", type=int, default=2, help="tcgen05 cta_group of the GEMMs (1 or 2)")
+    ap.add_argument("--vq", default="fp16", choices=["fp16", "fp32"], help="VQ distance arithmetic")
+    ap.add_argument("--cpu-images", type=int, default=16, help="images timed by the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "seedb200" else args.warmup
+
+    if args.impl == "reference":
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        rank = int(os.environ.get("RANK", "0"))
+        r = reference_arm(args, world, rank)
+        if r is None:
+            return
+        line = {"impl": "reference", "metric": r["metric"], "value": round(r["value"], 3), "unit": r["unit"],
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(r["ms_per_step"], 2), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": r["workload"], "note": "reference algorithm on the host CPU (oracle port of "
+                           "/root/reference, pinned by tests/golden); no GPU involved"},
+                "cpu_baseline": {"value": round(r["value"], 3), "unit": r["unit"], "cores": r["cores"], "kind": "port",
+                                 "sample": r["sample"]},
+                "e2e": {"value": round(r["value"], 3), "unit": r["unit"], "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the seedb200 arm has no CPU fallback; use --impl reference)")
+    world, rank, local = dist_setup(args.gpus)
+    res = encode_arm(args, world, rank, local) if args.workload == "encode" else llama_arm(args, world, rank, local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

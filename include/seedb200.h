@@ -53,6 +53,12 @@ const char* seedb200_last_error(void);
  * last reset (bench.py's "gpu_launches"). */
 int64_t seedb200_launch_count(void);
 void seedb200_reset_launch_count(void);
+/* Optional per-kernel timing for bench.py's roofline: between begin and end every GEMM / attention launch of
+ * the calling thread is bracketed by CUDA events on its stream.  end() synchronises, then reports for
+ * kind 0 (tcgen05 GEMM) and kind 1 (attention): launches, summed device milliseconds and, for the GEMM, the
+ * summed algorithmic FLOPs (2*M*N*K per launch).  out[kind*3 + {0,1,2}] = {launches, ms, flops}. */
+int seedb200_profile_begin(void);
+int seedb200_profile_end(double* out6);
 
 /* A named tensor handed to *_create.  Pointers are borrowed DEVICE pointers to
  * contiguous fp16 data; the caller keeps them alive for the handle's lifetime.

@@ -292,7 +292,9 @@ static int launch_attn(const seedb200_attn_desc& d, cudaStream_t stream) {
   p.nq = d.nq; p.nk = d.nk; p.head_dim = d.head_dim; p.causal = d.causal;
   p.scale_log2 = d.scale * 1.4426950408889634f;
   dim3 grid((d.nq + BQ - 1) / BQ, d.heads, d.batch);
+  profile_mark_begin(1, stream);
   kern<<<grid, NW * 32, smem, stream>>>(p);
+  profile_mark_end(1, stream, 4.0 * (double)d.batch * d.heads * (double)d.nq * d.nk * d.head_dim * (d.causal ? 0.5 : 1.0));
   SB_LAUNCH_CHECK();
   return 0;
 }

@@ -5,6 +5,7 @@
 
 #include <map>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "ops.h"
@@ -21,6 +22,26 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+
+struct ProfRec { cudaEvent_t a, b; int kind; double flops; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec>* g_prof = nullptr;
+
+bool profile_enabled() { return g_prof_on; }
+void profile_mark_begin(int kind, cudaStream_t stream) {
+  if (!g_prof_on) return;
+  ProfRec r;
+  r.kind = kind; r.flops = 0.0;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, stream);
+  g_prof->push_back(r);
+}
+void profile_mark_end(int kind, cudaStream_t stream, double flops) {
+  if (!g_prof_on || g_prof->empty()) return;
+  ProfRec& r = g_prof->back();
+  r.flops = flops;
+  cudaEventRecord(r.b, stream);
+}
 
 int num_sms() {
   static int sms = 0;
@@ -68,6 +89,34 @@ int seedb200_version(void) { return SEEDB200_VERSION; }
 const char* seedb200_last_error(void) { return sb::g_err; }
 int64_t seedb200_launch_count(void) { return sb::g_launches; }
 void seedb200_reset_launch_count(void) { sb::g_launches = 0; }
+
+int seedb200_profile_begin(void) {
+  if (sb::g_prof == nullptr) sb::g_prof = new std::vector<sb::ProfRec>();
+  sb::g_prof->clear();
+  sb::g_prof_on = true;
+  return 0;
+}
+int seedb200_profile_end(double* out6) {
+  if (!sb::g_prof_on || out6 == nullptr) {
+    sb::set_error("profile_end without profile_begin");
+    return SEEDB200_ERR_INVALID;
+  }
+  sb::g_prof_on = false;
+  SB_CHECK_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < 6; ++i) out6[i] = 0.0;
+  for (auto& r : *sb::g_prof) {
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    if (r.kind >= 0 && r.kind < 2) {
+      out6[r.kind * 3 + 0] += 1.0;
+      out6[r.kind * 3 + 1] += ms;
+      out6[r.kind * 3 + 2] += r.flops;
+    }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  sb::g_prof->clear();
+  return 0;
+}
 
 int seedb200_rope_kv_append(const void* qkv, const int64_t* positions, int B, int S, int H, int D, int past_len,
                             int max_seq, void* q_out, void* k_cache, void* v_cache, void* stream) {

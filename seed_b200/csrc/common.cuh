@@ -53,6 +53,11 @@ void count_launch(int n = 1);
 
 int num_sms();
 
+// per-kernel event timing (seedb200_profile_begin/end); no-ops unless enabled on this thread
+bool profile_enabled();
+void profile_mark_begin(int kind, cudaStream_t stream);
+void profile_mark_end(int kind, cudaStream_t stream, double flops);
+
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------
 // device helpers

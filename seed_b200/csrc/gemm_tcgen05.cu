@@ -469,7 +469,9 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  profile_mark_begin(0, stream);
   SB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  profile_mark_end(0, stream, 2.0 * (double)d.M * (double)d.N * (double)d.K);
   count_launch();
   return 0;
 }

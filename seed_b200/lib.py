@@ -21,6 +21,7 @@ VQ_FP16, VQ_FP32 = 0, 1
 # every symbol include/seedb200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "seedb200_version", "seedb200_last_error", "seedb200_launch_count", "seedb200_reset_launch_count",
+    "seedb200_profile_begin", "seedb200_profile_end",
     "seedb200_gemm", "seedb200_layernorm", "seedb200_rmsnorm", "seedb200_attention", "seedb200_vq_argmin",
     "seedb200_patchify", "seedb200_rope_kv_append", "seedb200_embedding",
     "seedb200_encoder_create", "seedb200_encoder_destroy", "seedb200_encoder_encode",
@@ -87,6 +88,7 @@ def load() -> C.CDLL:
     lib.seedb200_last_error.restype = C.c_char_p
     lib.seedb200_launch_count.restype = C.c_int64
     lib.seedb200_reset_launch_count.restype = None
+    lib.seedb200_profile_end.argtypes = [C.POINTER(C.c_double)]
     lib.seedb200_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     lib.seedb200_layernorm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_int, C.c_int, C.c_float, C.c_void_p]
@@ -152,6 +154,18 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     load().seedb200_reset_launch_count()
+
+
+def profile_begin() -> None:
+    check(load().seedb200_profile_begin(), "seedb200_profile_begin")
+
+
+def profile_end() -> dict:
+    """-> {"gemm": {"launches", "ms", "flops"}, "attention": {...}} for the kernels launched since profile_begin()."""
+    out = (C.c_double * 6)()
+    check(load().seedb200_profile_end(out), "seedb200_profile_end")
+    return {"gemm": {"launches": int(out[0]), "ms": out[1], "flops": out[2]},
+            "attention": {"launches": int(out[3]), "ms": out[4], "flops": out[5]}}
 
 
 # --------------------------------------------------------------------------------------------------
