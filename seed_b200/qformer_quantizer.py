@@ -18,8 +18,9 @@ from . import lib as L
 
 # state-dict prefixes of the reference model that the inference path never reads
 # (recon_s branch `pos_embed`/`blocks.*`, BERT text branch, LM head): qformer_quantizer.py:206-211,238-250
-_UNUSED_PREFIXES = ("pos_embed", "blocks.", "Qformer.cls", "Qformer.bert.embeddings.word_embeddings",
+_UNUSED_PREFIXES = ("blocks.", "Qformer.cls", "Qformer.bert.embeddings.word_embeddings",
                     "Qformer.bert.embeddings.position_embeddings", "Qformer.bert.embeddings.position_ids")
+_UNUSED_KEYS = ("pos_embed",)
 _UNUSED_RE = re.compile(r"^Qformer\.bert\.encoder\.layer\.\d+\.(intermediate|output)\.")
 
 
@@ -49,7 +50,8 @@ class Blip2QformerQuantizer(nn.Module):
         dev = torch.device(device)
         if dev.type != "cuda" or not torch.cuda.is_available():
             raise RuntimeError("Blip2QformerQuantizer (seed_b200) needs a CUDA device: there is no CPU path")
-        used = {k: v for k, v in state_dict.items() if not k.startswith(_UNUSED_PREFIXES) and not _UNUSED_RE.match(k)}
+        used = {k: v for k, v in state_dict.items()
+                if k not in _UNUSED_KEYS and not k.startswith(_UNUSED_PREFIXES) and not _UNUSED_RE.match(k)}
         self.vit_depth = _depth(used, r"visual_encoder\.blocks\.(\d+)\.")
         self.qformer_layers = _depth(used, r"Qformer\.bert\.encoder\.layer\.(\d+)\.")
         self.detok_depth = _depth(used, r"blocks_image\.(\d+)\.")

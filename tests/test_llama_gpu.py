@@ -65,6 +65,11 @@ def test_prefill_decode_consistency_and_foreign_past():
         ref_logits, _, ref_past = R.llama_forward(sd, ids, heads, layers)
     out = model(input_ids=ids.cuda(), use_cache=True)
     assert rel(out.logits, ref_logits) <= LOGIT_TOL
+    # chunked prefill continuing from the handle's own cache
+    out_a1 = model(input_ids=ids[:, :100].cuda(), use_cache=True)
+    assert rel(out_a1.logits, ref_logits[:, :100]) <= LOGIT_TOL
+    out_a2 = model(input_ids=ids[:, 100:].cuda(), past_key_values=out_a1.past_key_values, use_cache=True)
+    assert rel(out_a2.logits, ref_logits[:, 100:]) <= LOGIT_TOL, rel(out_a2.logits, ref_logits[:, 100:])
     # chunked prefill with a past computed by the ORACLE (foreign tensors are copied into the cache)
     with torch.no_grad():
         _, _, past100 = R.llama_forward(sd, ids[:, :100], heads, layers)

@@ -197,6 +197,8 @@ ATTN_CASES = [
     (1, 4, 300, 300, 128, True),      # LLaMA prefill
     (2, 2, 2048, 2048, 128, True),
     (1, 2, 5, 133, 128, True),        # chunked prefill with past: bottom-right aligned causal
+    (2, 8, 100, 200, 128, True),      # 100 new tokens after a 100-token past (8-warp tile, nk != nq)
+    (1, 2, 130, 300, 128, True),
     (1, 3, 1, 77, 128, False),        # single query through the prefill kernel
     (1, 2, 100, 100, 64, False),
 ]
