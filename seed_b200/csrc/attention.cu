@@ -56,6 +56,12 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {   // ex2.approx: -inf -> +0, 2 ulp
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 constexpr int ATT_BK = 64;
 
 // Load `rows` rows x head_dim halves (row stride ts elements) into smem rows of LDS halves; rows >= valid
@@ -74,7 +80,7 @@ __device__ __forceinline__ void load_tile_async(uint32_t smem, const __half* gba
 }
 
 template <int DPAD, int NW>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, (NW * 32 <= 288 && DPAD <= 96) ? 2 : 1)
 attn_fwd_kernel(const AttnParams p) {
   constexpr int BQ = NW * 16;
   constexpr int LDS = DPAD + 8;            // padded row stride (halves): conflict-free ldmatrix
@@ -125,13 +131,18 @@ attn_fwd_kernel(const AttnParams p) {
   for (int i = 0; i < DPAD / 8; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.0f; }
   float m_run[2] = {-INFINITY, -INFINITY};
   float l_run[2] = {0.0f, 0.0f};
-  uint32_t qf[KSTEPS][4];
 
   const int row_lo = q0 + warp * 16 + (lane >> 2);   // this thread's two query rows
   const int row_hi = row_lo + 8;
+  const int warp_row_max = q0 + warp * 16 + 15;
+  const uint32_t q_frag_addr = sQ_a + (uint32_t)((warp * 16 + (lane & 15)) * LDS + (lane >> 4) * 8) * 2u;
 
   for (int kt = 0; kt < n_ktiles; ++kt) {
     const int buf = kt & 1;
+    // one barrier per tile: tile kt has landed and is visible, and every warp is done with tile kt-1, whose
+    // buffer is refilled right below while tile kt is being consumed
+    cp_async_wait<0>();
+    __syncthreads();
     if (kt + 1 < n_ktiles) {
       const int nb = buf ^ 1;
       load_tile_async<LDS>(sK_a + nb * ATT_BK * LDS * 2, kg, p.k_ts, (kt + 1) * ATT_BK, ATT_BK, p.nk, chunks, tid,
@@ -139,19 +150,16 @@ attn_fwd_kernel(const AttnParams p) {
       load_tile_async<LDS>(sV_a + nb * ATT_BK * LDS * 2, vg, p.v_ts, (kt + 1) * ATT_BK, ATT_BK, p.nk, chunks, tid,
                            NTHREADS);
       cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
     }
-    __syncthreads();
 
-    if (kt == 0) {
-#pragma unroll
-      for (int ks = 0; ks < KSTEPS; ++ks) {
-        const uint32_t a = sQ_a + (uint32_t)((warp * 16 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8) * 2u;
-        ldsm_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], a);
-      }
-    }
+    // keys of this tile that exist / that this warp may see (a ragged last tile only pays for what it holds:
+    // 257 keys = 4 full tiles + 1 key, not 5 tiles)
+    const int key0 = kt * ATT_BK;
+    int valid = min(ATT_BK, p.nk - key0);
+    if (p.causal) valid = min(valid, warp_row_max + causal_off + 1 - key0);
+    if (valid <= 0) continue;                         // warp-uniform
+    const int npairs = (valid + 15) >> 4;             // 16-key groups to compute (1..4)
+    const bool need_mask = (valid < ATT_BK) || (p.causal && key0 + ATT_BK - 1 > q0 + warp * 16 + causal_off);
 
     // ---- S = Q K^T for this warp's 16 rows x 64 keys ----
     float s[8][4];
@@ -160,32 +168,47 @@ attn_fwd_kernel(const AttnParams p) {
     const uint32_t kbase = sK_a + buf * ATT_BK * LDS * 2;
 #pragma unroll
     for (int ks = 0; ks < KSTEPS; ++ks) {
+      uint32_t qf[4];
+      ldsm_x4(qf[0], qf[1], qf[2], qf[3], q_frag_addr + ks * 32);
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
-        const int mi = lane >> 3;
-        const int key = np * 16 + (mi >> 1) * 8 + (lane & 7);
-        const int dcol = ks * 16 + (mi & 1) * 8;
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4(b0, b1, b2, b3, kbase + (uint32_t)(key * LDS + dcol) * 2u);
-        mma16816(s[2 * np], qf[ks], b0, b1);
-        mma16816(s[2 * np + 1], qf[ks], b2, b3);
+        if (np < npairs) {
+          const int mi = lane >> 3;
+          const int key = np * 16 + (mi >> 1) * 8 + (lane & 7);
+          const int dcol = ks * 16 + (mi & 1) * 8;
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(b0, b1, b2, b3, kbase + (uint32_t)(key * LDS + dcol) * 2u);
+          mma16816(s[2 * np], qf, b0, b1);
+          mma16816(s[2 * np + 1], qf, b2, b3);
+        }
       }
     }
 
     // ---- scale, mask, online softmax ----
-    const int kcol0 = kt * ATT_BK + (lane & 3) * 2;
     float mx[2] = {-INFINITY, -INFINITY};
+    if (need_mask) {
+      const int kcol0 = key0 + (lane & 3) * 2;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = kcol0 + nt * 8 + (e & 1);
-        const int row = (e < 2) ? row_lo : row_hi;
-        float val = s[nt][e] * p.scale_log2;
-        const bool masked = (col >= p.nk) || (p.causal && col > row + causal_off);
-        val = masked ? -INFINITY : val;
-        s[nt][e] = val;
-        mx[e >> 1] = fmaxf(mx[e >> 1], val);
+        for (int e = 0; e < 4; ++e) {
+          const int col = kcol0 + nt * 8 + (e & 1);
+          const int row = (e < 2) ? row_lo : row_hi;
+          const bool masked = (col >= p.nk) || (p.causal && col > row + causal_off);
+          const float val = masked ? -INFINITY : s[nt][e] * p.scale_log2;
+          s[nt][e] = val;
+          mx[e >> 1] = fmaxf(mx[e >> 1], val);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float val = s[nt][e] * p.scale_log2;
+          s[nt][e] = val;
+          mx[e >> 1] = fmaxf(mx[e >> 1], val);
+        }
       }
     }
     float corr[2], m_use[2];
@@ -195,7 +218,7 @@ attn_fwd_kernel(const AttnParams p) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float m_new = fmaxf(m_run[r], mx[r]);
       m_use[r] = (m_new == -INFINITY) ? 0.0f : m_new;
-      corr[r] = exp2f(m_run[r] - m_use[r]);     // m_run = -inf -> 0
+      corr[r] = fast_exp2(m_run[r] - m_use[r]);     // m_run = -inf -> 0
       m_run[r] = m_new;
       l_run[r] *= corr[r];
     }
@@ -203,10 +226,10 @@ attn_fwd_kernel(const AttnParams p) {
     uint32_t pf[4][4];   // P as A fragments for 4 key-steps of 16
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = exp2f(s[nt][0] - m_use[0]);
-      const float p1 = exp2f(s[nt][1] - m_use[0]);
-      const float p2 = exp2f(s[nt][2] - m_use[1]);
-      const float p3 = exp2f(s[nt][3] - m_use[1]);
+      const float p0 = fast_exp2(s[nt][0] - m_use[0]);
+      const float p1 = fast_exp2(s[nt][1] - m_use[0]);
+      const float p2 = fast_exp2(s[nt][2] - m_use[1]);
+      const float p3 = fast_exp2(s[nt][3] - m_use[1]);
       // the reference rounds the probabilities to fp16 before P.V (autocast, eva_vit.py:155-156);
       // accumulate the row sum from the rounded values so that sum(P)/l is consistent
       const __half2 h01 = __floats2half2_rn(p0, p1);
@@ -235,18 +258,19 @@ attn_fwd_kernel(const AttnParams p) {
     const uint32_t vbase = sV_a + buf * ATT_BK * LDS * 2;
 #pragma unroll
     for (int ks2 = 0; ks2 < 4; ++ks2) {
+      if (ks2 < npairs) {
 #pragma unroll
-      for (int dp = 0; dp < DPAD / 16; ++dp) {
-        const int mi = lane >> 3;
-        const int key = ks2 * 16 + (mi & 1) * 8 + (lane & 7);
-        const int dcol = dp * 16 + (mi >> 1) * 8;
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4_t(b0, b1, b2, b3, vbase + (uint32_t)(key * LDS + dcol) * 2u);
-        mma16816(o_acc[2 * dp], pf[ks2], b0, b1);
-        mma16816(o_acc[2 * dp + 1], pf[ks2], b2, b3);
+        for (int dp = 0; dp < DPAD / 16; ++dp) {
+          const int mi = lane >> 3;
+          const int key = ks2 * 16 + (mi & 1) * 8 + (lane & 7);
+          const int dcol = dp * 16 + (mi >> 1) * 8;
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t(b0, b1, b2, b3, vbase + (uint32_t)(key * LDS + dcol) * 2u);
+          mma16816(o_acc[2 * dp], pf[ks2], b0, b1);
+          mma16816(o_acc[2 * dp + 1], pf[ks2], b2, b3);
+        }
       }
     }
-    __syncthreads();   // all warps done with this buffer before it is refilled
   }
 
   // ---- finalize: quad-reduce the row sums, normalise, store ----
@@ -280,6 +304,8 @@ static int launch_attn(const seedb200_attn_desc& d, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // ask for the full shared-memory carve-out so that two CTAs of the 83 KB ViT tile are co-resident
+    SB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
   AttnParams p;

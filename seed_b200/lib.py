@@ -249,8 +249,9 @@ def vq_argmin(z: torch.Tensor, codebook: torch.Tensor, mode: int = VQ_FP16) -> t
 def patchify(images: torch.Tensor, kpad: int = 592) -> torch.Tensor:
     _need_cuda_f16(images, "patchify.images")
     B = images.shape[0]
+    images = images.contiguous()
     cols = torch.empty((B * 256, kpad), dtype=torch.float16, device=images.device)
-    check(load().seedb200_patchify(images.contiguous().data_ptr(), B, cols.data_ptr(), kpad, stream_ptr()),
+    check(load().seedb200_patchify(images.data_ptr(), B, cols.data_ptr(), kpad, stream_ptr()),
           "seedb200_patchify")
     return cols
 
@@ -423,8 +424,10 @@ class Llama:
 
     def kv_load(self, layer: int, k: torch.Tensor, v: torch.Tensor) -> None:
         B, H, P, D = k.shape
-        check(load().seedb200_llama_kv_load(self._h, layer, k.contiguous().data_ptr(), v.contiguous().data_ptr(), B,
-                                            P, stream_ptr()), "seedb200_llama_kv_load")
+        kc, vc = k.contiguous(), v.contiguous()   # keep BOTH alive across the call: two unnamed temporaries would
+        # be freed immediately and the caching allocator hands the second one the first one's block
+        check(load().seedb200_llama_kv_load(self._h, layer, kc.data_ptr(), vc.data_ptr(), B, P, stream_ptr()),
+              "seedb200_llama_kv_load")
 
     def tap_hidden(self, T: int) -> torch.Tensor:
         out = torch.empty((T, self.hidden), dtype=torch.float16, device=self.device)
