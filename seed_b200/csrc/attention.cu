@@ -325,6 +325,10 @@ static int launch_attn(const seedb200_attn_desc& d, cudaStream_t stream) {
   return 0;
 }
 
+bool vit_attention_tc_applicable(const seedb200_attn_desc& d);
+int vit_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream);
+int get_option(const char* key);
+
 int attention(const seedb200_attn_desc& d, cudaStream_t stream) {
   SB_REQUIRE(d.q && d.k && d.v && d.o, "attention: null operand");
   SB_REQUIRE(d.batch > 0 && d.heads > 0 && d.nq > 0 && d.nk > 0, "attention: empty problem");
@@ -339,6 +343,7 @@ int attention(const seedb200_attn_desc& d, cudaStream_t stream) {
   SB_REQUIRE(((uintptr_t)d.q % 16 == 0) && ((uintptr_t)d.k % 16 == 0) && ((uintptr_t)d.v % 16 == 0) &&
                  ((uintptr_t)d.o % 4 == 0),
              "attention: misaligned pointer");
+  if (vit_attention_tc_applicable(d) && get_option("vit_attention_tc") != 0) return vit_attention_tc(d, stream);
   if (d.head_dim == 64) {
     if (d.nq <= 32) return launch_attn<64, 2>(d, stream);
     return launch_attn<64, 4>(d, stream);

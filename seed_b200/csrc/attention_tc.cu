@@ -1,0 +1,326 @@
+// attention_tc.cu -- ViT-g/14 attention (257 x 257 tokens, 16 heads x 88) on the 5th-gen tensor cores.
+//
+// Replaces eva_vit.py:139-156 (`attn = softmax(q*scale @ k^T); x = attn @ v`) for the shape that is 23% of the
+// encode step on the mma.sync kernel (attention.cu) although it is only 2.8% of its FLOPs.
+//
+// One persistent CTA per SM walks (image, head) items.  Per item:
+//   * all 8 compute warps stage Q, K (K-major, head_dim zero-padded 88 -> 96) and V^T (transposed on the fly
+//     so that keys become the contraction dimension) into shared memory in the canonical NON-swizzled UMMA
+//     layout (8 x 16-byte core matrices; LBO = 128 B along K, SBO between 8-row groups).  No swizzle is what
+//     lets 88/257 be padded freely with plain stores;
+//   * for each 128-row query tile: one thread issues S = Q K^T as tcgen05.mma 128x256x16 + 128x16x16 into TMEM
+//     (272 fp32 columns), the compute warps (one row per thread, two warps per TMEM lane quarter splitting
+//     the columns) run an exact two-pass fp32 softmax straight out of TMEM (tcgen05.ld), write P (fp16, as
+//     the reference rounds it under autocast) back to shared memory in the same canonical layout, the
+//     issuer runs O = P V (128x96x16 x 17) into 96 more TMEM columns, and the compute warps normalise and
+//     store O.
+// Synchronisation: tcgen05.commit -> mbarrier for "S ready" / "O ready", mbarrier arrives (one per compute
+// warp) for "P written" / "TMEM free", fence.proxy.async between generic-proxy smem writes and UMMA reads.
+#include "common.cuh"
+#include "ops.h"
+
+namespace sb {
+
+constexpr int VA_D = 88, VA_DP = 96, VA_N = 257, VA_KP = 272;
+constexpr int VA_SBO_QK = (VA_DP / 8) * 128;       // 1536: bytes between 8-row groups of Q / K
+constexpr int VA_SBO_PV = (VA_KP / 8) * 128;       // 4352: bytes between 8-row groups of P / V^T
+constexpr int VA_Q_BYTES = 33 * VA_SBO_QK;         // 264 rows
+constexpr int VA_K_BYTES = 33 * VA_SBO_QK;
+constexpr int VA_V_BYTES = (VA_DP / 8) * VA_SBO_PV;   // 96 d-rows x 272 keys
+constexpr int VA_P_BYTES = 16 * VA_SBO_PV;            // 128 rows x 272 keys
+constexpr int VA_MISC_BYTES = 4 * 128 * 4 + 64;       // max/sum exchange + barriers + tmem slot
+constexpr int VA_SMEM = VA_Q_BYTES + VA_K_BYTES + VA_V_BYTES + VA_P_BYTES + VA_MISC_BYTES + 128;
+constexpr int VA_THREADS = 288;                       // 8 compute warps + 1 MMA warp
+constexpr int VA_TMEM_COLS = 512;
+constexpr int VA_O_COL = 272;
+
+struct VitAttnParams {
+  const __half* q; const __half* k; const __half* v; __half* o;
+  long long q_bs, q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, o_bs, o_hs, o_ts;
+  int items, heads;
+  float scale_log2;
+};
+
+// K-major, no swizzle: LBO (K direction) = 128 B, SBO (M/N direction) given
+__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t addr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(128 >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, float& sum) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  sum += f.x + f.y;
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(VA_THREADS, 1)
+vit_attention_tc_kernel(const VitAttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base, sK = sQ + VA_Q_BYTES, sV = sK + VA_K_BYTES, sP = sV + VA_V_BYTES;
+  const uint32_t misc = sP + VA_P_BYTES;
+  float* s_max = reinterpret_cast<float*>(gen + (misc - base));     // [2][128]
+  float* s_sum = s_max + 256;                                       // [2][128]
+  const uint32_t bar_s = misc + 2048, bar_p = bar_s + 8, bar_o = bar_s + 16, bar_free = bar_s + 24;
+  const uint32_t tmem_slot = bar_s + 32;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 8);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_free, 8);
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc<1>(tmem_slot, VA_TMEM_COLS);
+  // zero Q, K, V^T once: the padding (head_dim 88..95, keys 257..271) is never written afterwards
+  for (uint32_t off = tid * 16; off < (uint32_t)(VA_Q_BYTES + VA_K_BYTES + VA_V_BYTES); off += VA_THREADS * 16)
+    *reinterpret_cast<uint4*>(gen + off) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  constexpr uint32_t IDESC_S256 = make_idesc_f16(128, 256);
+  constexpr uint32_t IDESC_S16 = make_idesc_f16(128, 16);
+  constexpr uint32_t IDESC_O = make_idesc_f16(128, VA_DP);
+
+  uint32_t tile_ctr = 0;   // every mbarrier completes exactly once per tile: parity = tile_ctr & 1
+  for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    const int b = item / p.heads, h = item - b * p.heads;
+    // ---------------- stage Q, K, V^T (compute warps) ----------------
+    if (warp < 8) {
+      const __half* qg = p.q + b * p.q_bs + h * p.q_hs;
+      const __half* kg = p.k + b * p.k_bs + h * p.k_hs;
+      const __half* vg = p.v + b * p.v_bs + h * p.v_hs;
+      constexpr int CH = VA_D / 8;   // 11 16-byte chunks per row
+      for (int i = tid; i < VA_N * CH; i += 256) {
+        const int r = i / CH, c = i - r * CH;
+        const uint4 qv = __ldg(reinterpret_cast<const uint4*>(qg + (long long)r * p.q_ts + c * 8));
+        const uint4 kv = __ldg(reinterpret_cast<const uint4*>(kg + (long long)r * p.k_ts + c * 8));
+        const uint32_t off = (uint32_t)(r >> 3) * VA_SBO_QK + c * 128 + (r & 7) * 16;
+        *reinterpret_cast<uint4*>(gen + (sQ - base) + off) = qv;
+        *reinterpret_cast<uint4*>(gen + (sK - base) + off) = kv;
+      }
+      // V^T: thread <-> (chunk c, key): consecutive lanes take consecutive keys
+      for (int i = tid; i < VA_N * CH; i += 256) {
+        const int c = i / VA_N, key = i - c * VA_N;
+        const uint4 vv = __ldg(reinterpret_cast<const uint4*>(vg + (long long)key * p.v_ts + c * 8));
+        const __half* hv = reinterpret_cast<const __half*>(&vv);
+        __half* dst = reinterpret_cast<__half*>(gen + (sV - base) + (uint32_t)c * VA_SBO_PV + (key >> 3) * 128 + (key & 7) * 2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j * 8] = hv[j];     // d = c*8 + j -> +16 bytes per d row
+      }
+      fence_proxy_async_smem();
+    }
+    __syncthreads();
+
+    for (int t = 0; t < 3; ++t, ++tile_ctr) {
+      const uint32_t par = tile_ctr & 1;
+      if (warp == 8) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+          if (tile_ctr > 0) mbar_wait(bar_free, (tile_ctr - 1) & 1);   // S/O/P of the previous tile consumed
+          tc_fence_after();
+          const uint32_t qa = sQ + (uint32_t)t * 16 * VA_SBO_QK;
+#pragma unroll
+          for (int j = 0; j < VA_DP / 16; ++j)
+            umma_f16<1>(tmem, make_desc_nosw(qa + j * 256, VA_SBO_QK), make_desc_nosw(sK + j * 256, VA_SBO_QK),
+                        IDESC_S256, j > 0);
+#pragma unroll
+          for (int j = 0; j < VA_DP / 16; ++j)
+            umma_f16<1>(tmem + 256, make_desc_nosw(qa + j * 256, VA_SBO_QK),
+                        make_desc_nosw(sK + 32 * VA_SBO_QK + j * 256, VA_SBO_QK), IDESC_S16, j > 0);
+          umma_commit<1>(bar_s);
+          mbar_wait(bar_p, par);
+          tc_fence_after();
+#pragma unroll
+          for (int j = 0; j < VA_KP / 16; ++j)
+            umma_f16<1>(tmem + VA_O_COL, make_desc_nosw(sP + j * 256, VA_SBO_PV), make_desc_nosw(sV + j * 256, VA_SBO_PV),
+                        IDESC_O, j > 0);
+          umma_commit<1>(bar_o);
+        }
+        __syncwarp();
+      } else {
+        // ======================= softmax + epilogue =======================
+        const int quarter = warp & 3, hf = warp >> 2;
+        const int rl = quarter * 32 + lane;               // row inside the tile
+        const int row = t * 128 + rl;
+        const bool warp_live = (t * 128 + quarter * 32) < VA_N;   // warp-uniform
+        const bool valid = row < VA_N;
+        const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+        mbar_wait(bar_s, par);
+        tc_fence_after();
+        float mx = -INFINITY;
+        if (warp_live) {
+          // pass 1: row maximum over this warp's half of the keys
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld32(trow + hf * 128 + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+          }
+          if (hf == 1) {
+            uint32_t r[16];
+            tmem_ld16(trow + 256, r);
+            tmem_ld_wait();
+            mx = fmaxf(mx, __uint_as_float(r[0]));        // key 256; columns 257..271 are padding
+          }
+        }
+        s_max[hf * 128 + rl] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float m = fmaxf(s_max[rl], s_max[128 + rl]) * p.scale_log2;   // scale > 0
+        float sum = 0.0f;
+        if (warp_live) {
+          // pass 2: P = exp2(s*scale*log2e - m), rounded to fp16, into the canonical K-major layout
+          uint8_t* prow = gen + (sP - base) + (uint32_t)(rl >> 3) * VA_SBO_PV + (rl & 7) * 16;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld32(trow + hf * 128 + c * 32, r);
+            tmem_ld_wait();
+            const int kc0 = (hf * 128 + c * 32) >> 3;     // first 8-key core matrix of this chunk
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 o;
+              o.x = pack2(ex2f(fmaf(__uint_as_float(r[g * 8 + 0]), p.scale_log2, -m)),
+                          ex2f(fmaf(__uint_as_float(r[g * 8 + 1]), p.scale_log2, -m)), sum);
+              o.y = pack2(ex2f(fmaf(__uint_as_float(r[g * 8 + 2]), p.scale_log2, -m)),
+                          ex2f(fmaf(__uint_as_float(r[g * 8 + 3]), p.scale_log2, -m)), sum);
+              o.z = pack2(ex2f(fmaf(__uint_as_float(r[g * 8 + 4]), p.scale_log2, -m)),
+                          ex2f(fmaf(__uint_as_float(r[g * 8 + 5]), p.scale_log2, -m)), sum);
+              o.w = pack2(ex2f(fmaf(__uint_as_float(r[g * 8 + 6]), p.scale_log2, -m)),
+                          ex2f(fmaf(__uint_as_float(r[g * 8 + 7]), p.scale_log2, -m)), sum);
+              if (valid) *reinterpret_cast<uint4*>(prow + (kc0 + g) * 128) = o;
+            }
+          }
+          if (hf == 1) {
+            uint32_t r[16];
+            tmem_ld16(trow + 256, r);
+            tmem_ld_wait();
+            float dummy = 0.0f;
+            uint4 o = make_uint4(0, 0, 0, 0);
+            o.x = pack2(ex2f(fmaf(__uint_as_float(r[0]), p.scale_log2, -m)), 0.0f, sum);
+            (void)dummy;
+            if (valid) {
+              *reinterpret_cast<uint4*>(prow + 32 * 128) = o;                       // keys 256..263
+              *reinterpret_cast<uint4*>(prow + 33 * 128) = make_uint4(0, 0, 0, 0);  // keys 264..271
+            }
+          }
+        }
+        s_sum[hf * 128 + rl] = sum;
+        fence_proxy_async_smem();     // P (generic-proxy stores) must be visible to the tensor core
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p);
+
+        mbar_wait(bar_o, par);
+        tc_fence_after();
+        if (warp_live) {
+          const float total = s_sum[rl] + s_sum[128 + rl];
+          const float inv = total > 0.0f ? 1.0f / total : 0.0f;
+          uint32_t r0[32], r1[16];
+          // hf 0: output dims 0..47, hf 1: 48..95 (only 48..87 exist)
+          tmem_ld32(trow + VA_O_COL + hf * 48, r0);
+          tmem_ld16(trow + VA_O_COL + hf * 48 + 32, r1);
+          tmem_ld_wait();
+          if (valid) {
+            __half* og = p.o + b * p.o_bs + h * p.o_hs + (long long)row * p.o_ts + hf * 48;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 o;
+              float unused = 0.0f;
+              o.x = pack2(__uint_as_float(r0[g * 8 + 0]) * inv, __uint_as_float(r0[g * 8 + 1]) * inv, unused);
+              o.y = pack2(__uint_as_float(r0[g * 8 + 2]) * inv, __uint_as_float(r0[g * 8 + 3]) * inv, unused);
+              o.z = pack2(__uint_as_float(r0[g * 8 + 4]) * inv, __uint_as_float(r0[g * 8 + 5]) * inv, unused);
+              o.w = pack2(__uint_as_float(r0[g * 8 + 6]) * inv, __uint_as_float(r0[g * 8 + 7]) * inv, unused);
+              *reinterpret_cast<uint4*>(og + g * 8) = o;
+            }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              if (hf == 0 || g == 0) {     // dims 80..87 exist, 88..95 are padding
+                uint4 o;
+                float unused = 0.0f;
+                o.x = pack2(__uint_as_float(r1[g * 8 + 0]) * inv, __uint_as_float(r1[g * 8 + 1]) * inv, unused);
+                o.y = pack2(__uint_as_float(r1[g * 8 + 2]) * inv, __uint_as_float(r1[g * 8 + 3]) * inv, unused);
+                o.z = pack2(__uint_as_float(r1[g * 8 + 4]) * inv, __uint_as_float(r1[g * 8 + 5]) * inv, unused);
+                o.w = pack2(__uint_as_float(r1[g * 8 + 6]) * inv, __uint_as_float(r1[g * 8 + 7]) * inv, unused);
+                *reinterpret_cast<uint4*>(og + 32 + g * 8) = o;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_free);
+      }
+    }
+    // the next item's staging overwrites Q/K/V^T: every MMA of this item has retired (the compute warps
+    // waited on bar_o of the last tile); make the whole CTA agree before touching shared memory again
+    __syncthreads();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<1>(tmem, VA_TMEM_COLS);
+}
+
+bool vit_attention_tc_applicable(const seedb200_attn_desc& d) {
+  return d.head_dim == VA_D && d.nq == VA_N && d.nk == VA_N && d.causal == 0 && d.o_hs % 8 == 0 && d.o_ts % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(d.o) & 15) == 0;
+}
+
+int vit_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SB_CHECK_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VA_SMEM));
+    attr_set = true;
+  }
+  VitAttnParams p;
+  p.q = static_cast<const __half*>(d.q); p.k = static_cast<const __half*>(d.k);
+  p.v = static_cast<const __half*>(d.v); p.o = static_cast<__half*>(d.o);
+  p.q_bs = d.q_bs; p.q_hs = d.q_hs; p.q_ts = d.q_ts;
+  p.k_bs = d.k_bs; p.k_hs = d.k_hs; p.k_ts = d.k_ts;
+  p.v_bs = d.v_bs; p.v_hs = d.v_hs; p.v_ts = d.v_ts;
+  p.o_bs = d.o_bs; p.o_hs = d.o_hs; p.o_ts = d.o_ts;
+  p.items = d.batch * d.heads; p.heads = d.heads;
+  p.scale_log2 = d.scale * 1.4426950408889634f;
+  int grid = num_sms();
+  if (grid > p.items) grid = p.items;
+  profile_mark_begin(1, stream);
+  vit_attention_tc_kernel<<<grid, VA_THREADS, VA_SMEM, stream>>>(p);
+  profile_mark_end(1, stream, 4.0 * (double)d.batch * d.heads * (double)d.nq * d.nk * d.head_dim);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace sb

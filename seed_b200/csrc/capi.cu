@@ -5,6 +5,7 @@
 
 #include <map>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -22,6 +23,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+int set_option(const char* key, int value);
 
 struct ProfRec { cudaEvent_t a, b; int kind; double flops; };
 static thread_local bool g_prof_on = false;
@@ -41,6 +43,24 @@ void profile_mark_end(int kind, cudaStream_t stream, double flops) {
   ProfRec& r = g_prof->back();
   r.flops = flops;
   cudaEventRecord(r.b, stream);
+}
+
+static std::map<std::string, int>& options() {
+  static std::map<std::string, int> o = {{"vit_attention_tc", 1}};
+  return o;
+}
+int get_option(const char* key) {
+  auto it = options().find(key);
+  return it == options().end() ? 0 : it->second;
+}
+int set_option(const char* key, int value) {
+  auto it = options().find(key);
+  if (it == options().end()) {
+    set_error("unknown option '%s'", key);
+    return SEEDB200_ERR_INVALID;
+  }
+  it->second = value;
+  return 0;
 }
 
 int num_sms() {
@@ -89,6 +109,14 @@ int seedb200_version(void) { return SEEDB200_VERSION; }
 const char* seedb200_last_error(void) { return sb::g_err; }
 int64_t seedb200_launch_count(void) { return sb::g_launches; }
 void seedb200_reset_launch_count(void) { sb::g_launches = 0; }
+
+int seedb200_set_option(const char* key, int value) {
+  if (key == nullptr) {
+    sb::set_error("set_option: null key");
+    return SEEDB200_ERR_INVALID;
+  }
+  return sb::set_option(key, value);
+}
 
 int seedb200_profile_begin(void) {
   if (sb::g_prof == nullptr) sb::g_prof = new std::vector<sb::ProfRec>();

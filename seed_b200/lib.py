@@ -21,7 +21,7 @@ VQ_FP16, VQ_FP32 = 0, 1
 # every symbol include/seedb200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "seedb200_version", "seedb200_last_error", "seedb200_launch_count", "seedb200_reset_launch_count",
-    "seedb200_profile_begin", "seedb200_profile_end",
+    "seedb200_profile_begin", "seedb200_profile_end", "seedb200_set_option",
     "seedb200_gemm", "seedb200_layernorm", "seedb200_rmsnorm", "seedb200_attention", "seedb200_vq_argmin",
     "seedb200_patchify", "seedb200_rope_kv_append", "seedb200_embedding",
     "seedb200_encoder_create", "seedb200_encoder_destroy", "seedb200_encoder_encode",
@@ -154,6 +154,12 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     load().seedb200_reset_launch_count()
+
+
+def set_option(key: str, value: int) -> None:
+    lib = load()
+    lib.seedb200_set_option.argtypes = [C.c_char_p, C.c_int]
+    check(lib.seedb200_set_option(key.encode(), int(value)), "seedb200_set_option")
 
 
 def profile_begin() -> None:

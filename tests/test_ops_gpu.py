@@ -218,6 +218,26 @@ def test_attention(lib, B, H, Nq, Nk, D, causal):
     assert (o.float() - ref.float()).abs().max().item() < 1e-2
 
 
+@pytest.mark.parametrize("use_tc", [1, 0])
+@pytest.mark.parametrize("B", [1, 5, 40])
+def test_vit_attention_tcgen05_vs_mma_paths(lib, B, use_tc):
+    """the 257x257x88 ViT shape on the tcgen05 kernel (attention_tc.cu) and on the mma.sync kernel; B=40 gives
+    640 (image, head) items so every persistent CTA walks several of them"""
+    H, N, D = 16, 257, 88
+    qkv = rand16(B * N, 3 * H * D, seed=34)
+    v4 = qkv.view(B, N, 3, H, D)
+    q, k, v = (v4[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    lib.set_option("vit_attention_tc", use_tc)
+    try:
+        o = lib.attention(q, k, v, D ** -0.5, False)
+        torch.cuda.synchronize()
+    finally:
+        lib.set_option("vit_attention_tc", 1)
+    ref = R.attention_ref(q, k, v, D ** -0.5, False)
+    assert rel_err(o, ref) < 2e-3, rel_err(o, ref)
+    assert (o.float() - ref.float()).abs().max().item() < 1e-2
+
+
 def test_attention_strided_qkv_layout(lib):
     """the ViT layout: q/k/v are column slices of one [B*257, 4224] GEMM output."""
     B, H, N, D = 2, 16, 257, 88
