@@ -43,11 +43,16 @@ struct GemmParams {
   int res_mod, res_offset;
 };
 
-template <int BN, int CTAS>
+// KSUB: 64-wide K sub-blocks per pipeline stage.  KSUB = 2 halves the per-stage fixed cost in the MMA issuer
+// (one mbarrier wait + one tcgen05.commit per 8 MMAs instead of per 4), which is what bounded the
+// short-N tiles (ncu: tensor pipe 64% active with neither operands nor the epilogue late).
+template <int BN, int CTAS, int KSUB = 2>
 struct GemmCfg {
   static constexpr int LOAD_N = BN / CTAS;
-  static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
-  static constexpr int B_BYTES = LOAD_N * GEMM_BLOCK_K * 2;
+  static constexpr int A_SUB = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;      // one 64-wide sub-block of A
+  static constexpr int B_SUB = LOAD_N * GEMM_BLOCK_K * 2;
+  static constexpr int A_BYTES = KSUB * A_SUB;
+  static constexpr int B_BYTES = KSUB * B_SUB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -57,9 +62,9 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + BAR_BYTES;
   // keep one CTA per SM (TMEM is allocated per CTA): request more than half of the SM's smem
   static constexpr int SMEM_REQUEST = SMEM_BYTES < 120 * 1024 ? 120 * 1024 : SMEM_BYTES;
-  static_assert(B_BYTES % 1024 == 0, "W stage must keep 1024-byte alignment for SWIZZLE_128B");
+  static_assert(B_SUB % 1024 == 0, "W stage must keep 1024-byte alignment for SWIZZLE_128B");
   static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
-  static_assert(STAGES >= 3, "pipeline too shallow");
+  static_assert(STAGES >= 2, "pipeline too shallow");
 };
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -176,11 +181,12 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
   }
 }
 
-template <int BN, int CTAS, int MODE>
+template <int BN, int CTAS, int MODE, int KSUB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmParams p) {
-  using Cfg = GemmCfg<BN, CTAS>;
+  using Cfg = GemmCfg<BN, CTAS, KSUB>;
+  constexpr int STAGE_K = GEMM_BLOCK_K * KSUB;
   constexpr int STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -227,7 +233,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  const int num_kb = (p.K + STAGE_K - 1) / STAGE_K;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int tile0 = (CTAS == 2) ? (blockIdx.x >> 1) : blockIdx.x;
   const int tile_step = (CTAS == 2) ? (gridDim.x >> 1) : gridDim.x;
@@ -246,13 +252,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t sb_ = smem_b + stage * Cfg::B_BYTES;
           if constexpr (CTAS == 1) {
             mbar_arrive_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
-            tma_load_2d(sa, &tmap_a, full_bar + 8 * stage, kb * GEMM_BLOCK_K, m_idx);
-            tma_load_2d(sb_, &tmap_b, full_bar + 8 * stage, kb * GEMM_BLOCK_K, n_idx);
+#pragma unroll
+            for (int ks = 0; ks < KSUB; ++ks) {
+              tma_load_2d(sa + ks * Cfg::A_SUB, &tmap_a, full_bar + 8 * stage, kb * STAGE_K + ks * GEMM_BLOCK_K, m_idx);
+              tma_load_2d(sb_ + ks * Cfg::B_SUB, &tmap_b, full_bar + 8 * stage, kb * STAGE_K + ks * GEMM_BLOCK_K, n_idx);
+            }
           } else {
             const uint32_t lead_bar = mapa_shared(full_bar + 8 * stage, 0);
             if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * Cfg::STAGE_BYTES);
-            tma_load_2d_2cta(sa, &tmap_a, lead_bar, kb * GEMM_BLOCK_K, m_idx);
-            tma_load_2d_2cta(sb_, &tmap_b, lead_bar, kb * GEMM_BLOCK_K, n_idx);
+#pragma unroll
+            for (int ks = 0; ks < KSUB; ++ks) {
+              tma_load_2d_2cta(sa + ks * Cfg::A_SUB, &tmap_a, lead_bar, kb * STAGE_K + ks * GEMM_BLOCK_K, m_idx);
+              tma_load_2d_2cta(sb_ + ks * Cfg::B_SUB, &tmap_b, lead_bar, kb * STAGE_K + ks * GEMM_BLOCK_K, n_idx);
+            }
             if (!leader) mbar_arrive_cluster(lead_bar);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -273,12 +285,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc_sw128(smem_a + stage * Cfg::A_BYTES);
-          const uint64_t bdesc = make_smem_desc_sw128(smem_b + stage * Cfg::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-            // advance 16 halves = 32 bytes inside the 128-byte swizzle atom: +2 in 16-byte units
-            umma_f16<CTAS>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int ks = 0; ks < KSUB; ++ks) {
+            const uint64_t adesc = make_smem_desc_sw128(smem_a + stage * Cfg::A_BYTES + ks * Cfg::A_SUB);
+            const uint64_t bdesc = make_smem_desc_sw128(smem_b + stage * Cfg::B_BYTES + ks * Cfg::B_SUB);
+#pragma unroll
+            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+              // advance 16 halves = 32 bytes inside the 128-byte swizzle atom: +2 in 16-byte units
+              umma_f16<CTAS>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | ks | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit<CTAS>(empty_bar + 8 * stage);            // frees the smem slot (both CTAs)
           if (kb == num_kb - 1) umma_commit<CTAS>(tfull_bar + 8 * as);  // accumulator ready
@@ -308,6 +323,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int c_end = half_id == 0 ? CH0 : NCHUNK;
     const int n_limit = (MODE == 1) ? p.N / 2 : p.N;
     const bool has_bias = (MODE == 0) && (p.bias != nullptr);
+    if (has_bias && etid < BN && tile0 < total_tiles) {
+      const int n = (tile0 % p.n_tiles) * BN + etid;
+      bias_smem[etid] = (n < p.N) ? p.bias[n] : __float2half(0.0f);
+    }
     int iter = 0;
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++iter) {
       const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
@@ -327,12 +346,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
       // stage this tile's bias in shared memory and prefetch the first residual chunk while the MMAs of
       // the tile are still running (both are global-memory latencies that used to sit in the chunk loop)
+      __half bias_next = __float2half(0.0f);
       if (has_bias) {
-        if (etid < BN) {
-          const int n = n_tile0 + etid;
-          bias_smem[as * 256 + etid] = (n < p.N) ? p.bias[n] : __float2half(0.0f);
-        }
+        // this tile's bias was staged one tile ago (or in the prologue); the barrier publishes it
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int next = tile + tile_step;
+        if (next < total_tiles && etid < BN) {     // issue the load now, consume it after the chunk loop
+          const int n = (next % p.n_tiles) * BN + etid;
+          if (n < p.N) bias_next = p.bias[n];
+        }
       }
       uint4 rn0 = make_uint4(0, 0, 0, 0), rn1 = rn0;
       bool rn_ok = false;
@@ -377,6 +399,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           epilogue_store16<MODE>(p, r0, r1, has_bias ? bias_smem + as * 256 + c * 16 : nullptr, res_row, out_row,
                                  rc_ok, rc0, rc1, n_tile0 + c * 16, n_limit);
       }
+      // stage the next tile's bias (other accumulator stage: nobody reads it until the next barrier)
+      if (has_bias && etid < BN) bias_smem[(as ^ 1) * 256 + etid] = bias_next;
     }
   }
 
@@ -428,11 +452,11 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t col
   return 0;
 }
 
-template <int BN, int CTAS, int MODE>
+template <int BN, int CTAS, int MODE, int KSUB>
 static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CTAS>;
+  using Cfg = GemmCfg<BN, CTAS, KSUB>;
   static bool attr_set = false;
-  auto kern = gemm_tcgen05_kernel<BN, CTAS, MODE>;
+  auto kern = gemm_tcgen05_kernel<BN, CTAS, MODE, KSUB>;
   if (!attr_set) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_REQUEST));
     attr_set = true;
@@ -488,6 +512,8 @@ static int pick_bn(int N, int mode) {
   return 256;
 }
 
+int get_option(const char* key);
+
 int gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   SB_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "gemm: non-positive shape M=%d N=%d K=%d", d.M, d.N, d.K);
   SB_REQUIRE(d.A && d.W && d.out, "gemm: null operand");
@@ -502,8 +528,12 @@ int gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   SB_REQUIRE(ctas == 1 || ctas == 2, "gemm: ctas must be 1 or 2 (got %d)", ctas);
   if (ctas == 2 && (bn < 64 || d.M <= GEMM_BLOCK_M)) ctas = 1;   // pairs only pay off on big tiles
 
-#define SB_GEMM_CASE(BN_, CT_, MD_) \
-  if (bn == BN_ && ctas == CT_ && d.mode == MD_) return launch_gemm<BN_, CT_, MD_>(d, stream);
+  const int ksub = (d.K > 64 && get_option("gemm_ksub") != 1) ? 2 : 1;
+#define SB_GEMM_CASE(BN_, CT_, MD_)                                                   \
+  if (bn == BN_ && ctas == CT_ && d.mode == MD_) {                                    \
+    if (ksub == 2) return launch_gemm<BN_, CT_, MD_, 2>(d, stream);                   \
+    return launch_gemm<BN_, CT_, MD_, 1>(d, stream);                                  \
+  }
   SB_GEMM_CASE(256, 1, 0) SB_GEMM_CASE(256, 2, 0)
   SB_GEMM_CASE(192, 1, 0) SB_GEMM_CASE(192, 2, 0)
   SB_GEMM_CASE(176, 1, 0) SB_GEMM_CASE(176, 2, 0)
