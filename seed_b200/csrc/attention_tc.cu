@@ -28,9 +28,9 @@ constexpr int VA_Q_BYTES = 33 * VA_SBO_QK;         // 264 rows
 constexpr int VA_K_BYTES = 33 * VA_SBO_QK;
 constexpr int VA_V_BYTES = (VA_DP / 8) * VA_SBO_PV;   // 96 d-rows x 272 keys
 constexpr int VA_P_BYTES = 16 * VA_SBO_PV;            // 128 rows x 272 keys
-constexpr int VA_MISC_BYTES = 4 * 128 * 4 + 64;       // max/sum exchange + barriers + tmem slot
+constexpr int VA_MISC_BYTES = 4 * 128 * 4 + 1088 + 64;   // max/sum exchange, row-256 probabilities, barriers, tmem slot
 constexpr int VA_SMEM = VA_Q_BYTES + VA_K_BYTES + VA_V_BYTES + VA_P_BYTES + VA_MISC_BYTES + 128;
-constexpr int VA_THREADS = 288;                       // 8 compute warps + 1 MMA warp
+constexpr int VA_THREADS = 320;                       // 8 softmax warps + MMA warp + row-256 warp
 constexpr int VA_TMEM_COLS = 512;
 constexpr int VA_O_COL = 272;
 
@@ -85,9 +85,14 @@ vit_attention_tc_kernel(const VitAttnParams p) {
   const uint32_t misc = sP + VA_P_BYTES;
   float* s_max = reinterpret_cast<float*>(gen + (misc - base));     // [2][128]
   float* s_sum = s_max + 256;                                       // [2][128]
-  const uint32_t bar_s = misc + 2048, bar_p = bar_s + 8, bar_o = bar_s + 16, bar_free = bar_s + 24;
+  float* s_cls = s_sum + 256;                                       // [272] probabilities of query row 256
+  const uint32_t bar_s = misc + 2048 + 1088, bar_p = bar_s + 8, bar_o = bar_s + 16, bar_free = bar_s + 24;
   const uint32_t tmem_slot = bar_s + 32;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+  uint8_t* gQ = gen;
+  uint8_t* gK = gen + VA_Q_BYTES;
+  uint8_t* gV = gK + VA_K_BYTES;
+  uint8_t* gP = gV + VA_V_BYTES;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -111,131 +116,242 @@ vit_attention_tc_kernel(const VitAttnParams p) {
   constexpr uint32_t IDESC_S256 = make_idesc_f16(128, 256);
   constexpr uint32_t IDESC_S16 = make_idesc_f16(128, 16);
   constexpr uint32_t IDESC_O = make_idesc_f16(128, VA_DP);
+  constexpr int CH = VA_D / 8;            // 11 16-byte chunks per row
+  constexpr int NCHUNK = VA_N * CH;       // 2827 chunks per operand
+  constexpr int PER_T = (NCHUNK + 255) / 256;   // 12 per thread
 
-  uint32_t tile_ctr = 0;   // every mbarrier completes exactly once per tile: parity = tile_ctr & 1
+  auto issue_s = [&](int t) {             // S = Q_t K^T : 128 x 272 into TMEM columns [0, 272)
+    const uint32_t qa = sQ + (uint32_t)t * 16 * VA_SBO_QK;
+#pragma unroll
+    for (int j = 0; j < VA_DP / 16; ++j)
+      umma_f16<1>(tmem, make_desc_nosw(qa + j * 256, VA_SBO_QK), make_desc_nosw(sK + j * 256, VA_SBO_QK), IDESC_S256,
+                  j > 0);
+#pragma unroll
+    for (int j = 0; j < VA_DP / 16; ++j)
+      umma_f16<1>(tmem + 256, make_desc_nosw(qa + j * 256, VA_SBO_QK),
+                  make_desc_nosw(sK + 32 * VA_SBO_QK + j * 256, VA_SBO_QK), IDESC_S16, j > 0);
+    umma_commit<1>(bar_s);
+  };
+
+  uint32_t tile_ctr = 0;   // bar_s / bar_p / bar_o / bar_free complete exactly once per tile: parity = tile_ctr & 1
   for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
     const int b = item / p.heads, h = item - b * p.heads;
-    // ---------------- stage Q, K, V^T (compute warps) ----------------
+    // ---------------- stage Q, K, V^T (8 compute warps, loads batched before the stores) ----------------
     if (warp < 8) {
       const __half* qg = p.q + b * p.q_bs + h * p.q_hs;
       const __half* kg = p.k + b * p.k_bs + h * p.k_hs;
       const __half* vg = p.v + b * p.v_bs + h * p.v_hs;
-      constexpr int CH = VA_D / 8;   // 11 16-byte chunks per row
-      for (int i = tid; i < VA_N * CH; i += 256) {
-        const int r = i / CH, c = i - r * CH;
-        const uint4 qv = __ldg(reinterpret_cast<const uint4*>(qg + (long long)r * p.q_ts + c * 8));
-        const uint4 kv = __ldg(reinterpret_cast<const uint4*>(kg + (long long)r * p.k_ts + c * 8));
-        const uint32_t off = (uint32_t)(r >> 3) * VA_SBO_QK + c * 128 + (r & 7) * 16;
-        *reinterpret_cast<uint4*>(gen + (sQ - base) + off) = qv;
-        *reinterpret_cast<uint4*>(gen + (sK - base) + off) = kv;
+#pragma unroll
+      for (int half_ = 0; half_ < 2; ++half_) {      // two batches of 6 chunks: 12 loads in flight per thread
+        uint4 qv[6], kv[6];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          const int i = tid + (half_ * 6 + u) * 256;
+          if (i < NCHUNK) {
+            const int r = i / CH, c = i - r * CH;
+            qv[u] = __ldg(reinterpret_cast<const uint4*>(qg + (long long)r * p.q_ts + c * 8));
+            kv[u] = __ldg(reinterpret_cast<const uint4*>(kg + (long long)r * p.k_ts + c * 8));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          const int i = tid + (half_ * 6 + u) * 256;
+          if (i < NCHUNK) {
+            const int r = i / CH, c = i - r * CH;
+            const uint32_t off = (uint32_t)(r >> 3) * VA_SBO_QK + c * 128 + (r & 7) * 16;
+            *reinterpret_cast<uint4*>(gQ + off) = qv[u];
+            *reinterpret_cast<uint4*>(gK + off) = kv[u];
+          }
+        }
       }
       // V^T: thread <-> (chunk c, key): consecutive lanes take consecutive keys
-      for (int i = tid; i < VA_N * CH; i += 256) {
-        const int c = i / VA_N, key = i - c * VA_N;
-        const uint4 vv = __ldg(reinterpret_cast<const uint4*>(vg + (long long)key * p.v_ts + c * 8));
-        const __half* hv = reinterpret_cast<const __half*>(&vv);
-        __half* dst = reinterpret_cast<__half*>(gen + (sV - base) + (uint32_t)c * VA_SBO_PV + (key >> 3) * 128 + (key & 7) * 2);
+      {
+        uint4 vv[PER_T];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j * 8] = hv[j];     // d = c*8 + j -> +16 bytes per d row
+        for (int u = 0; u < PER_T; ++u) {
+          const int i = tid + u * 256;
+          if (i < NCHUNK) {
+            const int c = i / VA_N, key = i - c * VA_N;
+            vv[u] = __ldg(reinterpret_cast<const uint4*>(vg + (long long)key * p.v_ts + c * 8));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < PER_T; ++u) {
+          const int i = tid + u * 256;
+          if (i < NCHUNK) {
+            const int c = i / VA_N, key = i - c * VA_N;
+            const __half* hv = reinterpret_cast<const __half*>(&vv[u]);
+            __half* dst = reinterpret_cast<__half*>(gV + (uint32_t)c * VA_SBO_PV + (key >> 3) * 128 + (key & 7) * 2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j * 8] = hv[j];     // d = c*8 + j -> +16 bytes per d row
+          }
+        }
       }
       fence_proxy_async_smem();
     }
     __syncthreads();
 
-    for (int t = 0; t < 3; ++t, ++tile_ctr) {
-      const uint32_t par = tile_ctr & 1;
-      if (warp == 8) {
-        // ======================= MMA issuer =======================
-        if (lane == 0) {
-          if (tile_ctr > 0) mbar_wait(bar_free, (tile_ctr - 1) & 1);   // S/O/P of the previous tile consumed
-          tc_fence_after();
-          const uint32_t qa = sQ + (uint32_t)t * 16 * VA_SBO_QK;
-#pragma unroll
-          for (int j = 0; j < VA_DP / 16; ++j)
-            umma_f16<1>(tmem, make_desc_nosw(qa + j * 256, VA_SBO_QK), make_desc_nosw(sK + j * 256, VA_SBO_QK),
-                        IDESC_S256, j > 0);
-#pragma unroll
-          for (int j = 0; j < VA_DP / 16; ++j)
-            umma_f16<1>(tmem + 256, make_desc_nosw(qa + j * 256, VA_SBO_QK),
-                        make_desc_nosw(sK + 32 * VA_SBO_QK + j * 256, VA_SBO_QK), IDESC_S16, j > 0);
-          umma_commit<1>(bar_s);
-          mbar_wait(bar_p, par);
+    if (warp == 8) {
+      // ======================= MMA issuer =======================
+      if (lane == 0) {
+        issue_s(0);
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t ctr = tile_ctr + t;
+          mbar_wait(bar_p, ctr & 1);                      // P_t written, S_t fully read
+          if (ctr > 0) mbar_wait(bar_free, (ctr - 1) & 1);   // O of the previous tile has been read out
           tc_fence_after();
 #pragma unroll
           for (int j = 0; j < VA_KP / 16; ++j)
             umma_f16<1>(tmem + VA_O_COL, make_desc_nosw(sP + j * 256, VA_SBO_PV), make_desc_nosw(sV + j * 256, VA_SBO_PV),
                         IDESC_O, j > 0);
           umma_commit<1>(bar_o);
+          if (t == 0) issue_s(1);                         // S of the next tile runs under this tile's epilogue
         }
-        __syncwarp();
-      } else {
-        // ======================= softmax + epilogue =======================
-        const int quarter = warp & 3, hf = warp >> 2;
-        const int rl = quarter * 32 + lane;               // row inside the tile
+      }
+      __syncwarp();
+    } else if (warp == 9) {
+      // ======================= query row 256 (the 257th token) on the CUDA cores =======================
+      // 1 row x 257 keys x 88 dims: a third 128-row MMA tile would be 99% padding
+      float qv[VA_D];
+      {
+        const uint8_t* qrow = gQ + 32 * VA_SBO_QK;         // row 256 = first row of group 32
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(qrow + c * 128);
+          const __half* hh = reinterpret_cast<const __half*>(&raw);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) qv[c * 8 + j] = __half2float(hh[j]);
+        }
+      }
+      float sc[9];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int key = lane + 32 * i;
+        float acc = 0.0f;
+        if (key < VA_N) {
+          const uint8_t* krow = gK + (uint32_t)(key >> 3) * VA_SBO_QK + (key & 7) * 16;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(krow + c * 128);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(h2[j]);
+              acc = fmaf(qv[c * 8 + 2 * j], f.x, acc);
+              acc = fmaf(qv[c * 8 + 2 * j + 1], f.y, acc);
+            }
+          }
+          acc *= p.scale_log2;
+          mx = fmaxf(mx, acc);
+        } else {
+          acc = -INFINITY;
+        }
+        sc[i] = acc;
+      }
+      mx = warp_max(mx);
+      float sum = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int key = lane + 32 * i;
+        const float pr = __half2float(__float2half_rn(ex2f(sc[i] - mx)));   // rounded to fp16 like the tile path
+        sum += pr;
+        if (key < VA_KP) s_cls[key] = (key < VA_N) ? pr : 0.0f;
+      }
+      sum = warp_sum(sum);
+      __syncwarp();
+      const float inv = 1.0f / sum;
+      __half* og = p.o + b * p.o_bs + h * p.o_hs + (long long)(VA_N - 1) * p.o_ts;
+#pragma unroll
+      for (int dd = 0; dd < 3; ++dd) {
+        const int d = lane + 32 * dd;
+        if (d < VA_D) {
+          const uint8_t* vrow = gV + (uint32_t)(d >> 3) * VA_SBO_PV + (d & 7) * 16;
+          float acc = 0.0f;
+#pragma unroll 4
+          for (int kc = 0; kc < VA_KP / 8; ++kc) {        // 34 groups of 8 keys (pad keys hold zeros)
+            const uint4 raw = *reinterpret_cast<const uint4*>(vrow + kc * 128);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+            const float4 p0 = *reinterpret_cast<const float4*>(s_cls + kc * 8);
+            const float4 p1 = *reinterpret_cast<const float4*>(s_cls + kc * 8 + 4);
+            const float2 v0 = __half22float2(h2[0]), v1 = __half22float2(h2[1]);
+            const float2 v2 = __half22float2(h2[2]), v3 = __half22float2(h2[3]);
+            acc = fmaf(p0.x, v0.x, acc); acc = fmaf(p0.y, v0.y, acc);
+            acc = fmaf(p0.z, v1.x, acc); acc = fmaf(p0.w, v1.y, acc);
+            acc = fmaf(p1.x, v2.x, acc); acc = fmaf(p1.y, v2.y, acc);
+            acc = fmaf(p1.z, v3.x, acc); acc = fmaf(p1.w, v3.y, acc);
+          }
+          og[d] = __float2half_rn(acc * inv);
+        }
+      }
+    } else {
+      // ======================= softmax + epilogue (rows 0..255 in two 128-row tiles) =======================
+      const int quarter = warp & 3, hf = warp >> 2;
+      const int rl = quarter * 32 + lane;               // row inside the tile
+      const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+      uint8_t* prow = gP + (uint32_t)(rl >> 3) * VA_SBO_PV + (rl & 7) * 16;
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t par = (tile_ctr + t) & 1;
         const int row = t * 128 + rl;
-        const bool warp_live = (t * 128 + quarter * 32) < VA_N;   // warp-uniform
-        const bool valid = row < VA_N;
-        const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
         mbar_wait(bar_s, par);
         tc_fence_after();
+        // pass 1: row maximum over this warp's half of the keys
         float mx = -INFINITY;
-        if (warp_live) {
-          // pass 1: row maximum over this warp's half of the keys
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tmem_ld32(trow + hf * 128 + c * 32, r);
-            tmem_ld_wait();
+        {
+          uint32_t ra[32], rb[32];
+          tmem_ld32(trow + hf * 128, ra);
+          tmem_ld32(trow + hf * 128 + 32, rb);
+          tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-          }
-          if (hf == 1) {
-            uint32_t r[16];
-            tmem_ld16(trow + 256, r);
-            tmem_ld_wait();
-            mx = fmaxf(mx, __uint_as_float(r[0]));        // key 256; columns 257..271 are padding
-          }
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[j]), __uint_as_float(rb[j])));
+          tmem_ld32(trow + hf * 128 + 64, ra);
+          tmem_ld32(trow + hf * 128 + 96, rb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[j]), __uint_as_float(rb[j])));
+        }
+        float s256 = 0.0f;
+        if (hf == 1) {
+          uint32_t r[16];
+          tmem_ld16(trow + 256, r);
+          tmem_ld_wait();
+          s256 = __uint_as_float(r[0]);                   // key 256; columns 257..271 are padding
+          mx = fmaxf(mx, s256);
         }
         s_max[hf * 128 + rl] = mx;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const float m = fmaxf(s_max[rl], s_max[128 + rl]) * p.scale_log2;   // scale > 0
         float sum = 0.0f;
-        if (warp_live) {
-          // pass 2: P = exp2(s*scale*log2e - m), rounded to fp16, into the canonical K-major layout
-          uint8_t* prow = gen + (sP - base) + (uint32_t)(rl >> 3) * VA_SBO_PV + (rl & 7) * 16;
+        // pass 2: P = exp2(s*scale*log2e - m), rounded to fp16, into the canonical K-major layout
+        if (t > 0) {
+          // P_{t-1} is still being read by its P.V MMAs until bar_o of the previous tile: this thread waited on
+          // that barrier in the previous iteration's epilogue, so the buffer is free here.
+        }
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tmem_ld32(trow + hf * 128 + c * 32, r);
-            tmem_ld_wait();
-            const int kc0 = (hf * 128 + c * 32) >> 3;     // first 8-key core matrix of this chunk
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(trow + hf * 128 + c * 32, r);
+          tmem_ld_wait();
+          const int kc0 = (hf * 128 + c * 32) >> 3;     // first 8-key core matrix of this chunk
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 o;
-              o.x = pack2(ex2f(fmaf(__uint_as_float(r[g * 8 + 0]), p.scale_log2, -m)),
-                          ex2f(fmaf(__uint_as_float(r[g * 8 + 1]), p.scale_log2, -m)), sum);
-              o.y = pack2(ex2f(fmaf(__uint_as_float(r[g * 8 + 2]), p.scale_log2, -m)),
-                          ex2f(fmaf(__uint_as_float(r[g * 8 + 3]), p.scale_log2, -m)), sum);
-              o.z = pack2(ex2f(fmaf(__uint_as_float(r[g * 8 + 4]), p.scale_log2, -m)),
-                          ex2f(fmaf(__uint_as_float(r[g * 8 + 5]), p.scale_log2, -m)), sum);
-              o.w = pack2(ex2f(fmaf(__uint_as_float(r[g * 8 + 6]), p.scale_log2, -m)),
-                          ex2f(fmaf(__uint_as_float(r[g * 8 + 7]), p.scale_log2, -m)), sum);
-              if (valid) *reinterpret_cast<uint4*>(prow + (kc0 + g) * 128) = o;
-            }
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            o.x = pack2(ex2f(fmaf(__uint_as_float(r[g * 8 + 0]), p.scale_log2, -m)),
+                        ex2f(fmaf(__uint_as_float(r[g * 8 + 1]), p.scale_log2, -m)), sum);
+            o.y = pack2(ex2f(fmaf(__uint_as_float(r[g * 8 + 2]), p.scale_log2, -m)),
+                        ex2f(fmaf(__uint_as_float(r[g * 8 + 3]), p.scale_log2, -m)), sum);
+            o.z = pack2(ex2f(fmaf(__uint_as_float(r[g * 8 + 4]), p.scale_log2, -m)),
+                        ex2f(fmaf(__uint_as_float(r[g * 8 + 5]), p.scale_log2, -m)), sum);
+            o.w = pack2(ex2f(fmaf(__uint_as_float(r[g * 8 + 6]), p.scale_log2, -m)),
+                        ex2f(fmaf(__uint_as_float(r[g * 8 + 7]), p.scale_log2, -m)), sum);
+            *reinterpret_cast<uint4*>(prow + (kc0 + g) * 128) = o;
           }
-          if (hf == 1) {
-            uint32_t r[16];
-            tmem_ld16(trow + 256, r);
-            tmem_ld_wait();
-            float dummy = 0.0f;
-            uint4 o = make_uint4(0, 0, 0, 0);
-            o.x = pack2(ex2f(fmaf(__uint_as_float(r[0]), p.scale_log2, -m)), 0.0f, sum);
-            (void)dummy;
-            if (valid) {
-              *reinterpret_cast<uint4*>(prow + 32 * 128) = o;                       // keys 256..263
-              *reinterpret_cast<uint4*>(prow + 33 * 128) = make_uint4(0, 0, 0, 0);  // keys 264..271
-            }
-          }
+        }
+        if (hf == 1) {
+          uint4 o = make_uint4(0, 0, 0, 0);
+          o.x = pack2(ex2f(fmaf(s256, p.scale_log2, -m)), 0.0f, sum);
+          *reinterpret_cast<uint4*>(prow + 32 * 128) = o;                       // keys 256..263
+          *reinterpret_cast<uint4*>(prow + 33 * 128) = make_uint4(0, 0, 0, 0);  // keys 264..271
         }
         s_sum[hf * 128 + rl] = sum;
         fence_proxy_async_smem();     // P (generic-proxy stores) must be visible to the tensor core
@@ -245,7 +361,7 @@ vit_attention_tc_kernel(const VitAttnParams p) {
 
         mbar_wait(bar_o, par);
         tc_fence_after();
-        if (warp_live) {
+        {
           const float total = s_sum[rl] + s_sum[128 + rl];
           const float inv = total > 0.0f ? 1.0f / total : 0.0f;
           uint32_t r0[32], r1[16];
@@ -253,39 +369,38 @@ vit_attention_tc_kernel(const VitAttnParams p) {
           tmem_ld32(trow + VA_O_COL + hf * 48, r0);
           tmem_ld16(trow + VA_O_COL + hf * 48 + 32, r1);
           tmem_ld_wait();
-          if (valid) {
-            __half* og = p.o + b * p.o_bs + h * p.o_hs + (long long)row * p.o_ts + hf * 48;
+          // O is in registers: hand the TMEM columns back before the global stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_free);
+          __half* og = p.o + b * p.o_bs + h * p.o_hs + (long long)row * p.o_ts + hf * 48;
+          float unused = 0.0f;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            o.x = pack2(__uint_as_float(r0[g * 8 + 0]) * inv, __uint_as_float(r0[g * 8 + 1]) * inv, unused);
+            o.y = pack2(__uint_as_float(r0[g * 8 + 2]) * inv, __uint_as_float(r0[g * 8 + 3]) * inv, unused);
+            o.z = pack2(__uint_as_float(r0[g * 8 + 4]) * inv, __uint_as_float(r0[g * 8 + 5]) * inv, unused);
+            o.w = pack2(__uint_as_float(r0[g * 8 + 6]) * inv, __uint_as_float(r0[g * 8 + 7]) * inv, unused);
+            *reinterpret_cast<uint4*>(og + g * 8) = o;
+          }
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (hf == 0 || g == 0) {     // dims 80..87 exist, 88..95 are padding
               uint4 o;
-              float unused = 0.0f;
-              o.x = pack2(__uint_as_float(r0[g * 8 + 0]) * inv, __uint_as_float(r0[g * 8 + 1]) * inv, unused);
-              o.y = pack2(__uint_as_float(r0[g * 8 + 2]) * inv, __uint_as_float(r0[g * 8 + 3]) * inv, unused);
-              o.z = pack2(__uint_as_float(r0[g * 8 + 4]) * inv, __uint_as_float(r0[g * 8 + 5]) * inv, unused);
-              o.w = pack2(__uint_as_float(r0[g * 8 + 6]) * inv, __uint_as_float(r0[g * 8 + 7]) * inv, unused);
-              *reinterpret_cast<uint4*>(og + g * 8) = o;
-            }
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              if (hf == 0 || g == 0) {     // dims 80..87 exist, 88..95 are padding
-                uint4 o;
-                float unused = 0.0f;
-                o.x = pack2(__uint_as_float(r1[g * 8 + 0]) * inv, __uint_as_float(r1[g * 8 + 1]) * inv, unused);
-                o.y = pack2(__uint_as_float(r1[g * 8 + 2]) * inv, __uint_as_float(r1[g * 8 + 3]) * inv, unused);
-                o.z = pack2(__uint_as_float(r1[g * 8 + 4]) * inv, __uint_as_float(r1[g * 8 + 5]) * inv, unused);
-                o.w = pack2(__uint_as_float(r1[g * 8 + 6]) * inv, __uint_as_float(r1[g * 8 + 7]) * inv, unused);
-                *reinterpret_cast<uint4*>(og + 32 + g * 8) = o;
-              }
+              o.x = pack2(__uint_as_float(r1[g * 8 + 0]) * inv, __uint_as_float(r1[g * 8 + 1]) * inv, unused);
+              o.y = pack2(__uint_as_float(r1[g * 8 + 2]) * inv, __uint_as_float(r1[g * 8 + 3]) * inv, unused);
+              o.z = pack2(__uint_as_float(r1[g * 8 + 4]) * inv, __uint_as_float(r1[g * 8 + 5]) * inv, unused);
+              o.w = pack2(__uint_as_float(r1[g * 8 + 6]) * inv, __uint_as_float(r1[g * 8 + 7]) * inv, unused);
+              *reinterpret_cast<uint4*>(og + 32 + g * 8) = o;
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_free);
       }
     }
+    tile_ctr += 2;
     // the next item's staging overwrites Q/K/V^T: every MMA of this item has retired (the compute warps
-    // waited on bar_o of the last tile); make the whole CTA agree before touching shared memory again
+    // waited on bar_o of the last tile) and the row-256 warp is done reading; make the whole CTA agree
     __syncthreads();
   }
 

@@ -528,7 +528,9 @@ int gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   SB_REQUIRE(ctas == 1 || ctas == 2, "gemm: ctas must be 1 or 2 (got %d)", ctas);
   if (ctas == 2 && (bn < 64 || d.M <= GEMM_BLOCK_M)) ctas = 1;   // pairs only pay off on big tiles
 
-  const int ksub = (d.K > 64 && get_option("gemm_ksub") != 1) ? 2 : 1;
+  // 128-deep stages pay off where the stage count stays >= 3 (CTA pairs with wide tiles); measured on B200:
+  // qkv/fc1/fc2 +10% with pairs, -5% on single CTAs (2 stages) and on the BN=176 proj tile
+  const int ksub = (d.K > 64 && ctas == 2 && bn >= 192 && get_option("gemm_ksub") != 1) ? 2 : 1;
 #define SB_GEMM_CASE(BN_, CT_, MD_)                                                   \
   if (bn == BN_ && ctas == CT_ && d.mode == MD_) {                                    \
     if (ksub == 2) return launch_gemm<BN_, CT_, MD_, 2>(d, stream);                   \
