@@ -33,6 +33,7 @@ constexpr int VA_SMEM = VA_Q_BYTES + VA_K_BYTES + VA_V_BYTES + VA_P_BYTES + VA_M
 constexpr int VA_THREADS = 320;                       // 8 softmax warps + MMA warp + row-256 warp
 constexpr int VA_TMEM_COLS = 512;
 constexpr int VA_O_COL = 272;
+constexpr int VA_P_COL = 368;                          // P (fp16 x2 per column): 136 columns, ends at 504
 
 struct VitAttnParams {
   const __half* q; const __half* k; const __half* v; __half* o;
@@ -61,6 +62,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (P, fp16 packed two per 32-bit column) stays in tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -202,8 +230,7 @@ vit_attention_tc_kernel(const VitAttnParams p) {
           tc_fence_after();
 #pragma unroll
           for (int j = 0; j < VA_KP / 16; ++j)
-            umma_f16<1>(tmem + VA_O_COL, make_desc_nosw(sP + j * 256, VA_SBO_PV), make_desc_nosw(sV + j * 256, VA_SBO_PV),
-                        IDESC_O, j > 0);
+            umma_f16_ts(tmem + VA_O_COL, tmem + VA_P_COL + j * 8, make_desc_nosw(sV + j * 256, VA_SBO_PV), IDESC_O, j > 0);
           umma_commit<1>(bar_o);
           if (t == 0) issue_s(1);                         // S of the next tile runs under this tile's epilogue
         }
@@ -332,29 +359,20 @@ vit_attention_tc_kernel(const VitAttnParams p) {
           uint32_t r[32];
           tmem_ld32(trow + hf * 128 + c * 32, r);
           tmem_ld_wait();
-          const int kc0 = (hf * 128 + c * 32) >> 3;     // first 8-key core matrix of this chunk
+          uint32_t pk[16];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 o;
-            o.x = pack2(ex2f(fmaf(__uint_as_float(r[g * 8 + 0]), p.scale_log2, -m)),
-                        ex2f(fmaf(__uint_as_float(r[g * 8 + 1]), p.scale_log2, -m)), sum);
-            o.y = pack2(ex2f(fmaf(__uint_as_float(r[g * 8 + 2]), p.scale_log2, -m)),
-                        ex2f(fmaf(__uint_as_float(r[g * 8 + 3]), p.scale_log2, -m)), sum);
-            o.z = pack2(ex2f(fmaf(__uint_as_float(r[g * 8 + 4]), p.scale_log2, -m)),
-                        ex2f(fmaf(__uint_as_float(r[g * 8 + 5]), p.scale_log2, -m)), sum);
-            o.w = pack2(ex2f(fmaf(__uint_as_float(r[g * 8 + 6]), p.scale_log2, -m)),
-                        ex2f(fmaf(__uint_as_float(r[g * 8 + 7]), p.scale_log2, -m)), sum);
-            *reinterpret_cast<uint4*>(prow + (kc0 + g) * 128) = o;
-          }
+          for (int g = 0; g < 16; ++g)
+            pk[g] = pack2(ex2f(fmaf(__uint_as_float(r[2 * g]), p.scale_log2, -m)),
+                          ex2f(fmaf(__uint_as_float(r[2 * g + 1]), p.scale_log2, -m)), sum);
+          tmem_st16(trow + VA_P_COL + hf * 64 + c * 16, pk);      // keys hf*128 + c*32 .. +31
         }
         if (hf == 1) {
-          uint4 o = make_uint4(0, 0, 0, 0);
-          o.x = pack2(ex2f(fmaf(s256, p.scale_log2, -m)), 0.0f, sum);
-          *reinterpret_cast<uint4*>(prow + 32 * 128) = o;                       // keys 256..263
-          *reinterpret_cast<uint4*>(prow + 33 * 128) = make_uint4(0, 0, 0, 0);  // keys 264..271
+          uint32_t pk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          pk[0] = pack2(ex2f(fmaf(s256, p.scale_log2, -m)), 0.0f, sum);
+          tmem_st8(trow + VA_P_COL + 128, pk);                     // keys 256..271 (only 256 exists)
         }
+        tmem_st_wait();
         s_sum[hf * 128 + rl] = sum;
-        fence_proxy_async_smem();     // P (generic-proxy stores) must be visible to the tensor core
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p);
