@@ -22,15 +22,15 @@
 namespace sb {
 
 constexpr int VA_D = 88, VA_DP = 96, VA_N = 257, VA_KP = 272;
-constexpr int VA_SBO_QK = (VA_DP / 8) * 128;       // 1536: bytes between 8-row groups of Q / K
-constexpr int VA_SBO_PV = (VA_KP / 8) * 128;       // 4352: bytes between 8-row groups of P / V^T
-constexpr int VA_Q_BYTES = 33 * VA_SBO_QK;         // 264 rows
-constexpr int VA_K_BYTES = 33 * VA_SBO_QK;
-constexpr int VA_V_BYTES = (VA_DP / 8) * VA_SBO_PV;   // 96 d-rows x 272 keys
-constexpr int VA_P_BYTES = 16 * VA_SBO_PV;            // 128 rows x 272 keys
-constexpr int VA_MISC_BYTES = 4 * 128 * 4 + 1088 + 64;   // max/sum exchange, row-256 probabilities, barriers, tmem slot
-constexpr int VA_SMEM = VA_Q_BYTES + VA_K_BYTES + VA_V_BYTES + VA_P_BYTES + VA_MISC_BYTES + 128;
-constexpr int VA_THREADS = 320;                       // 8 softmax warps + MMA warp + row-256 warp
+constexpr int VA_G = (VA_DP / 8) * 128;            // 1536: bytes of one 8-row group (12 chunks of 8 halves)
+constexpr int VA_K_BYTES = 33 * VA_G;              // keys 0..263 (x2 buffers)
+constexpr int VA_Q0_BYTES = 16 * VA_G;             // query rows 0..127
+constexpr int VA_Q1_BYTES = 17 * VA_G;             // query rows 128..255 and the group holding row 256
+constexpr int VA_V_BYTES = 34 * VA_G;              // keys 0..271 (P.V walks 17 steps of 16 keys)
+constexpr int VA_DATA_BYTES = 2 * VA_K_BYTES + VA_Q0_BYTES + VA_Q1_BYTES + VA_V_BYTES;
+constexpr int VA_MISC_BYTES = 4 * 128 * 4 + 1088 + 128;   // max/sum exchange, row-256 probabilities, barriers, tmem slot
+constexpr int VA_SMEM = VA_DATA_BYTES + VA_MISC_BYTES + 128;
+constexpr int VA_THREADS = 448;                       // 8 softmax warps, MMA warp, row-256 warp, 4 loader warps
 constexpr int VA_TMEM_COLS = 512;
 constexpr int VA_O_COL = 272;
 constexpr int VA_P_COL = 368;                          // P (fp16 x2 per column): 136 columns, ends at 504
@@ -42,15 +42,23 @@ struct VitAttnParams {
   float scale_log2;
 };
 
-// K-major, no swizzle: LBO (K direction) = 128 B, SBO (M/N direction) given
-__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t addr, uint32_t sbo) {
+// No-swizzle canonical layouts (8 x 16-byte core matrices, 128 B each).  The shared-memory image used here is
+//   byte(r, c) = (r / 8) * VA_G + (c / 8) * 128 + (r % 8) * 16 + (c % 8) * 2      (r = token, c = head dim)
+// * as a K-major operand (Q, K: contraction over c): LBO = 128 (next core matrix along K), SBO = VA_G;
+// * as an MN-major B operand (V: contraction over r = keys, N = c): SBO = 128 (next 8 of N), LBO = VA_G (next
+//   8 keys) -- the same bytes, so V needs no transposition.
+__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t addr, uint32_t lbo, uint32_t sbo) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>(128 >> 4) << 16;
+  d |= static_cast<uint64_t>(lbo >> 4) << 16;
   d |= static_cast<uint64_t>(sbo >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   return d;
 }
+__device__ __forceinline__ void cp_async16_tc(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all_tc() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -109,31 +117,33 @@ vit_attention_tc_kernel(const VitAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sQ = base, sK = sQ + VA_Q_BYTES, sV = sK + VA_K_BYTES, sP = sV + VA_V_BYTES;
-  const uint32_t misc = sP + VA_P_BYTES;
+  const uint32_t sK0 = base, sQ0 = sK0 + 2 * VA_K_BYTES, sQ1 = sQ0 + VA_Q0_BYTES, sV = sQ1 + VA_Q1_BYTES;
+  const uint32_t misc = sV + VA_V_BYTES;
   float* s_max = reinterpret_cast<float*>(gen + (misc - base));     // [2][128]
   float* s_sum = s_max + 256;                                       // [2][128]
   float* s_cls = s_sum + 256;                                       // [272] probabilities of query row 256
-  const uint32_t bar_s = misc + 2048 + 1088, bar_p = bar_s + 8, bar_o = bar_s + 16, bar_free = bar_s + 24;
-  const uint32_t tmem_slot = bar_s + 32;
+  const uint32_t bars = misc + 2048 + 1088;
+  const uint32_t bar_s = bars, bar_p = bars + 8, bar_o = bars + 16, bar_free = bars + 24;
+  const uint32_t q0_full = bars + 32, q0_empty = bars + 40, q1_full = bars + 48, q1_empty = bars + 56;
+  const uint32_t v_full = bars + 64, v_empty = bars + 72, k_full = bars + 80 /*[2]*/, k_empty = bars + 96 /*[2]*/;
+  const uint32_t tmem_slot = bars + 112;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
-  uint8_t* gQ = gen;
-  uint8_t* gK = gen + VA_Q_BYTES;
-  uint8_t* gV = gK + VA_K_BYTES;
-  uint8_t* gP = gV + VA_V_BYTES;
+  uint8_t* gQ1 = gen + (sQ1 - base);
+  uint8_t* gV = gen + (sV - base);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 8);
-    mbar_init(bar_o, 1);
-    mbar_init(bar_free, 8);
+    mbar_init(bar_s, 1); mbar_init(bar_p, 8); mbar_init(bar_o, 1); mbar_init(bar_free, 8);
+    mbar_init(q0_full, 1); mbar_init(q0_empty, 1);
+    mbar_init(q1_full, 1); mbar_init(q1_empty, 2);      // S(1) retired + row-256 warp done
+    mbar_init(v_full, 1);  mbar_init(v_empty, 2);       // P.V(1) retired + row-256 warp done
+    for (int i = 0; i < 2; ++i) { mbar_init(k_full + 8 * i, 1); mbar_init(k_empty + 8 * i, 2); }
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc<1>(tmem_slot, VA_TMEM_COLS);
-  // zero Q, K, V^T once: the padding (head_dim 88..95, keys 257..271) is never written afterwards
-  for (uint32_t off = tid * 16; off < (uint32_t)(VA_Q_BYTES + VA_K_BYTES + VA_V_BYTES); off += VA_THREADS * 16)
+  // zero every operand buffer once: the padding (head_dim 88..95, rows/keys 257..271) is never written again
+  for (uint32_t off = tid * 16; off < (uint32_t)VA_DATA_BYTES; off += VA_THREADS * 16)
     *reinterpret_cast<uint4*>(gen + off) = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   tc_fence_before();
@@ -143,105 +153,94 @@ vit_attention_tc_kernel(const VitAttnParams p) {
 
   constexpr uint32_t IDESC_S256 = make_idesc_f16(128, 256);
   constexpr uint32_t IDESC_S16 = make_idesc_f16(128, 16);
-  constexpr uint32_t IDESC_O = make_idesc_f16(128, VA_DP);
+  constexpr uint32_t IDESC_O = make_idesc_f16(128, VA_DP) | (1u << 16);   // B (= V) is MN-major
   constexpr int CH = VA_D / 8;            // 11 16-byte chunks per row
-  constexpr int NCHUNK = VA_N * CH;       // 2827 chunks per operand
-  constexpr int PER_T = (NCHUNK + 255) / 256;   // 12 per thread
 
-  auto issue_s = [&](int t) {             // S = Q_t K^T : 128 x 272 into TMEM columns [0, 272)
-    const uint32_t qa = sQ + (uint32_t)t * 16 * VA_SBO_QK;
-#pragma unroll
-    for (int j = 0; j < VA_DP / 16; ++j)
-      umma_f16<1>(tmem, make_desc_nosw(qa + j * 256, VA_SBO_QK), make_desc_nosw(sK + j * 256, VA_SBO_QK), IDESC_S256,
-                  j > 0);
-#pragma unroll
-    for (int j = 0; j < VA_DP / 16; ++j)
-      umma_f16<1>(tmem + 256, make_desc_nosw(qa + j * 256, VA_SBO_QK),
-                  make_desc_nosw(sK + 32 * VA_SBO_QK + j * 256, VA_SBO_QK), IDESC_S16, j > 0);
-    umma_commit<1>(bar_s);
-  };
-
-  uint32_t tile_ctr = 0;   // bar_s / bar_p / bar_o / bar_free complete exactly once per tile: parity = tile_ctr & 1
-  for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-    const int b = item / p.heads, h = item - b * p.heads;
-    // ---------------- stage Q, K, V^T (8 compute warps, loads batched before the stores) ----------------
-    if (warp < 8) {
-      const __half* qg = p.q + b * p.q_bs + h * p.q_hs;
-      const __half* kg = p.k + b * p.k_bs + h * p.k_hs;
-      const __half* vg = p.v + b * p.v_bs + h * p.v_hs;
-#pragma unroll
-      for (int half_ = 0; half_ < 2; ++half_) {      // two batches of 6 chunks: 12 loads in flight per thread
-        uint4 qv[6], kv[6];
-#pragma unroll
-        for (int u = 0; u < 6; ++u) {
-          const int i = tid + (half_ * 6 + u) * 256;
-          if (i < NCHUNK) {
-            const int r = i / CH, c = i - r * CH;
-            qv[u] = __ldg(reinterpret_cast<const uint4*>(qg + (long long)r * p.q_ts + c * 8));
-            kv[u] = __ldg(reinterpret_cast<const uint4*>(kg + (long long)r * p.k_ts + c * 8));
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 6; ++u) {
-          const int i = tid + (half_ * 6 + u) * 256;
-          if (i < NCHUNK) {
-            const int r = i / CH, c = i - r * CH;
-            const uint32_t off = (uint32_t)(r >> 3) * VA_SBO_QK + c * 128 + (r & 7) * 16;
-            *reinterpret_cast<uint4*>(gQ + off) = qv[u];
-            *reinterpret_cast<uint4*>(gK + off) = kv[u];
-          }
-        }
+  if (warp >= 10) {
+    // ======================= loaders: one warp per operand buffer, cp.async 16-byte copies =======================
+    const int which = warp - 10;            // 0: Q rows 0..127, 1: K, 2: Q rows 128..256, 3: V
+    uint32_t n = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+      const int b = item / p.heads, h = item - b * p.heads;
+      const __half* src; long long ts; int row0, rows; uint32_t dst, full, empty, par;
+      if (which == 0)      { src = p.q + b * p.q_bs + h * p.q_hs; ts = p.q_ts; row0 = 0;   rows = 128; dst = sQ0; full = q0_full; empty = q0_empty; par = n & 1; }
+      else if (which == 1) { src = p.k + b * p.k_bs + h * p.k_hs; ts = p.k_ts; row0 = 0;   rows = VA_N; dst = sK0 + (n & 1) * VA_K_BYTES; full = k_full + 8 * (n & 1); empty = k_empty + 8 * (n & 1); par = (n >> 1) & 1; }
+      else if (which == 2) { src = p.q + b * p.q_bs + h * p.q_hs; ts = p.q_ts; row0 = 128; rows = VA_N - 128; dst = sQ1; full = q1_full; empty = q1_empty; par = n & 1; }
+      else                 { src = p.v + b * p.v_bs + h * p.v_hs; ts = p.v_ts; row0 = 0;   rows = VA_N; dst = sV; full = v_full; empty = v_empty; par = n & 1; }
+      mbar_wait(empty, par ^ 1);            // previous contents consumed (passes immediately the first time)
+      const int total = rows * CH;
+      for (int i = lane; i < total; i += 32) {
+        const int r = i / CH, c = i - r * CH;
+        cp_async16_tc(dst + (uint32_t)(r >> 3) * VA_G + c * 128 + (r & 7) * 16, src + (long long)(row0 + r) * ts + c * 8);
       }
-      // V^T: thread <-> (chunk c, key): consecutive lanes take consecutive keys
-      {
-        uint4 vv[PER_T];
-#pragma unroll
-        for (int u = 0; u < PER_T; ++u) {
-          const int i = tid + u * 256;
-          if (i < NCHUNK) {
-            const int c = i / VA_N, key = i - c * VA_N;
-            vv[u] = __ldg(reinterpret_cast<const uint4*>(vg + (long long)key * p.v_ts + c * 8));
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < PER_T; ++u) {
-          const int i = tid + u * 256;
-          if (i < NCHUNK) {
-            const int c = i / VA_N, key = i - c * VA_N;
-            const __half* hv = reinterpret_cast<const __half*>(&vv[u]);
-            __half* dst = reinterpret_cast<__half*>(gV + (uint32_t)c * VA_SBO_PV + (key >> 3) * 128 + (key & 7) * 2);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j * 8] = hv[j];     // d = c*8 + j -> +16 bytes per d row
-          }
-        }
-      }
-      fence_proxy_async_smem();
+      cp_async_wait_all_tc();
+      fence_proxy_async_smem();             // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full);
     }
-    __syncthreads();
-
-    if (warp == 8) {
-      // ======================= MMA issuer =======================
-      if (lane == 0) {
-        issue_s(0);
-        for (int t = 0; t < 2; ++t) {
-          const uint32_t ctr = tile_ctr + t;
-          mbar_wait(bar_p, ctr & 1);                      // P_t written, S_t fully read
-          if (ctr > 0) mbar_wait(bar_free, (ctr - 1) & 1);   // O of the previous tile has been read out
-          tc_fence_after();
+  } else if (warp == 8) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+        const uint32_t kb = n & 1, c0 = 2 * n;
+        const uint32_t sK = sK0 + kb * VA_K_BYTES;
+        auto issue_s = [&](uint32_t qa) {       // S = Q_tile K^T : 128 x 272 into TMEM columns [0, 272)
+#pragma unroll
+          for (int j = 0; j < VA_DP / 16; ++j)
+            umma_f16<1>(tmem, make_desc_nosw(qa + j * 256, 128, VA_G), make_desc_nosw(sK + j * 256, 128, VA_G), IDESC_S256,
+                        j > 0);
+#pragma unroll
+          for (int j = 0; j < VA_DP / 16; ++j)
+            umma_f16<1>(tmem + 256, make_desc_nosw(qa + j * 256, 128, VA_G),
+                        make_desc_nosw(sK + 32 * VA_G + j * 256, 128, VA_G), IDESC_S16, j > 0);
+          umma_commit<1>(bar_s);
+        };
+        auto issue_pv = [&]() {                 // O = P V : A = P in TMEM, B = V (MN-major), 17 steps of 16 keys
 #pragma unroll
           for (int j = 0; j < VA_KP / 16; ++j)
-            umma_f16_ts(tmem + VA_O_COL, tmem + VA_P_COL + j * 8, make_desc_nosw(sV + j * 256, VA_SBO_PV), IDESC_O, j > 0);
+            umma_f16_ts(tmem + VA_O_COL, tmem + VA_P_COL + j * 8, make_desc_nosw(sV + j * 2 * VA_G, VA_G, 128), IDESC_O,
+                        j > 0);
           umma_commit<1>(bar_o);
-          if (t == 0) issue_s(1);                         // S of the next tile runs under this tile's epilogue
-        }
+        };
+        mbar_wait(q0_full, n & 1);
+        mbar_wait(k_full + 8 * kb, (n >> 1) & 1);
+        tc_fence_after();
+        issue_s(sQ0);
+        umma_commit<1>(q0_empty);               // Q rows 0..127 may be overwritten once S(0) has retired
+        // ---- tile 0 ----
+        mbar_wait(bar_p, c0 & 1);               // P(0) in TMEM, S(0) fully read
+        mbar_wait(v_full, n & 1);
+        if (c0 > 0) mbar_wait(bar_free, (c0 - 1) & 1);   // O of the previous tile read out
+        tc_fence_after();
+        issue_pv();
+        mbar_wait(q1_full, n & 1);
+        tc_fence_after();
+        issue_s(sQ1);                           // runs under tile 0's epilogue
+        umma_commit<1>(q1_empty);
+        umma_commit<1>(k_empty + 8 * kb);
+        // ---- tile 1 ----
+        mbar_wait(bar_p, (c0 + 1) & 1);
+        mbar_wait(bar_free, c0 & 1);
+        tc_fence_after();
+        issue_pv();
+        umma_commit<1>(v_empty);
       }
-      __syncwarp();
-    } else if (warp == 9) {
-      // ======================= query row 256 (the 257th token) on the CUDA cores =======================
-      // 1 row x 257 keys x 88 dims: a third 128-row MMA tile would be 99% padding
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ======================= query row 256 (the 257th token) on the CUDA cores =======================
+    uint32_t n = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+      const int b = item / p.heads, h = item - b * p.heads;
+      const uint32_t kb = n & 1;
+      const uint8_t* gK = gen + (sK0 - base) + kb * VA_K_BYTES;
+      mbar_wait(k_full + 8 * kb, (n >> 1) & 1);
+      mbar_wait(q1_full, n & 1);
+      mbar_wait(v_full, n & 1);
       float qv[VA_D];
       {
-        const uint8_t* qrow = gQ + 32 * VA_SBO_QK;         // row 256 = first row of group 32
+        const uint8_t* qrow = gQ1 + 16 * VA_G;             // row 256 = local row 128 = first row of group 16
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           const uint4 raw = *reinterpret_cast<const uint4*>(qrow + c * 128);
@@ -255,9 +254,10 @@ vit_attention_tc_kernel(const VitAttnParams p) {
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
         const int key = lane + 32 * i;
-        float acc = 0.0f;
+        float acc = -INFINITY;
         if (key < VA_N) {
-          const uint8_t* krow = gK + (uint32_t)(key >> 3) * VA_SBO_QK + (key & 7) * 16;
+          acc = 0.0f;
+          const uint8_t* krow = gK + (uint32_t)(key >> 3) * VA_G + (key & 7) * 16;
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             const uint4 raw = *reinterpret_cast<const uint4*>(krow + c * 128);
@@ -271,8 +271,6 @@ vit_attention_tc_kernel(const VitAttnParams p) {
           }
           acc *= p.scale_log2;
           mx = fmaxf(mx, acc);
-        } else {
-          acc = -INFINITY;
         }
         sc[i] = acc;
       }
@@ -287,38 +285,58 @@ vit_attention_tc_kernel(const VitAttnParams p) {
       }
       sum = warp_sum(sum);
       __syncwarp();
-      const float inv = 1.0f / sum;
-      __half* og = p.o + b * p.o_bs + h * p.o_hs + (long long)(VA_N - 1) * p.o_ts;
+      // out[d] = sum_k p_k V[k][d]: lane <-> (8-dim chunk, key parity)
+      const int dc = lane % CH, ph = lane / CH;     // lanes 0..21 work, 22..31 idle
+      float acc8[8];
 #pragma unroll
-      for (int dd = 0; dd < 3; ++dd) {
-        const int d = lane + 32 * dd;
-        if (d < VA_D) {
-          const uint8_t* vrow = gV + (uint32_t)(d >> 3) * VA_SBO_PV + (d & 7) * 16;
-          float acc = 0.0f;
-#pragma unroll 4
-          for (int kc = 0; kc < VA_KP / 8; ++kc) {        // 34 groups of 8 keys (pad keys hold zeros)
-            const uint4 raw = *reinterpret_cast<const uint4*>(vrow + kc * 128);
-            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-            const float4 p0 = *reinterpret_cast<const float4*>(s_cls + kc * 8);
-            const float4 p1 = *reinterpret_cast<const float4*>(s_cls + kc * 8 + 4);
-            const float2 v0 = __half22float2(h2[0]), v1 = __half22float2(h2[1]);
-            const float2 v2 = __half22float2(h2[2]), v3 = __half22float2(h2[3]);
-            acc = fmaf(p0.x, v0.x, acc); acc = fmaf(p0.y, v0.y, acc);
-            acc = fmaf(p0.z, v1.x, acc); acc = fmaf(p0.w, v1.y, acc);
-            acc = fmaf(p1.x, v2.x, acc); acc = fmaf(p1.y, v2.y, acc);
-            acc = fmaf(p1.z, v3.x, acc); acc = fmaf(p1.w, v3.y, acc);
+      for (int j = 0; j < 8; ++j) acc8[j] = 0.0f;
+      if (ph < 2) {
+        for (int key = ph; key < VA_N; key += 2) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(gV + (uint32_t)(key >> 3) * VA_G + dc * 128 + (key & 7) * 16);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+          const float pk = s_cls[key];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h2[j]);
+            acc8[2 * j] = fmaf(pk, f.x, acc8[2 * j]);
+            acc8[2 * j + 1] = fmaf(pk, f.y, acc8[2 * j + 1]);
           }
-          og[d] = __float2half_rn(acc * inv);
         }
       }
-    } else {
-      // ======================= softmax + epilogue (rows 0..255 in two 128-row tiles) =======================
-      const int quarter = warp & 3, hf = warp >> 2;
-      const int rl = quarter * 32 + lane;               // row inside the tile
-      const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
-      uint8_t* prow = gP + (uint32_t)(rl >> 3) * VA_SBO_PV + (rl & 7) * 16;
+      // everything this warp reads from shared memory has been read: release the buffers
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(k_empty + 8 * kb);
+        mbar_arrive(q1_empty);
+        mbar_arrive(v_empty);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float other = __shfl_sync(0xffffffffu, acc8[j], (lane + CH) & 31);   // partner = same chunk, other parity
+        acc8[j] += other;
+      }
+      if (lane < CH) {
+        const float inv = 1.0f / sum;
+        __half* og = p.o + b * p.o_bs + h * p.o_hs + (long long)(VA_N - 1) * p.o_ts + dc * 8;
+        uint4 o;
+        float unused = 0.0f;
+        o.x = pack2(acc8[0] * inv, acc8[1] * inv, unused);
+        o.y = pack2(acc8[2] * inv, acc8[3] * inv, unused);
+        o.z = pack2(acc8[4] * inv, acc8[5] * inv, unused);
+        o.w = pack2(acc8[6] * inv, acc8[7] * inv, unused);
+        *reinterpret_cast<uint4*>(og) = o;
+      }
+    }
+  } else {
+    // ======================= softmax + epilogue (rows 0..255 in two 128-row tiles) =======================
+    const int quarter = warp & 3, hf = warp >> 2;
+    const int rl = quarter * 32 + lane;               // row inside the tile
+    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+    uint32_t n = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+      const int b = item / p.heads, h = item - b * p.heads;
       for (int t = 0; t < 2; ++t) {
-        const uint32_t par = (tile_ctr + t) & 1;
+        const uint32_t par = (2 * n + t) & 1;
         const int row = t * 128 + rl;
         mbar_wait(bar_s, par);
         tc_fence_after();
@@ -349,11 +367,8 @@ vit_attention_tc_kernel(const VitAttnParams p) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const float m = fmaxf(s_max[rl], s_max[128 + rl]) * p.scale_log2;   // scale > 0
         float sum = 0.0f;
-        // pass 2: P = exp2(s*scale*log2e - m), rounded to fp16, into the canonical K-major layout
-        if (t > 0) {
-          // P_{t-1} is still being read by its P.V MMAs until bar_o of the previous tile: this thread waited on
-          // that barrier in the previous iteration's epilogue, so the buffer is free here.
-        }
+        // pass 2: P = exp2(s*scale*log2e - m), rounded to fp16 (as the reference does under autocast), packed two
+        // per TMEM column.  The P columns are free: S of this tile was issued after the previous P.V.
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t r[32];
@@ -416,10 +431,6 @@ vit_attention_tc_kernel(const VitAttnParams p) {
         }
       }
     }
-    tile_ctr += 2;
-    // the next item's staging overwrites Q/K/V^T: every MMA of this item has retired (the compute warps
-    // waited on bar_o of the last tile) and the row-256 warp is done reading; make the whole CTA agree
-    __syncthreads();
   }
 
   tc_fence_before();
