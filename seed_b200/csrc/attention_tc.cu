@@ -28,12 +28,18 @@ constexpr int VA_Q0_BYTES = 16 * VA_G;             // query rows 0..127
 constexpr int VA_Q1_BYTES = 17 * VA_G;             // query rows 128..255 and the group holding row 256
 constexpr int VA_V_BYTES = 34 * VA_G;              // keys 0..271 (P.V walks 17 steps of 16 keys)
 constexpr int VA_DATA_BYTES = 2 * VA_K_BYTES + VA_Q0_BYTES + VA_Q1_BYTES + VA_V_BYTES;
-constexpr int VA_MISC_BYTES = 4 * 128 * 4 + 1088 + 128;   // max/sum exchange, row-256 probabilities, barriers, tmem slot
+constexpr int VA_MISC_BYTES = 4 * 128 * 4 + 1088 + 256;   // max/sum exchange, row-256 probabilities, barriers, tmem slot
 constexpr int VA_SMEM = VA_DATA_BYTES + VA_MISC_BYTES + 128;
 constexpr int VA_THREADS = 448;                       // 8 softmax warps, MMA warp, row-256 warp, 4 loader warps
 constexpr int VA_TMEM_COLS = 512;
-constexpr int VA_O_COL = 272;
-constexpr int VA_P_COL = 368;                          // P (fp16 x2 per column): 136 columns, ends at 504
+// TMEM map of one tile pipeline u (base = 256 * u); everything aliases the 256 fp32 columns of S:
+//   S      keys 0..255                      [0, 256)
+//   P      keys 0..127 (fp16 x2 / column)   [0, 64)     written in place behind the S chunks already consumed
+//          keys 128..255                    [128, 192)
+//   O      dims 0..47                       [64, 112)   written by P.V after every S column has been read
+//          dims 48..95                      [192, 240)
+constexpr int VA_TILE_COLS = 256;
+constexpr int VA_OLO_COL = 64, VA_OHI_COL = 192;
 
 struct VitAttnParams {
   const __half* q; const __half* k; const __half* v; __half* o;
@@ -123,22 +129,28 @@ vit_attention_tc_kernel(const VitAttnParams p) {
   float* s_sum = s_max + 256;                                       // [2][128]
   float* s_cls = s_sum + 256;                                       // [272] probabilities of query row 256
   const uint32_t bars = misc + 2048 + 1088;
-  const uint32_t bar_s = bars, bar_p = bars + 8, bar_o = bars + 16, bar_free = bars + 24;
-  const uint32_t q0_full = bars + 32, q0_empty = bars + 40, q1_full = bars + 48, q1_empty = bars + 56;
-  const uint32_t v_full = bars + 64, v_empty = bars + 72, k_full = bars + 80 /*[2]*/, k_empty = bars + 96 /*[2]*/;
-  const uint32_t tmem_slot = bars + 112;
+  const uint32_t bar_s = bars, bar_p = bars + 16, bar_o = bars + 32, bar_free = bars + 48;      // [2] each: per tile pipeline
+  const uint32_t q_full = bars + 64 /*[2]*/, q_empty = bars + 80 /*[2]*/;
+  const uint32_t v_full = bars + 96, v_empty = bars + 104, k_full = bars + 112 /*[2]*/, k_empty = bars + 128 /*[2]*/;
+  const uint32_t tmem_slot = bars + 144;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+  uint8_t* gQ0 = gen + (sQ0 - base);
   uint8_t* gQ1 = gen + (sQ1 - base);
   uint8_t* gV = gen + (sV - base);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    mbar_init(bar_s, 1); mbar_init(bar_p, 8); mbar_init(bar_o, 1); mbar_init(bar_free, 8);
-    mbar_init(q0_full, 1); mbar_init(q0_empty, 1);
-    mbar_init(q1_full, 1); mbar_init(q1_empty, 2);      // S(1) retired + row-256 warp done
-    mbar_init(v_full, 1);  mbar_init(v_empty, 2);       // P.V(1) retired + row-256 warp done
-    for (int i = 0; i < 2; ++i) { mbar_init(k_full + 8 * i, 1); mbar_init(k_empty + 8 * i, 2); }
+    for (int u = 0; u < 2; ++u) {
+      mbar_init(bar_s + 8 * u, 1); mbar_init(bar_p + 8 * u, 4); mbar_init(bar_o + 8 * u, 1); mbar_init(bar_free + 8 * u, 4);
+      mbar_init(q_full + 8 * u, 1);
+      mbar_init(k_full + 8 * u, 1);
+      mbar_init(k_empty + 8 * u, 10);      // S(1) retired + 8 softmax warps (key 256) + row-256 warp
+    }
+    mbar_init(q_empty, 5);                 // S(0) retired + 4 softmax warps of tile 0 (their q rows, for key 256)
+    mbar_init(q_empty + 8, 6);             // S(1) retired + 4 softmax warps of tile 1 + row-256 warp
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 10);                // P.V(1) retired + 8 softmax warps (key 256) + row-256 warp
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc<1>(tmem_slot, VA_TMEM_COLS);
@@ -152,8 +164,7 @@ vit_attention_tc_kernel(const VitAttnParams p) {
   const uint32_t tmem = *tmem_slot_ptr;
 
   constexpr uint32_t IDESC_S256 = make_idesc_f16(128, 256);
-  constexpr uint32_t IDESC_S16 = make_idesc_f16(128, 16);
-  constexpr uint32_t IDESC_O = make_idesc_f16(128, VA_DP) | (1u << 16);   // B (= V) is MN-major
+  constexpr uint32_t IDESC_O = make_idesc_f16(128, 48) | (1u << 16);      // half of the head dim; B (= V) is MN-major
   constexpr int CH = VA_D / 8;            // 11 16-byte chunks per row
 
   if (warp >= 10) {
@@ -163,9 +174,9 @@ vit_attention_tc_kernel(const VitAttnParams p) {
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
       const int b = item / p.heads, h = item - b * p.heads;
       const __half* src; long long ts; int row0, rows; uint32_t dst, full, empty, par;
-      if (which == 0)      { src = p.q + b * p.q_bs + h * p.q_hs; ts = p.q_ts; row0 = 0;   rows = 128; dst = sQ0; full = q0_full; empty = q0_empty; par = n & 1; }
+      if (which == 0)      { src = p.q + b * p.q_bs + h * p.q_hs; ts = p.q_ts; row0 = 0;   rows = 128; dst = sQ0; full = q_full; empty = q_empty; par = n & 1; }
       else if (which == 1) { src = p.k + b * p.k_bs + h * p.k_hs; ts = p.k_ts; row0 = 0;   rows = VA_N; dst = sK0 + (n & 1) * VA_K_BYTES; full = k_full + 8 * (n & 1); empty = k_empty + 8 * (n & 1); par = (n >> 1) & 1; }
-      else if (which == 2) { src = p.q + b * p.q_bs + h * p.q_hs; ts = p.q_ts; row0 = 128; rows = VA_N - 128; dst = sQ1; full = q1_full; empty = q1_empty; par = n & 1; }
+      else if (which == 2) { src = p.q + b * p.q_bs + h * p.q_hs; ts = p.q_ts; row0 = 128; rows = VA_N - 128; dst = sQ1; full = q_full + 8; empty = q_empty + 8; par = n & 1; }
       else                 { src = p.v + b * p.v_bs + h * p.v_hs; ts = p.v_ts; row0 = 0;   rows = VA_N; dst = sV; full = v_full; empty = v_empty; par = n & 1; }
       mbar_wait(empty, par ^ 1);            // previous contents consumed (passes immediately the first time)
       const int total = rows * CH;
@@ -183,47 +194,41 @@ vit_attention_tc_kernel(const VitAttnParams p) {
     if (lane == 0) {
       uint32_t n = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
-        const uint32_t kb = n & 1, c0 = 2 * n;
+        const uint32_t kb = n & 1, pn = n & 1;
         const uint32_t sK = sK0 + kb * VA_K_BYTES;
-        auto issue_s = [&](uint32_t qa) {       // S = Q_tile K^T : 128 x 272 into TMEM columns [0, 272)
+        auto issue_s = [&](int u) {             // S_u = Q_u K^T (keys 0..255) into the tile's 256 TMEM columns
+          const uint32_t qa = u == 0 ? sQ0 : sQ1;
 #pragma unroll
           for (int j = 0; j < VA_DP / 16; ++j)
-            umma_f16<1>(tmem, make_desc_nosw(qa + j * 256, 128, VA_G), make_desc_nosw(sK + j * 256, 128, VA_G), IDESC_S256,
-                        j > 0);
+            umma_f16<1>(tmem + u * VA_TILE_COLS, make_desc_nosw(qa + j * 256, 128, VA_G),
+                        make_desc_nosw(sK + j * 256, 128, VA_G), IDESC_S256, j > 0);
+          umma_commit<1>(bar_s + 8 * u);
+          umma_commit<1>(q_empty + 8 * u);      // the Q rows may be overwritten once S has retired (and the softmax
+        };                                      // warps have read their rows for key 256)
+        auto issue_pv = [&](int u) {            // O_u = P_u V: A = P in TMEM, B = V (MN-major), two 48-wide halves of d
+          const uint32_t tb = tmem + u * VA_TILE_COLS;
 #pragma unroll
-          for (int j = 0; j < VA_DP / 16; ++j)
-            umma_f16<1>(tmem + 256, make_desc_nosw(qa + j * 256, 128, VA_G),
-                        make_desc_nosw(sK + 32 * VA_G + j * 256, 128, VA_G), IDESC_S16, j > 0);
-          umma_commit<1>(bar_s);
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t pa = tb + (j < 8 ? j * 8 : 128 + (j - 8) * 8);
+            umma_f16_ts(tb + VA_OLO_COL, pa, make_desc_nosw(sV + j * 2 * VA_G, VA_G, 128), IDESC_O, j > 0);
+            umma_f16_ts(tb + VA_OHI_COL, pa, make_desc_nosw(sV + j * 2 * VA_G + 6 * 128, VA_G, 128), IDESC_O, j > 0);
+          }
+          umma_commit<1>(bar_o + 8 * u);
         };
-        auto issue_pv = [&]() {                 // O = P V : A = P in TMEM, B = V (MN-major), 17 steps of 16 keys
-#pragma unroll
-          for (int j = 0; j < VA_KP / 16; ++j)
-            umma_f16_ts(tmem + VA_O_COL, tmem + VA_P_COL + j * 8, make_desc_nosw(sV + j * 2 * VA_G, VA_G, 128), IDESC_O,
-                        j > 0);
-          umma_commit<1>(bar_o);
-        };
-        mbar_wait(q0_full, n & 1);
         mbar_wait(k_full + 8 * kb, (n >> 1) & 1);
-        tc_fence_after();
-        issue_s(sQ0);
-        umma_commit<1>(q0_empty);               // Q rows 0..127 may be overwritten once S(0) has retired
-        // ---- tile 0 ----
-        mbar_wait(bar_p, c0 & 1);               // P(0) in TMEM, S(0) fully read
-        mbar_wait(v_full, n & 1);
-        if (c0 > 0) mbar_wait(bar_free, (c0 - 1) & 1);   // O of the previous tile read out
-        tc_fence_after();
-        issue_pv();
-        mbar_wait(q1_full, n & 1);
-        tc_fence_after();
-        issue_s(sQ1);                           // runs under tile 0's epilogue
-        umma_commit<1>(q1_empty);
+        for (int u = 0; u < 2; ++u) {
+          mbar_wait(q_full + 8 * u, pn);
+          if (n > 0) mbar_wait(bar_free + 8 * u, pn ^ 1);    // O of this pipeline's previous tile has been read out
+          tc_fence_after();
+          issue_s(u);
+        }
         umma_commit<1>(k_empty + 8 * kb);
-        // ---- tile 1 ----
-        mbar_wait(bar_p, (c0 + 1) & 1);
-        mbar_wait(bar_free, c0 & 1);
-        tc_fence_after();
-        issue_pv();
+        mbar_wait(v_full, pn);
+        for (int u = 0; u < 2; ++u) {
+          mbar_wait(bar_p + 8 * u, pn);          // P_u in TMEM, S_u fully read
+          tc_fence_after();
+          issue_pv(u);
+        }
         umma_commit<1>(v_empty);
       }
     }
@@ -236,7 +241,7 @@ vit_attention_tc_kernel(const VitAttnParams p) {
       const uint32_t kb = n & 1;
       const uint8_t* gK = gen + (sK0 - base) + kb * VA_K_BYTES;
       mbar_wait(k_full + 8 * kb, (n >> 1) & 1);
-      mbar_wait(q1_full, n & 1);
+      mbar_wait(q_full + 8, n & 1);
       mbar_wait(v_full, n & 1);
       float qv[VA_D];
       {
@@ -307,7 +312,7 @@ vit_attention_tc_kernel(const VitAttnParams p) {
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(k_empty + 8 * kb);
-        mbar_arrive(q1_empty);
+        mbar_arrive(q_empty + 8);
         mbar_arrive(v_empty);
       }
 #pragma unroll
@@ -328,108 +333,117 @@ vit_attention_tc_kernel(const VitAttnParams p) {
       }
     }
   } else {
-    // ======================= softmax + epilogue (rows 0..255 in two 128-row tiles) =======================
-    const int quarter = warp & 3, hf = warp >> 2;
-    const int rl = quarter * 32 + lane;               // row inside the tile
-    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+    // ======================= softmax + epilogue: warps 0-3 own tile 0 (rows 0..127), warps 4-7 tile 1 =======================
+    const int quarter = warp & 3, u = warp >> 2;
+    const int rl = quarter * 32 + lane;               // row inside the tile: one full row (256 + 1 keys) per thread
+    const int row = u * 128 + rl;
+    const uint32_t trow = tmem + u * VA_TILE_COLS + ((uint32_t)(quarter * 32) << 16);
+    const uint8_t* qrow = (u == 0 ? gQ0 : gQ1) + (uint32_t)(rl >> 3) * VA_G + (rl & 7) * 16;
     uint32_t n = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
       const int b = item / p.heads, h = item - b * p.heads;
-      for (int t = 0; t < 2; ++t) {
-        const uint32_t par = (2 * n + t) & 1;
-        const int row = t * 128 + rl;
-        mbar_wait(bar_s, par);
-        tc_fence_after();
-        // pass 1: row maximum over this warp's half of the keys
-        float mx = -INFINITY;
-        {
-          uint32_t ra[32], rb[32];
-          tmem_ld32(trow + hf * 128, ra);
-          tmem_ld32(trow + hf * 128 + 32, rb);
-          tmem_ld_wait();
+      const uint32_t kb = n & 1, pn = n & 1;
+      // ---- key 256 on the CUDA cores (the MMA covers keys 0..255): s256 = q_row . k_256, under the S MMA ----
+      mbar_wait(q_full + 8 * u, pn);
+      mbar_wait(k_full + 8 * kb, (n >> 1) & 1);
+      float s256 = 0.0f;
+      {
+        const uint8_t* k256 = gen + (sK0 - base) + kb * VA_K_BYTES + 32 * VA_G;   // row 256 = first row of group 32
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[j]), __uint_as_float(rb[j])));
-          tmem_ld32(trow + hf * 128 + 64, ra);
-          tmem_ld32(trow + hf * 128 + 96, rb);
-          tmem_ld_wait();
+        for (int c = 0; c < CH; ++c) {
+          const uint4 qa = *reinterpret_cast<const uint4*>(qrow + c * 128);
+          const uint4 ka = *reinterpret_cast<const uint4*>(k256 + c * 128);
+          const __half2* q2 = reinterpret_cast<const __half2*>(&qa);
+          const __half2* k2 = reinterpret_cast<const __half2*>(&ka);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[j]), __uint_as_float(rb[j])));
-        }
-        float s256 = 0.0f;
-        if (hf == 1) {
-          uint32_t r[16];
-          tmem_ld16(trow + 256, r);
-          tmem_ld_wait();
-          s256 = __uint_as_float(r[0]);                   // key 256; columns 257..271 are padding
-          mx = fmaxf(mx, s256);
-        }
-        s_max[hf * 128 + rl] = mx;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float m = fmaxf(s_max[rl], s_max[128 + rl]) * p.scale_log2;   // scale > 0
-        float sum = 0.0f;
-        // pass 2: P = exp2(s*scale*log2e - m), rounded to fp16 (as the reference does under autocast), packed two
-        // per TMEM column.  The P columns are free: S of this tile was issued after the previous P.V.
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld32(trow + hf * 128 + c * 32, r);
-          tmem_ld_wait();
-          uint32_t pk[16];
-#pragma unroll
-          for (int g = 0; g < 16; ++g)
-            pk[g] = pack2(ex2f(fmaf(__uint_as_float(r[2 * g]), p.scale_log2, -m)),
-                          ex2f(fmaf(__uint_as_float(r[2 * g + 1]), p.scale_log2, -m)), sum);
-          tmem_st16(trow + VA_P_COL + hf * 64 + c * 16, pk);      // keys hf*128 + c*32 .. +31
-        }
-        if (hf == 1) {
-          uint32_t pk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          pk[0] = pack2(ex2f(fmaf(s256, p.scale_log2, -m)), 0.0f, sum);
-          tmem_st8(trow + VA_P_COL + 128, pk);                     // keys 256..271 (only 256 exists)
-        }
-        tmem_st_wait();
-        s_sum[hf * 128 + rl] = sum;
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p);
-
-        mbar_wait(bar_o, par);
-        tc_fence_after();
-        {
-          const float total = s_sum[rl] + s_sum[128 + rl];
-          const float inv = total > 0.0f ? 1.0f / total : 0.0f;
-          uint32_t r0[32], r1[16];
-          // hf 0: output dims 0..47, hf 1: 48..95 (only 48..87 exist)
-          tmem_ld32(trow + VA_O_COL + hf * 48, r0);
-          tmem_ld16(trow + VA_O_COL + hf * 48 + 32, r1);
-          tmem_ld_wait();
-          // O is in registers: hand the TMEM columns back before the global stores
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_free);
-          __half* og = p.o + b * p.o_bs + h * p.o_hs + (long long)row * p.o_ts + hf * 48;
-          float unused = 0.0f;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 o;
-            o.x = pack2(__uint_as_float(r0[g * 8 + 0]) * inv, __uint_as_float(r0[g * 8 + 1]) * inv, unused);
-            o.y = pack2(__uint_as_float(r0[g * 8 + 2]) * inv, __uint_as_float(r0[g * 8 + 3]) * inv, unused);
-            o.z = pack2(__uint_as_float(r0[g * 8 + 4]) * inv, __uint_as_float(r0[g * 8 + 5]) * inv, unused);
-            o.w = pack2(__uint_as_float(r0[g * 8 + 6]) * inv, __uint_as_float(r0[g * 8 + 7]) * inv, unused);
-            *reinterpret_cast<uint4*>(og + g * 8) = o;
-          }
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            if (hf == 0 || g == 0) {     // dims 80..87 exist, 88..95 are padding
-              uint4 o;
-              o.x = pack2(__uint_as_float(r1[g * 8 + 0]) * inv, __uint_as_float(r1[g * 8 + 1]) * inv, unused);
-              o.y = pack2(__uint_as_float(r1[g * 8 + 2]) * inv, __uint_as_float(r1[g * 8 + 3]) * inv, unused);
-              o.z = pack2(__uint_as_float(r1[g * 8 + 4]) * inv, __uint_as_float(r1[g * 8 + 5]) * inv, unused);
-              o.w = pack2(__uint_as_float(r1[g * 8 + 6]) * inv, __uint_as_float(r1[g * 8 + 7]) * inv, unused);
-              *reinterpret_cast<uint4*>(og + 32 + g * 8) = o;
-            }
+          for (int j = 0; j < 4; ++j) {
+            const float2 qf = __half22float2(q2[j]), kf = __half22float2(k2[j]);
+            s256 = fmaf(qf.x, kf.x, s256);
+            s256 = fmaf(qf.y, kf.y, s256);
           }
         }
       }
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(q_empty + 8 * u); mbar_arrive(k_empty + 8 * kb); }
+
+      mbar_wait(bar_s + 8 * u, pn);
+      tc_fence_after();
+      // pass 1: row maximum
+      float mx = s256;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t ra[32], rb[32];
+        tmem_ld32(trow + c * 64, ra);
+        tmem_ld32(trow + c * 64 + 32, rb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[j]), __uint_as_float(rb[j])));
+      }
+      const float m = mx * p.scale_log2;                 // scale > 0
+      // pass 2: P = exp2(s*scale*log2e - m), rounded to fp16 (as the reference does under autocast), written in
+      // place: chunk c of S (32 columns) becomes 16 packed columns that lie inside chunks already consumed
+      float sum = 0.0f;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[32];
+        tmem_ld32(trow + c * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int g = 0; g < 16; ++g)
+          pk[g] = pack2(ex2f(fmaf(__uint_as_float(r[2 * g]), p.scale_log2, -m)),
+                        ex2f(fmaf(__uint_as_float(r[2 * g + 1]), p.scale_log2, -m)), sum);
+        tmem_st16(trow + (c < 4 ? c * 16 : 128 + (c - 4) * 16), pk);
+      }
+      const float p256 = __half2float(__float2half_rn(ex2f(fmaf(s256, p.scale_log2, -m))));
+      sum += p256;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p + 8 * u);
+
+      const float inv = 1.0f / sum;
+      const float w256 = p256 * inv;
+      mbar_wait(bar_o + 8 * u, pn);
+      tc_fence_after();
+      __half* og = p.o + b * p.o_bs + h * p.o_hs + (long long)row * p.o_ts;
+      const uint8_t* v256 = gV + 32 * VA_G;                // V row 256 = first row of group 32 (v_full was needed by P.V)
+      float unused = 0.0f;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {                    // dims 0..47, then 48..95 (48..87 exist)
+        uint32_t r0[32], r1[16];
+        tmem_ld32(trow + (hh == 0 ? VA_OLO_COL : VA_OHI_COL), r0);
+        tmem_ld16(trow + (hh == 0 ? VA_OLO_COL : VA_OHI_COL) + 32, r1);
+        tmem_ld_wait();
+        if (hh == 1) {
+          // both halves of O are in registers / stored: hand the tile's TMEM columns back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_free + 8 * u);
+        }
+#pragma unroll
+        for (int g = 0; g < 6; ++g) {
+          if (hh == 0 || g < 5) {                          // chunk 11 (dims 88..95) is padding
+            const uint4 vv = *reinterpret_cast<const uint4*>(v256 + (hh * 6 + g) * 128);
+            const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
+            float o8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o8[j] = __uint_as_float(g < 4 ? r0[g * 8 + j] : r1[(g - 4) * 8 + j]) * inv;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 vf = __half22float2(v2[j]);
+              o8[2 * j] = fmaf(w256, vf.x, o8[2 * j]);
+              o8[2 * j + 1] = fmaf(w256, vf.y, o8[2 * j + 1]);
+            }
+            uint4 o;
+            o.x = pack2(o8[0], o8[1], unused); o.y = pack2(o8[2], o8[3], unused);
+            o.z = pack2(o8[4], o8[5], unused); o.w = pack2(o8[6], o8[7], unused);
+            *reinterpret_cast<uint4*>(og + (hh * 6 + g) * 8) = o;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(v_empty);                 // V row 256 has been read
     }
   }
 
