@@ -23,11 +23,11 @@ namespace sb {
 
 constexpr int VA_D = 88, VA_DP = 96, VA_N = 257, VA_KP = 272;
 constexpr int VA_G = (VA_DP / 8) * 128;            // 1536: bytes of one 8-row group (12 chunks of 8 halves)
-constexpr int VA_K_BYTES = 33 * VA_G;              // keys 0..263 (x2 buffers)
+constexpr int VA_K_BYTES = 34 * VA_G;              // keys 0..271 (the N=256 MMA reads groups 0..31; row 256 sits in group 32)
 constexpr int VA_Q0_BYTES = 16 * VA_G;             // query rows 0..127
 constexpr int VA_Q1_BYTES = 17 * VA_G;             // query rows 128..255 and the group holding row 256
-constexpr int VA_V_BYTES = 34 * VA_G;              // keys 0..271 (P.V walks 17 steps of 16 keys)
-constexpr int VA_DATA_BYTES = 2 * VA_K_BYTES + VA_Q0_BYTES + VA_Q1_BYTES + VA_V_BYTES;
+constexpr int VA_V_BYTES = 33 * VA_G;              // keys 0..263, x2 buffers (P.V walks 16 steps of 16 keys)
+constexpr int VA_DATA_BYTES = VA_K_BYTES + VA_Q0_BYTES + VA_Q1_BYTES + 2 * VA_V_BYTES;
 constexpr int VA_MISC_BYTES = 4 * 128 * 4 + 1088 + 256;   // max/sum exchange, row-256 probabilities, barriers, tmem slot
 constexpr int VA_SMEM = VA_DATA_BYTES + VA_MISC_BYTES + 128;
 constexpr int VA_THREADS = 448;                       // 8 softmax warps, MMA warp, row-256 warp, 4 loader warps
@@ -46,6 +46,7 @@ struct VitAttnParams {
   long long q_bs, q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, o_bs, o_hs, o_ts;
   int items, heads;
   float scale_log2;
+  long long* dbg;    // optional timeline of block 0: [16 slots][64 items][8 events] clock64 stamps (tools/attn_timeline.py)
 };
 
 // No-swizzle canonical layouts (8 x 16-byte core matrices, 128 B each).  The shared-memory image used here is
@@ -118,25 +119,31 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, float& sum) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+#define VA_STAMP(slot, ev)                                                                            \
+  do {                                                                                                \
+    if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && n < 64) p.dbg[((slot) * 64 + n) * 8 + (ev)] = clock64(); \
+  } while (0)
+
 __global__ void __launch_bounds__(VA_THREADS, 1)
 vit_attention_tc_kernel(const VitAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sK0 = base, sQ0 = sK0 + 2 * VA_K_BYTES, sQ1 = sQ0 + VA_Q0_BYTES, sV = sQ1 + VA_Q1_BYTES;
-  const uint32_t misc = sV + VA_V_BYTES;
+  const uint32_t sK0 = base, sQ0 = sK0 + VA_K_BYTES, sQ1 = sQ0 + VA_Q0_BYTES, sV0 = sQ1 + VA_Q1_BYTES;
+  const uint32_t misc = sV0 + 2 * VA_V_BYTES;
   float* s_max = reinterpret_cast<float*>(gen + (misc - base));     // [2][128]
   float* s_sum = s_max + 256;                                       // [2][128]
   float* s_cls = s_sum + 256;                                       // [272] probabilities of query row 256
   const uint32_t bars = misc + 2048 + 1088;
   const uint32_t bar_s = bars, bar_p = bars + 16, bar_o = bars + 32, bar_free = bars + 48;      // [2] each: per tile pipeline
   const uint32_t q_full = bars + 64 /*[2]*/, q_empty = bars + 80 /*[2]*/;
-  const uint32_t v_full = bars + 96, v_empty = bars + 104, k_full = bars + 112 /*[2]*/, k_empty = bars + 128 /*[2]*/;
+  const uint32_t k_full = bars + 96, k_empty = bars + 104, v_full = bars + 112 /*[2]*/, v_empty = bars + 128 /*[2]*/;
   const uint32_t tmem_slot = bars + 144;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
   uint8_t* gQ0 = gen + (sQ0 - base);
   uint8_t* gQ1 = gen + (sQ1 - base);
-  uint8_t* gV = gen + (sV - base);
+  uint8_t* gV0 = gen + (sV0 - base);
+  const uint8_t* gK = gen + (sK0 - base);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -144,13 +151,13 @@ vit_attention_tc_kernel(const VitAttnParams p) {
     for (int u = 0; u < 2; ++u) {
       mbar_init(bar_s + 8 * u, 1); mbar_init(bar_p + 8 * u, 4); mbar_init(bar_o + 8 * u, 1); mbar_init(bar_free + 8 * u, 4);
       mbar_init(q_full + 8 * u, 1);
-      mbar_init(k_full + 8 * u, 1);
-      mbar_init(k_empty + 8 * u, 10);      // S(1) retired + 8 softmax warps (key 256) + row-256 warp
+      mbar_init(v_full + 8 * u, 1);
+      mbar_init(v_empty + 8 * u, 10);      // P.V(1) retired + 8 softmax warps (value row 256) + row-256 warp
     }
     mbar_init(q_empty, 5);                 // S(0) retired + 4 softmax warps of tile 0 (their q rows, for key 256)
     mbar_init(q_empty + 8, 6);             // S(1) retired + 4 softmax warps of tile 1 + row-256 warp
-    mbar_init(v_full, 1);
-    mbar_init(v_empty, 10);                // P.V(1) retired + 8 softmax warps (key 256) + row-256 warp
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 10);                // S(1) retired + 8 softmax warps (key row 256) + row-256 warp
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc<1>(tmem_slot, VA_TMEM_COLS);
@@ -169,39 +176,53 @@ vit_attention_tc_kernel(const VitAttnParams p) {
 
   if (warp >= 10) {
     // ======================= loaders: one warp per operand buffer, cp.async 16-byte copies =======================
+    // One instruction moves 8 rows x 4 chunks (512 B): the 8 rows fill one 128-byte core-matrix column each, so the
+    // shared-memory side needs the minimum 4 wavefronts, and the addresses are pure adds (no divisions).
     const int which = warp - 10;            // 0: Q rows 0..127, 1: K, 2: Q rows 128..256, 3: V
+    const int r8 = lane & 7, cq = lane >> 3;
     uint32_t n = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
       const int b = item / p.heads, h = item - b * p.heads;
       const __half* src; long long ts; int row0, rows; uint32_t dst, full, empty, par;
       if (which == 0)      { src = p.q + b * p.q_bs + h * p.q_hs; ts = p.q_ts; row0 = 0;   rows = 128; dst = sQ0; full = q_full; empty = q_empty; par = n & 1; }
-      else if (which == 1) { src = p.k + b * p.k_bs + h * p.k_hs; ts = p.k_ts; row0 = 0;   rows = VA_N; dst = sK0 + (n & 1) * VA_K_BYTES; full = k_full + 8 * (n & 1); empty = k_empty + 8 * (n & 1); par = (n >> 1) & 1; }
+      else if (which == 1) { src = p.k + b * p.k_bs + h * p.k_hs; ts = p.k_ts; row0 = 0;   rows = VA_N; dst = sK0; full = k_full; empty = k_empty; par = n & 1; }
       else if (which == 2) { src = p.q + b * p.q_bs + h * p.q_hs; ts = p.q_ts; row0 = 128; rows = VA_N - 128; dst = sQ1; full = q_full + 8; empty = q_empty + 8; par = n & 1; }
-      else                 { src = p.v + b * p.v_bs + h * p.v_hs; ts = p.v_ts; row0 = 0;   rows = VA_N; dst = sV; full = v_full; empty = v_empty; par = n & 1; }
+      else                 { src = p.v + b * p.v_bs + h * p.v_hs; ts = p.v_ts; row0 = 0;   rows = VA_N; dst = sV0 + (n & 1) * VA_V_BYTES; full = v_full + 8 * (n & 1); empty = v_empty + 8 * (n & 1); par = (n >> 1) & 1; }
+      VA_STAMP(10 + which, 0);
       mbar_wait(empty, par ^ 1);            // previous contents consumed (passes immediately the first time)
-      const int total = rows * CH;
-      for (int i = lane; i < total; i += 32) {
-        const int r = i / CH, c = i - r * CH;
-        cp_async16_tc(dst + (uint32_t)(r >> 3) * VA_G + c * 128 + (r & 7) * 16, src + (long long)(row0 + r) * ts + c * 8);
+      VA_STAMP(10 + which, 1);
+      const int groups = (rows + 7) >> 3;
+      const __half* rp = src + (long long)(row0 + r8) * ts + cq * 8;
+      uint32_t dp = dst + cq * 128 + r8 * 16;
+      for (int g = 0; g < groups; ++g) {
+        if (g * 8 + r8 < rows) {
+          cp_async16_tc(dp, rp);                                  // chunks 0..3
+          cp_async16_tc(dp + 4 * 128, rp + 32);                   // chunks 4..7
+          if (cq < 3) cp_async16_tc(dp + 8 * 128, rp + 64);       // chunks 8..10 (chunk 11 is the zero padding)
+        }
+        rp += 8 * ts;
+        dp += VA_G;
       }
+      VA_STAMP(10 + which, 2);
       cp_async_wait_all_tc();
       fence_proxy_async_smem();             // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(full);
+      VA_STAMP(10 + which, 3);
     }
   } else if (warp == 8) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
       uint32_t n = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
-        const uint32_t kb = n & 1, pn = n & 1;
-        const uint32_t sK = sK0 + kb * VA_K_BYTES;
+        const uint32_t vb = n & 1, pn = n & 1;
+        const uint32_t sV = sV0 + vb * VA_V_BYTES;
         auto issue_s = [&](int u) {             // S_u = Q_u K^T (keys 0..255) into the tile's 256 TMEM columns
           const uint32_t qa = u == 0 ? sQ0 : sQ1;
 #pragma unroll
           for (int j = 0; j < VA_DP / 16; ++j)
             umma_f16<1>(tmem + u * VA_TILE_COLS, make_desc_nosw(qa + j * 256, 128, VA_G),
-                        make_desc_nosw(sK + j * 256, 128, VA_G), IDESC_S256, j > 0);
+                        make_desc_nosw(sK0 + j * 256, 128, VA_G), IDESC_S256, j > 0);
           umma_commit<1>(bar_s + 8 * u);
           umma_commit<1>(q_empty + 8 * u);      // the Q rows may be overwritten once S has retired (and the softmax
         };                                      // warps have read their rows for key 256)
@@ -215,34 +236,39 @@ vit_attention_tc_kernel(const VitAttnParams p) {
           }
           umma_commit<1>(bar_o + 8 * u);
         };
-        mbar_wait(k_full + 8 * kb, (n >> 1) & 1);
+        VA_STAMP(8, 0);
+        mbar_wait(k_full, pn);
         for (int u = 0; u < 2; ++u) {
           mbar_wait(q_full + 8 * u, pn);
           if (n > 0) mbar_wait(bar_free + 8 * u, pn ^ 1);    // O of this pipeline's previous tile has been read out
           tc_fence_after();
+          VA_STAMP(8, 1 + u);
           issue_s(u);
         }
-        umma_commit<1>(k_empty + 8 * kb);
-        mbar_wait(v_full, pn);
+        umma_commit<1>(k_empty);
+        VA_STAMP(8, 3);
+        mbar_wait(v_full + 8 * vb, (n >> 1) & 1);
+        VA_STAMP(8, 4);
         for (int u = 0; u < 2; ++u) {
           mbar_wait(bar_p + 8 * u, pn);          // P_u in TMEM, S_u fully read
           tc_fence_after();
+          VA_STAMP(8, 5 + u);
           issue_pv(u);
         }
-        umma_commit<1>(v_empty);
+        umma_commit<1>(v_empty + 8 * vb);
+        VA_STAMP(8, 7);
       }
     }
     __syncwarp();
   } else if (warp == 9) {
     // ======================= query row 256 (the 257th token) on the CUDA cores =======================
+    // 1 row x 257 keys x 88 dims: a third 128-row MMA tile would be 99% padding.  Lane <-> keys {lane + 32 i}; the nine
+    // dot products / nine value rows per lane are independent chains, so a single warp keeps the FMA pipe busy.
     uint32_t n = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
       const int b = item / p.heads, h = item - b * p.heads;
-      const uint32_t kb = n & 1;
-      const uint8_t* gK = gen + (sK0 - base) + kb * VA_K_BYTES;
-      mbar_wait(k_full + 8 * kb, (n >> 1) & 1);
+      const uint32_t vb = n & 1;
       mbar_wait(q_full + 8, n & 1);
-      mbar_wait(v_full, n & 1);
       float qv[VA_D];
       {
         const uint8_t* qrow = gQ1 + 16 * VA_G;             // row 256 = local row 128 = first row of group 16
@@ -254,82 +280,84 @@ vit_attention_tc_kernel(const VitAttnParams p) {
           for (int j = 0; j < 8; ++j) qv[c * 8 + j] = __half2float(hh[j]);
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_empty + 8);             // the q row now lives in registers
+      mbar_wait(k_full, n & 1);
       float sc[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) sc[i] = 0.0f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          const int key = min(lane + 32 * i, VA_N - 1);    // lanes past the end recompute key 256 (masked below)
+          const uint4 raw = *reinterpret_cast<const uint4*>(gK + (uint32_t)(key >> 3) * VA_G + (key & 7) * 16 + c * 128);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h2[j]);
+            sc[i] = fmaf(qv[c * 8 + 2 * j], f.x, sc[i]);
+            sc[i] = fmaf(qv[c * 8 + 2 * j + 1], f.y, sc[i]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(k_empty);
       float mx = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
-        const int key = lane + 32 * i;
-        float acc = -INFINITY;
-        if (key < VA_N) {
-          acc = 0.0f;
-          const uint8_t* krow = gK + (uint32_t)(key >> 3) * VA_G + (key & 7) * 16;
-#pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(krow + c * 128);
-            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __half22float2(h2[j]);
-              acc = fmaf(qv[c * 8 + 2 * j], f.x, acc);
-              acc = fmaf(qv[c * 8 + 2 * j + 1], f.y, acc);
-            }
-          }
-          acc *= p.scale_log2;
-          mx = fmaxf(mx, acc);
-        }
-        sc[i] = acc;
+        sc[i] = (lane + 32 * i < VA_N) ? sc[i] * p.scale_log2 : -INFINITY;
+        mx = fmaxf(mx, sc[i]);
       }
       mx = warp_max(mx);
       float sum = 0.0f;
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
-        const int key = lane + 32 * i;
-        const float pr = __half2float(__float2half_rn(ex2f(sc[i] - mx)));   // rounded to fp16 like the tile path
-        sum += pr;
-        if (key < VA_KP) s_cls[key] = (key < VA_N) ? pr : 0.0f;
+        sc[i] = __half2float(__float2half_rn(ex2f(sc[i] - mx)));   // P rounded to fp16 like the tile path; 0 past the end
+        sum += sc[i];
       }
       sum = warp_sum(sum);
-      __syncwarp();
-      // out[d] = sum_k p_k V[k][d]: lane <-> (8-dim chunk, key parity)
-      const int dc = lane % CH, ph = lane / CH;     // lanes 0..21 work, 22..31 idle
-      float acc8[8];
+      // out[d] = sum_k p_k V[k][d]: every lane accumulates all 88 dims over its nine keys, then a butterfly reduction
+      mbar_wait(v_full + 8 * vb, (n >> 1) & 1);
+      const uint8_t* gV = gV0 + vb * VA_V_BYTES;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc8[j] = 0.0f;
-      if (ph < 2) {
-        for (int key = ph; key < VA_N; key += 2) {
-          const uint4 raw = *reinterpret_cast<const uint4*>(gV + (uint32_t)(key >> 3) * VA_G + dc * 128 + (key & 7) * 16);
+      for (int d = 0; d < VA_D; ++d) qv[d] = 0.0f;         // reuse the registers as the output accumulator
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int key = min(lane + 32 * i, VA_N - 1);
+        const float pk = sc[i];                            // 0 for keys past the end
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(gV + (uint32_t)(key >> 3) * VA_G + (key & 7) * 16 + c * 128);
           const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-          const float pk = s_cls[key];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float2 f = __half22float2(h2[j]);
-            acc8[2 * j] = fmaf(pk, f.x, acc8[2 * j]);
-            acc8[2 * j + 1] = fmaf(pk, f.y, acc8[2 * j + 1]);
+            qv[c * 8 + 2 * j] = fmaf(pk, f.x, qv[c * 8 + 2 * j]);
+            qv[c * 8 + 2 * j + 1] = fmaf(pk, f.y, qv[c * 8 + 2 * j + 1]);
           }
         }
       }
-      // everything this warp reads from shared memory has been read: release the buffers
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(k_empty + 8 * kb);
-        mbar_arrive(q_empty + 8);
-        mbar_arrive(v_empty);
-      }
+      if (lane == 0) mbar_arrive(v_empty + 8 * vb);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float other = __shfl_sync(0xffffffffu, acc8[j], (lane + CH) & 31);   // partner = same chunk, other parity
-        acc8[j] += other;
+      for (int d = 0; d < VA_D; ++d) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) qv[d] += __shfl_xor_sync(0xffffffffu, qv[d], o);
       }
-      if (lane < CH) {
-        const float inv = 1.0f / sum;
-        __half* og = p.o + b * p.o_bs + h * p.o_hs + (long long)(VA_N - 1) * p.o_ts + dc * 8;
-        uint4 o;
-        float unused = 0.0f;
-        o.x = pack2(acc8[0] * inv, acc8[1] * inv, unused);
-        o.y = pack2(acc8[2] * inv, acc8[3] * inv, unused);
-        o.z = pack2(acc8[4] * inv, acc8[5] * inv, unused);
-        o.w = pack2(acc8[6] * inv, acc8[7] * inv, unused);
-        *reinterpret_cast<uint4*>(og) = o;
+      const float inv = 1.0f / sum;
+      __half* og = p.o + b * p.o_bs + h * p.o_hs + (long long)(VA_N - 1) * p.o_ts;
+      float unused = 0.0f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        if (lane == c) {
+          uint4 o;
+          o.x = pack2(qv[c * 8 + 0] * inv, qv[c * 8 + 1] * inv, unused);
+          o.y = pack2(qv[c * 8 + 2] * inv, qv[c * 8 + 3] * inv, unused);
+          o.z = pack2(qv[c * 8 + 4] * inv, qv[c * 8 + 5] * inv, unused);
+          o.w = pack2(qv[c * 8 + 6] * inv, qv[c * 8 + 7] * inv, unused);
+          *reinterpret_cast<uint4*>(og + c * 8) = o;
+        }
       }
     }
   } else {
@@ -342,13 +370,15 @@ vit_attention_tc_kernel(const VitAttnParams p) {
     uint32_t n = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
       const int b = item / p.heads, h = item - b * p.heads;
-      const uint32_t kb = n & 1, pn = n & 1;
+      const uint32_t vb = n & 1, pn = n & 1;
       // ---- key 256 on the CUDA cores (the MMA covers keys 0..255): s256 = q_row . k_256, under the S MMA ----
+      VA_STAMP(warp, 0);
       mbar_wait(q_full + 8 * u, pn);
-      mbar_wait(k_full + 8 * kb, (n >> 1) & 1);
+      mbar_wait(k_full, pn);
+      VA_STAMP(warp, 1);
       float s256 = 0.0f;
       {
-        const uint8_t* k256 = gen + (sK0 - base) + kb * VA_K_BYTES + 32 * VA_G;   // row 256 = first row of group 32
+        const uint8_t* k256 = gK + 32 * VA_G;              // row 256 = first row of group 32
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           const uint4 qa = *reinterpret_cast<const uint4*>(qrow + c * 128);
@@ -364,10 +394,12 @@ vit_attention_tc_kernel(const VitAttnParams p) {
         }
       }
       __syncwarp();
-      if (lane == 0) { mbar_arrive(q_empty + 8 * u); mbar_arrive(k_empty + 8 * kb); }
+      if (lane == 0) { mbar_arrive(q_empty + 8 * u); mbar_arrive(k_empty); }
 
+      VA_STAMP(warp, 2);
       mbar_wait(bar_s + 8 * u, pn);
       tc_fence_after();
+      VA_STAMP(warp, 3);
       // pass 1: row maximum
       float mx = s256;
 #pragma unroll 1
@@ -379,6 +411,7 @@ vit_attention_tc_kernel(const VitAttnParams p) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[j]), __uint_as_float(rb[j])));
       }
+      VA_STAMP(warp, 4);
       const float m = mx * p.scale_log2;                 // scale > 0
       // pass 2: P = exp2(s*scale*log2e - m), rounded to fp16 (as the reference does under autocast), written in
       // place: chunk c of S (32 columns) becomes 16 packed columns that lie inside chunks already consumed
@@ -401,13 +434,15 @@ vit_attention_tc_kernel(const VitAttnParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p + 8 * u);
+      VA_STAMP(warp, 5);
 
       const float inv = 1.0f / sum;
       const float w256 = p256 * inv;
       mbar_wait(bar_o + 8 * u, pn);
       tc_fence_after();
+      VA_STAMP(warp, 6);
       __half* og = p.o + b * p.o_bs + h * p.o_hs + (long long)row * p.o_ts;
-      const uint8_t* v256 = gV + 32 * VA_G;                // V row 256 = first row of group 32 (v_full was needed by P.V)
+      const uint8_t* v256 = gV0 + vb * VA_V_BYTES + 32 * VA_G;   // V row 256 = first row of group 32 (P.V needed v_full)
       float unused = 0.0f;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {                    // dims 0..47, then 48..95 (48..87 exist)
@@ -443,7 +478,8 @@ vit_attention_tc_kernel(const VitAttnParams p) {
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(v_empty);                 // V row 256 has been read
+      if (lane == 0) mbar_arrive(v_empty + 8 * vb);         // V row 256 has been read
+      VA_STAMP(warp, 7);
     }
   }
 
@@ -451,6 +487,8 @@ vit_attention_tc_kernel(const VitAttnParams p) {
   __syncthreads();
   if (warp == 8) tmem_dealloc<1>(tmem, VA_TMEM_COLS);
 }
+
+long long get_option64(const char* key);
 
 bool vit_attention_tc_applicable(const seedb200_attn_desc& d) {
   return d.head_dim == VA_D && d.nq == VA_N && d.nk == VA_N && d.causal == 0 && d.o_hs % 8 == 0 && d.o_ts % 8 == 0 &&
@@ -472,6 +510,7 @@ int vit_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream) {
   p.o_bs = d.o_bs; p.o_hs = d.o_hs; p.o_ts = d.o_ts;
   p.items = d.batch * d.heads; p.heads = d.heads;
   p.scale_log2 = d.scale * 1.4426950408889634f;
+  p.dbg = reinterpret_cast<long long*>(static_cast<uintptr_t>(get_option64("vit_attention_dbg_ptr")));
   int grid = num_sms();
   if (grid > p.items) grid = p.items;
   profile_mark_begin(1, stream);

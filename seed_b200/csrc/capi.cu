@@ -49,6 +49,8 @@ static std::map<std::string, int>& options() {
   static std::map<std::string, int> o = {{"vit_attention_tc", 1}, {"gemm_ksub", 2}};
   return o;
 }
+static long long g_dbg_ptr = 0;
+long long get_option64(const char* key) { return std::string(key) == "vit_attention_dbg_ptr" ? g_dbg_ptr : 0; }
 int get_option(const char* key) {
   auto it = options().find(key);
   return it == options().end() ? 0 : it->second;
@@ -115,6 +117,13 @@ int seedb200_set_option(const char* key, int value) {
     sb::set_error("set_option: null key");
     return SEEDB200_ERR_INVALID;
   }
+  return sb::set_option(key, value);
+}
+
+/* debug only (not declared in seedb200.h): device buffer that receives the attention kernel's timeline */
+void seedb200_debug_set_attn_timeline(void* dev_ptr) { sb::g_dbg_ptr = (long long)(uintptr_t)dev_ptr; }
+
+static int seedb200_set_option_unused(const char* key, int value) {
   return sb::set_option(key, value);
 }
 
