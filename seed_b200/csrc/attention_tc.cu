@@ -138,7 +138,9 @@ vit_attention_tc_kernel(const VitAttnParams p) {
   const uint32_t bar_s = bars, bar_p = bars + 16, bar_o = bars + 32, bar_free = bars + 48;      // [2] each: per tile pipeline
   const uint32_t q_full = bars + 64 /*[2]*/, q_empty = bars + 80 /*[2]*/;
   const uint32_t k_full = bars + 96, k_empty = bars + 104, v_full = bars + 112 /*[2]*/, v_empty = bars + 128 /*[2]*/;
-  const uint32_t tmem_slot = bars + 144;
+  const uint32_t cls_bar = bars + 144;           // 8 softmax warps -> row-256 warp: scores of query 256 are in s_cls
+  const uint32_t cls_done = bars + 152;          // row-256 warp -> softmax warps: s_cls may be overwritten
+  const uint32_t tmem_slot = bars + 160;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
   uint8_t* gQ0 = gen + (sQ0 - base);
   uint8_t* gQ1 = gen + (sQ1 - base);
@@ -155,9 +157,11 @@ vit_attention_tc_kernel(const VitAttnParams p) {
       mbar_init(v_empty + 8 * u, 10);      // P.V(1) retired + 8 softmax warps (value row 256) + row-256 warp
     }
     mbar_init(q_empty, 5);                 // S(0) retired + 4 softmax warps of tile 0 (their q rows, for key 256)
-    mbar_init(q_empty + 8, 6);             // S(1) retired + 4 softmax warps of tile 1 + row-256 warp
+    mbar_init(q_empty + 8, 10);            // S(1) retired + all 8 softmax warps (tile-1 rows, query row 256) + row-256 warp
+    mbar_init(cls_bar, 8);
+    mbar_init(cls_done, 1);
     mbar_init(k_full, 1);
-    mbar_init(k_empty, 10);                // S(1) retired + 8 softmax warps (key row 256) + row-256 warp
+    mbar_init(k_empty, 10);                // S(1) retired + 8 softmax warps + row-256 warp (key row 256)
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc<1>(tmem_slot, VA_TMEM_COLS);
@@ -262,103 +266,93 @@ vit_attention_tc_kernel(const VitAttnParams p) {
     __syncwarp();
   } else if (warp == 9) {
     // ======================= query row 256 (the 257th token) on the CUDA cores =======================
-    // 1 row x 257 keys x 88 dims: a third 128-row MMA tile would be 99% padding.  Lane <-> keys {lane + 32 i}; the nine
-    // dot products / nine value rows per lane are independent chains, so a single warp keeps the FMA pipe busy.
+    // 1 row x 257 keys x 88 dims: a third 128-row MMA tile would be 99% padding.  The 256 softmax threads each
+    // contribute the score of "their" key (thread <-> key), this warp adds key 256, runs the softmax over the 257
+    // scores and the P.V product with the head dims spread over the lanes (no cross-lane reduction).
     uint32_t n = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
       const int b = item / p.heads, h = item - b * p.heads;
       const uint32_t vb = n & 1;
+      VA_STAMP(9, 0);
       mbar_wait(q_full + 8, n & 1);
-      float qv[VA_D];
-      {
-        const uint8_t* qrow = gQ1 + 16 * VA_G;             // row 256 = local row 128 = first row of group 16
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const uint4 raw = *reinterpret_cast<const uint4*>(qrow + c * 128);
-          const __half* hh = reinterpret_cast<const __half*>(&raw);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) qv[c * 8 + j] = __half2float(hh[j]);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(q_empty + 8);             // the q row now lives in registers
       mbar_wait(k_full, n & 1);
-      float sc[9];
+      VA_STAMP(9, 1);
+      // score of key 256: lanes 0..10 take one 8-dim chunk each
+      float part = 0.0f;
+      if (lane < CH) {
+        const uint4 qa = *reinterpret_cast<const uint4*>(gQ1 + 16 * VA_G + lane * 128);
+        const uint4 ka = *reinterpret_cast<const uint4*>(gK + 32 * VA_G + lane * 128);
+        const __half2* q2 = reinterpret_cast<const __half2*>(&qa);
+        const __half2* k2 = reinterpret_cast<const __half2*>(&ka);
 #pragma unroll
-      for (int i = 0; i < 9; ++i) sc[i] = 0.0f;
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          const int key = min(lane + 32 * i, VA_N - 1);    // lanes past the end recompute key 256 (masked below)
-          const uint4 raw = *reinterpret_cast<const uint4*>(gK + (uint32_t)(key >> 3) * VA_G + (key & 7) * 16 + c * 128);
-          const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(h2[j]);
-            sc[i] = fmaf(qv[c * 8 + 2 * j], f.x, sc[i]);
-            sc[i] = fmaf(qv[c * 8 + 2 * j + 1], f.y, sc[i]);
-          }
+        for (int j = 0; j < 4; ++j) {
+          const float2 qf = __half22float2(q2[j]), kf = __half22float2(k2[j]);
+          part = fmaf(qf.x, kf.x, part);
+          part = fmaf(qf.y, kf.y, part);
         }
       }
+      part = warp_sum(part);
       __syncwarp();
-      if (lane == 0) mbar_arrive(k_empty);
+      if (lane == 0) { mbar_arrive(k_empty); mbar_arrive(q_empty + 8); }
+      VA_STAMP(9, 2);
+      mbar_wait(cls_bar, n & 1);                          // the 256 distributed scores are in s_cls[0..255]
+      VA_STAMP(9, 3);
+      float sc[9];
       float mx = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
-        sc[i] = (lane + 32 * i < VA_N) ? sc[i] * p.scale_log2 : -INFINITY;
-        mx = fmaxf(mx, sc[i]);
+        const int key = lane + 32 * i;
+        float v = -INFINITY;
+        if (key < VA_N - 1) v = s_cls[key] * p.scale_log2;
+        else if (key == VA_N - 1) v = part * p.scale_log2;
+        sc[i] = v;
+        mx = fmaxf(mx, v);
       }
       mx = warp_max(mx);
       float sum = 0.0f;
+      __syncwarp();
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
-        sc[i] = __half2float(__float2half_rn(ex2f(sc[i] - mx)));   // P rounded to fp16 like the tile path; 0 past the end
-        sum += sc[i];
+        const int key = lane + 32 * i;
+        const float pr = __half2float(__float2half_rn(ex2f(sc[i] - mx)));   // P rounded to fp16 like the tile path
+        sum += pr;
+        if (key < VA_KP) s_cls[key] = pr;                  // 0 for keys 257..271
       }
       sum = warp_sum(sum);
-      // out[d] = sum_k p_k V[k][d]: every lane accumulates all 88 dims over its nine keys, then a butterfly reduction
+      __syncwarp();
+      VA_STAMP(9, 4);
       mbar_wait(v_full + 8 * vb, (n >> 1) & 1);
+      VA_STAMP(9, 5);
+      // out[d] = sum_k p_k V[k][d]: lane l owns the dim pairs l and l + 32 (44 pairs); keys walk in groups of 8
       const uint8_t* gV = gV0 + vb * VA_V_BYTES;
+      const int pr0 = lane, pr1 = lane + 32;               // pair index -> dims 2*pr, 2*pr+1
+      const bool has1 = pr1 < VA_D / 2;
+      const uint32_t off0 = (uint32_t)(pr0 >> 2) * 128 + (pr0 & 3) * 4;
+      const uint32_t off1 = (uint32_t)((has1 ? pr1 : 0) >> 2) * 128 + ((has1 ? pr1 : 0) & 3) * 4;
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll 2
+      for (int kg = 0; kg < 33; ++kg) {                    // 33 groups of 8 keys (rows 257..263 are zero, p = 0)
+        const float4 pa = *reinterpret_cast<const float4*>(s_cls + kg * 8);
+        const float4 pb = *reinterpret_cast<const float4*>(s_cls + kg * 8 + 4);
+        const float pk[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+        const uint8_t* vg = gV + (uint32_t)kg * VA_G;
 #pragma unroll
-      for (int d = 0; d < VA_D; ++d) qv[d] = 0.0f;         // reuse the registers as the output accumulator
-#pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        const int key = min(lane + 32 * i, VA_N - 1);
-        const float pk = sc[i];                            // 0 for keys past the end
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const uint4 raw = *reinterpret_cast<const uint4*>(gV + (uint32_t)(key >> 3) * VA_G + (key & 7) * 16 + c * 128);
-          const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(h2[j]);
-            qv[c * 8 + 2 * j] = fmaf(pk, f.x, qv[c * 8 + 2 * j]);
-            qv[c * 8 + 2 * j + 1] = fmaf(pk, f.y, qv[c * 8 + 2 * j + 1]);
-          }
+        for (int r = 0; r < 8; ++r) {
+          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(vg + r * 16 + off0));
+          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(vg + r * 16 + off1));
+          a0 = fmaf(pk[r], f0.x, a0); a1 = fmaf(pk[r], f0.y, a1);
+          b0 = fmaf(pk[r], f1.x, b0); b1 = fmaf(pk[r], f1.y, b1);
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(v_empty + 8 * vb);
-#pragma unroll
-      for (int d = 0; d < VA_D; ++d) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) qv[d] += __shfl_xor_sync(0xffffffffu, qv[d], o);
-      }
+      if (lane == 0) { mbar_arrive(v_empty + 8 * vb); mbar_arrive(cls_done); }
+      VA_STAMP(9, 6);
       const float inv = 1.0f / sum;
       __half* og = p.o + b * p.o_bs + h * p.o_hs + (long long)(VA_N - 1) * p.o_ts;
       float unused = 0.0f;
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        if (lane == c) {
-          uint4 o;
-          o.x = pack2(qv[c * 8 + 0] * inv, qv[c * 8 + 1] * inv, unused);
-          o.y = pack2(qv[c * 8 + 2] * inv, qv[c * 8 + 3] * inv, unused);
-          o.z = pack2(qv[c * 8 + 4] * inv, qv[c * 8 + 5] * inv, unused);
-          o.w = pack2(qv[c * 8 + 6] * inv, qv[c * 8 + 7] * inv, unused);
-          *reinterpret_cast<uint4*>(og + c * 8) = o;
-        }
-      }
+      *reinterpret_cast<uint32_t*>(og + 2 * pr0) = pack2(a0 * inv, a1 * inv, unused);
+      if (has1) *reinterpret_cast<uint32_t*>(og + 2 * pr1) = pack2(b0 * inv, b1 * inv, unused);
+      VA_STAMP(9, 7);
     }
   } else {
     // ======================= softmax + epilogue: warps 0-3 own tile 0 (rows 0..127), warps 4-7 tile 1 =======================
@@ -371,30 +365,43 @@ vit_attention_tc_kernel(const VitAttnParams p) {
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
       const int b = item / p.heads, h = item - b * p.heads;
       const uint32_t vb = n & 1, pn = n & 1;
-      // ---- key 256 on the CUDA cores (the MMA covers keys 0..255): s256 = q_row . k_256, under the S MMA ----
+      // ---- the 257th token on the CUDA cores, under the S MMA (which covers keys 0..255 x rows 0..255):
+      //      s256 = q_row . k_256 (key 256 for this thread's row) and t = q_256 . k_key (this thread's key for row 256)
       VA_STAMP(warp, 0);
       mbar_wait(q_full + 8 * u, pn);
+      if (u == 0) mbar_wait(q_full + 8, pn);                // query row 256 lives in the second Q buffer
       mbar_wait(k_full, pn);
+      if (n > 0) mbar_wait(cls_done, pn ^ 1);               // row-256 warp is done with last item's s_cls
       VA_STAMP(warp, 1);
-      float s256 = 0.0f;
+      float s256 = 0.0f, t256 = 0.0f;
       {
         const uint8_t* k256 = gK + 32 * VA_G;              // row 256 = first row of group 32
+        const uint8_t* q256 = gQ1 + 16 * VA_G;             // local row 128 of the second Q buffer
+        const uint8_t* krow = gK + (uint32_t)(row >> 3) * VA_G + (row & 7) * 16;    // key index == row index
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           const uint4 qa = *reinterpret_cast<const uint4*>(qrow + c * 128);
           const uint4 ka = *reinterpret_cast<const uint4*>(k256 + c * 128);
+          const uint4 qb = *reinterpret_cast<const uint4*>(q256 + c * 128);
+          const uint4 kb_ = *reinterpret_cast<const uint4*>(krow + c * 128);
           const __half2* q2 = reinterpret_cast<const __half2*>(&qa);
           const __half2* k2 = reinterpret_cast<const __half2*>(&ka);
+          const __half2* q3 = reinterpret_cast<const __half2*>(&qb);
+          const __half2* k3 = reinterpret_cast<const __half2*>(&kb_);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float2 qf = __half22float2(q2[j]), kf = __half22float2(k2[j]);
+            const float2 qg = __half22float2(q3[j]), kg = __half22float2(k3[j]);
             s256 = fmaf(qf.x, kf.x, s256);
             s256 = fmaf(qf.y, kf.y, s256);
+            t256 = fmaf(qg.x, kg.x, t256);
+            t256 = fmaf(qg.y, kg.y, t256);
           }
         }
       }
+      s_cls[row] = t256;
       __syncwarp();
-      if (lane == 0) { mbar_arrive(q_empty + 8 * u); mbar_arrive(k_empty); }
+      if (lane == 0) { mbar_arrive(q_empty + 8 * u); if (u == 0) mbar_arrive(q_empty + 8); mbar_arrive(k_empty); mbar_arrive(cls_bar); }
 
       VA_STAMP(warp, 2);
       mbar_wait(bar_s + 8 * u, pn);

@@ -19,13 +19,13 @@ torch.cuda.synchronize()
 lib.seedb200_debug_set_attn_timeline(None)
 t = dbg.cpu().view(16, 64, 8)
 t0 = int(t[8, 0, 0])
-names = {0: "softmax w0", 4: "softmax w4", 8: "mma", 10: "ld Q0", 11: "ld K", 12: "ld Q1", 13: "ld V"}
+names = {0: "softmax w0", 4: "softmax w4", 8: "mma", 9: "row256", 10: "ld Q0", 11: "ld K", 12: "ld Q1", 13: "ld V"}
 ev = {8: ["start", "S0 issue", "S1 issue", "wait v", "v ok", "PV0 issue", "PV1 issue", "end"],
       0: ["start", "q,k ok", "s256 done", "S ok", "max done", "P done", "O ok", "end"],
       10: ["start", "empty ok", "issued", "full"]}
-ev[4] = ev[0]; ev[11] = ev[12] = ev[13] = ev[10]
+ev[9] = ["start", "q ok", "k ok", "scores", "softmax", "v ok", "pv", "end"]; ev[4] = ev[0]; ev[11] = ev[12] = ev[13] = ev[10]
 for item in range(0, 6):
     print(f"--- item {item}")
-    for slot in (8, 0, 4, 10, 11, 12, 13):
+    for slot in (8, 9, 0, 4, 10, 11, 12, 13):
         row = [int(x) - t0 for x in t[slot, item, :len(ev[slot])]]
         print(f"{names[slot]:11s} " + "  ".join(f"{e}={x}" for e, x in zip(ev[slot], row)))
