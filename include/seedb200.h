@@ -59,7 +59,7 @@ void seedb200_reset_launch_count(void);
  * summed algorithmic FLOPs (2*M*N*K per launch).  out[kind*3 + {0,1,2}] = {launches, ms, flops}. */
 /* Process-wide switches (tests / A-B measurements).  "vit_attention_tc": 1 (default) routes the 257x257x88
  * ViT attention to the tcgen05 kernel (attention_tc.cu), 0 to the mma.sync kernel (attention.cu).
- * "gemm_ksub": 2 (default) = 128-deep GEMM pipeline stages, 1 = 64-deep.                                    */
+ * "gemm_ksub": 0 (default) = heuristic, 1 = 64-deep GEMM pipeline stages, 2 = 128-deep.                      */
 int seedb200_set_option(const char* key, int value);
 int seedb200_profile_begin(void);
 int seedb200_profile_end(double* out6);

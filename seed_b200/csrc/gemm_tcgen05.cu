@@ -500,9 +500,12 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   return 0;
 }
 
-static int pick_bn(int N, int mode) {
+static int pick_bn(int N, int mode, int ctas) {
   if (mode == 1) return 256;
   if (N % 256 == 0) return 256;
+  // CTA pairs: a 256-wide tile with a partly empty last column beats an exactly dividing narrower tile while
+  // the padding stays under 10% (N=1408: BN=256 1370 TFLOP/s vs BN=176 1323 on fc2, 1071 vs 967 on proj)
+  if (ctas == 2 && N >= 1024 && ((N + 255) / 256 * 256 - N) * 10 <= N) return 256;
   if (N % 192 == 0) return 192;
   if (N % 176 == 0) return 176;
   if (N % 128 == 0) return 128;
@@ -523,14 +526,18 @@ int gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
     SB_REQUIRE(d.N % 256 == 0, "gemm: SiLU-gate mode needs N %% 256 == 0 (got %d)", d.N);
     SB_REQUIRE(d.bias == nullptr && d.act == 0, "gemm: SiLU-gate mode takes no bias/activation");
   }
-  int bn = d.bn > 0 ? d.bn : pick_bn(d.N, d.mode);
   int ctas = d.ctas > 0 ? d.ctas : 1;
   SB_REQUIRE(ctas == 1 || ctas == 2, "gemm: ctas must be 1 or 2 (got %d)", ctas);
-  if (ctas == 2 && (bn < 64 || d.M <= GEMM_BLOCK_M)) ctas = 1;   // pairs only pay off on big tiles
+  if (ctas == 2 && d.M <= GEMM_BLOCK_M) ctas = 1;                 // pairs only pay off on big tiles
+  int bn = d.bn > 0 ? d.bn : pick_bn(d.N, d.mode, ctas);
+  if (ctas == 2 && bn < 64) ctas = 1;
 
-  // 128-deep stages pay off where the stage count stays >= 3 (CTA pairs with wide tiles); measured on B200:
-  // qkv/fc1/fc2 +10% with pairs, -5% on single CTAs (2 stages) and on the BN=176 proj tile
-  const int ksub = (d.K > 64 && ctas == 2 && bn >= 192 && get_option("gemm_ksub") != 1) ? 2 : 1;
+  // 128-deep stages pay off for CTA pairs on long reductions or exactly tiled wide outputs (measured on B200:
+  // qkv/fc1/fc2 +5..10%); they lose on short-K ragged tilings (proj BN=256: -26%) and on single CTAs (-5%).
+  // option gemm_ksub: 0 = this heuristic, 1 / 2 = force.
+  int ksub = (d.K > 64 && ctas == 2 && ((bn >= 192 && d.N % bn == 0) || d.K >= 4096)) ? 2 : 1;
+  if (get_option("gemm_ksub") == 1) ksub = 1;
+  if (get_option("gemm_ksub") == 2 && d.K > 64) ksub = 2;
 #define SB_GEMM_CASE(BN_, CT_, MD_)                                                   \
   if (bn == BN_ && ctas == CT_ && d.mode == MD_) {                                    \
     if (ksub == 2) return launch_gemm<BN_, CT_, MD_, 2>(d, stream);                   \
