@@ -151,18 +151,32 @@ def timed(fn, steps, warmup, world):
 # --------------------------------------------------------------------------------------------------
 # CPU legs: the oracle port of the reference algorithm (the only place bench.py executes oracle/)
 # --------------------------------------------------------------------------------------------------
-def cpu_encode_images_per_s(sd, n_images: int):
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_encode_images_per_s(sd, n_images: int, target_s: float = 20.0):
+    """Times oracle/restatement.py on a bounded sample: `n_images` (0 = sized from a one-image probe to ~target_s)."""
     from oracle import restatement as R
     from seed_b200 import synth
 
-    torch.set_num_threads(os.cpu_count())
-    x = synth.images(max(n_images, 1), seed=4242)
+    torch.set_num_threads(host_cores())
     with torch.no_grad():
-        R.encode(x[:1], sd, VIT_DEPTH, QF_LAYERS)          # warm-up
+        x1 = synth.images(1, seed=4241)
+        R.encode(x1, sd, VIT_DEPTH, QF_LAYERS)          # warm-up
+        t0 = time.perf_counter()
+        R.encode(x1, sd, VIT_DEPTH, QF_LAYERS)
+        probe = time.perf_counter() - t0
+        if n_images <= 0:
+            n_images = max(1, min(32, int(target_s / max(probe, 1e-3))))
+        x = synth.images(n_images, seed=4242)
         t0 = time.perf_counter()
         R.encode(x, sd, VIT_DEPTH, QF_LAYERS)
         dt = time.perf_counter() - t0
-    return n_images / dt, dt
+    return n_images / dt, dt, n_images
 
 
 def reference_arm(args, world, rank):
@@ -172,7 +186,7 @@ def reference_arm(args, world, rank):
         return None
     from seed_b200 import synth
 
-    cores = os.cpu_count()
+    cores = host_cores()
     torch.set_num_threads(cores)
     if args.workload == "encode":
         from oracle import restatement as R
@@ -289,9 +303,8 @@ def encode_arm(args, world, rank, local):
                 "whole_step_tflops": round(ENCODE_FLOPS_PER_IMAGE * B / (ms / args.steps * 1e-3) / 1e12, 1)}
     cpu = None
     if rank == 0 and not args.no_cpu:
-        n_cpu = args.cpu_images
-        v, dt = cpu_encode_images_per_s(sd, n_cpu)
-        cpu = {"value": round(v, 3), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+        v, dt, n_cpu = cpu_encode_images_per_s(sd, args.cpu_images)
+        cpu = {"value": round(v, 3), "unit": "images/s", "cores": host_cores(), "kind": "port",
                "sample": f"{n_cpu} of the {B} images, full depth, fp32, oracle/restatement.py, {dt:.1f} s"}
     total = B * world * args.steps
     res = {
@@ -306,7 +319,7 @@ def encode_arm(args, world, rank, local):
                    "gemm_cta_group": args.ctas or 1},
         "clocks": clocks,
         "e2e": {"value": round(total / (ms_e2e * 1e-3), 2), "unit": "images/s",
-                "h2d_bytes_per_step": B * 3 * 224 * 224 * 2, "d2h_bytes_per_step": B * world * 32 * 8,
+                "h2d_bytes_per_step": B * world * 3 * 224 * 224 * 2, "d2h_bytes_per_step": B * world * 32 * 8 * world,
                 "api": "models.seed_llama_tokenizer.ImageTokenizer.encode(pinned.to(cuda)) -> ids.cpu()"},
         "gpu_launches": int(launches) * args.steps,
         "roofline": roofline, "cpu_baseline": cpu, "id_parity": parity,
@@ -402,7 +415,7 @@ def main():
     ap.add_argument("--seq", type=int, default=2048, help="prompt length (llama_prefill)")
     ap.add_argument("--ctas", type=int, default=2, help="tcgen05 cta_group of the GEMMs (1 or 2)")
     ap.add_argument("--vq", default="fp16", choices=["fp16", "fp32"], help="VQ distance arithmetic")
-    ap.add_argument("--cpu-images", type=int, default=16, help="images timed by the cpu_baseline leg")
+    ap.add_argument("--cpu-images", type=int, default=0, help="images timed by the cpu_baseline leg (0 = ~20 s worth)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "seedb200" else args.warmup
