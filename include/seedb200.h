@@ -59,6 +59,8 @@ void seedb200_reset_launch_count(void);
  * summed algorithmic FLOPs (2*M*N*K per launch).  out[kind*3 + {0,1,2}] = {launches, ms, flops}. */
 /* Process-wide switches (tests / A-B measurements).  "vit_attention_tc": 1 (default) routes the 257x257x88
  * ViT attention to the tcgen05 kernel (attention_tc.cu), 0 to the mma.sync kernel (attention.cu).
+ * "causal_attention_tc": 1 (default) routes causal head_dim-128 attention with nq >= 128 (LLaMA prefill) to the
+ * tcgen05 kernel (attention_causal_tc.cu), 0 to the mma.sync kernel.
  * "gemm_ksub": 0 (default) = heuristic, 1 = 64-deep GEMM pipeline stages, 2 = 128-deep.                      */
 int seedb200_set_option(const char* key, int value);
 int seedb200_profile_begin(void);

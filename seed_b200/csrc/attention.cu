@@ -327,6 +327,8 @@ static int launch_attn(const seedb200_attn_desc& d, cudaStream_t stream) {
 
 bool vit_attention_tc_applicable(const seedb200_attn_desc& d);
 int vit_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream);
+bool causal_attention_tc_applicable(const seedb200_attn_desc& d);
+int causal_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream);
 int get_option(const char* key);
 
 int attention(const seedb200_attn_desc& d, cudaStream_t stream) {
@@ -344,6 +346,7 @@ int attention(const seedb200_attn_desc& d, cudaStream_t stream) {
                  ((uintptr_t)d.o % 4 == 0),
              "attention: misaligned pointer");
   if (vit_attention_tc_applicable(d) && get_option("vit_attention_tc") != 0) return vit_attention_tc(d, stream);
+  if (causal_attention_tc_applicable(d) && get_option("causal_attention_tc") != 0) return causal_attention_tc(d, stream);
   if (d.head_dim == 64) {
     if (d.nq <= 32) return launch_attn<64, 2>(d, stream);
     return launch_attn<64, 4>(d, stream);

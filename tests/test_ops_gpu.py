@@ -199,6 +199,10 @@ ATTN_CASES = [
     (1, 2, 5, 133, 128, True),        # chunked prefill with past: bottom-right aligned causal
     (2, 8, 100, 200, 128, True),      # 100 new tokens after a 100-token past (8-warp tile, nk != nq)
     (1, 2, 130, 300, 128, True),
+    (1, 3, 512, 640, 128, True),      # tcgen05 causal kernel: two tile pairs after a 128-token past
+    (2, 5, 257, 257, 128, True),      # ragged second pair (one row)
+    (1, 2, 128, 128, 128, True),      # single tile, second tile of the pair absent
+    (1, 40, 1024, 1024, 128, True),   # 160 items > 148 CTAs: snake schedule, several items per CTA
     (1, 3, 1, 77, 128, False),        # single query through the prefill kernel
     (1, 2, 100, 100, 64, False),
 ]
@@ -236,6 +240,43 @@ def test_vit_attention_tcgen05_vs_mma_paths(lib, B, use_tc):
     ref = R.attention_ref(q, k, v, D ** -0.5, False)
     assert rel_err(o, ref) < 2e-3, rel_err(o, ref)
     assert (o.float() - ref.float()).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("use_tc", [1, 0])
+def test_causal_attention_tcgen05_vs_mma_paths(lib, use_tc):
+    """LLaMA prefill layout (q from a fused projection buffer, K/V in a [B,H,max_seq,D] cache with a past) on the
+    tcgen05 kernel (attention_causal_tc.cu) and on the mma.sync kernel"""
+    B, H, S, D, past, max_seq = 2, 4, 700, 128, 333, 1200
+    qbuf = rand16(B * S, H * D, seed=35)
+    kc = rand16(B, H, max_seq, D, seed=36)
+    vc = rand16(B, H, max_seq, D, seed=37)
+    q = qbuf.view(B, S, H, D).permute(0, 2, 1, 3)
+    k, v = kc[:, :, :past + S], vc[:, :, :past + S]
+    lib.set_option("causal_attention_tc", use_tc)
+    try:
+        o = lib.attention(q, k, v, D ** -0.5, True)
+        torch.cuda.synchronize()
+    finally:
+        lib.set_option("causal_attention_tc", 1)
+    ref = R.attention_ref(q, k, v, D ** -0.5, True)
+    assert rel_err(o, ref) < 2e-3, rel_err(o, ref)
+    assert (o.float() - ref.float()).abs().max().item() < 1e-2
+
+
+def test_causal_attention_large_scores_rescale(lib):
+    """scores that grow along the sequence force the lazy O-rescaling branch (row max jumps by > 2^8 between tiles)"""
+    B, H, S, D = 1, 2, 512, 128
+    q = rand16(B, H, S, D, seed=38)
+    k = rand16(B, H, S, D, seed=39)
+    v = rand16(B, H, S, D, seed=40)
+    ramp = torch.linspace(0.2, 6.0, S, device=DEV, dtype=torch.float32)[None, None, :, None]
+    k = (k.float() * ramp).to(torch.float16)
+    q = (q.float() * 2.0).to(torch.float16)
+    o = lib.attention(q, k, v, D ** -0.5, True)
+    torch.cuda.synchronize()
+    ref = R.attention_ref(q, k, v, D ** -0.5, True)
+    assert torch.isfinite(o.float()).all()
+    assert rel_err(o, ref) < 3e-3, rel_err(o, ref)
 
 
 def test_attention_strided_qkv_layout(lib):
