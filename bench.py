@@ -327,14 +327,11 @@ def encode_arm(args, world, rank, local):
     return res
 
 
-def llama_arm(args, world, rank, local):
+def random_llama(dev, rank, h, nl, nh, ffn, V, max_seq, ctas):
+    """random-init llama_xformer weights generated on the device (HF key names), wrapped by the product class"""
     from transformers.models.llama.configuration_llama import LlamaConfig
-
     from models.llama_xformer import LlamaForCausalLM
-    from seed_b200 import lib as L, synth
 
-    dev = torch.device("cuda", local)
-    h, nl, nh, ffn, V, S = 4096, 32, 32, 11008, 40194, args.seq
     cfg = LlamaConfig(vocab_size=V, hidden_size=h, intermediate_size=ffn, num_hidden_layers=nl,
                       num_attention_heads=nh, num_key_value_heads=nh, rms_norm_eps=1e-6, max_position_embeddings=4096)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -353,9 +350,87 @@ def llama_arm(args, world, rank, local):
         sd[p + "mlp.down_proj.weight"] = rnd(h, ffn)
         sd[p + "input_layernorm.weight"] = rnd(h, std=0.05, mean=1.0)
         sd[p + "post_attention_layernorm.weight"] = rnd(h, std=0.05, mean=1.0)
-    model = LlamaForCausalLM(cfg, sd, device=dev, max_batch=1, max_seq=S, gemm_ctas=args.ctas)
+    model = LlamaForCausalLM(cfg, sd, device=dev, max_batch=1, max_seq=max_seq, gemm_ctas=ctas)
     del sd
     torch.cuda.empty_cache()
+    return model
+
+
+def llama_decode_arm(args, world, rank, local):
+    """BASELINE.json config #5: random-init 13B llama_xformer, interleaved 4-image prompt, prefill + 128 generated
+    tokens (greedy), batch 1.  A step = one generate() call; value = generated tokens/s over prefill+decode."""
+    from seed_b200 import lib as L, synth
+
+    dev = torch.device("cuda", local)
+    h, nl, nh, ffn, V = 5120, 40, 40, 13824, 40194
+    P, NEW = args.prompt, args.new_tokens
+    model = random_llama(dev, rank, h, nl, nh, ffn, V, P + NEW + 8, args.ctas)
+    ids_host = synth.prompt_ids(1, P, 4, seed=99 + rank).pin_memory()
+    ids = ids_host.to(dev)
+    out = {}
+
+    def step_device():
+        out["seq"] = model.generate(input_ids=ids, max_new_tokens=NEW, do_sample=False)
+
+    def step_e2e():
+        out["host"] = model.generate(input_ids=ids_host.to(dev, non_blocking=True), max_new_tokens=NEW, do_sample=False).cpu()
+
+    step_device(); torch.cuda.synchronize()
+    L.reset_launch_count()
+    with ClockSampler(local) as cs:
+        ms = timed(step_device, args.steps, args.warmup, world)
+    launches = L.launch_count() // (args.steps + args.warmup)
+    clocks = cs.summary()
+    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup), world)
+    # decode-only forwards (q_len 1 over the cache) between CUDA events: the HBM roofline of the token loop
+    o = model.forward(input_ids=ids, use_cache=True, last_logits_only=True)
+    nxt = o.logits[:, -1].float().argmax(-1)[:, None]
+    past = o.past_key_values
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_dec = min(64, NEW)
+    e0.record()
+    for _ in range(n_dec):
+        o = model.forward(input_ids=nxt, past_key_values=past, use_cache=True, last_logits_only=True)
+        past = o.past_key_values
+    e1.record(); torch.cuda.synchronize()
+    dec_ms = e0.elapsed_time(e1) / n_dec
+    peaks = measured_peaks()
+    weight_bytes = 2.0 * (nl * (4 * h * h + 3 * h * ffn) + h * V)      # every weight once per token (+ one embedding row)
+    kv_bytes = 2.0 * 2 * nl * nh * 128 * (P + n_dec / 2)
+    ach = (weight_bytes + kv_bytes) / (dec_ms * 1e-3) / 1e9
+    total_tok = NEW * world * args.steps
+    return {
+        "metric": "tokens/sec LLaMA-13B prefill+decode", "value": round(total_tok / (ms * 1e-3), 1), "unit": "tokens/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"llama13b_decode: random-init h5120/L40/H40/FFN13824/V40194, B=1, {P}-token prompt with 4 "
+                               f"image spans, {NEW} greedy tokens (1 prefill + {NEW - 1} cached decode forwards)",
+                   "global_batch": world, "seq_len": P + NEW,
+                   "parallelism": f"dp{world} (independent replicas, no collective)",
+                   "l2": "26 GB of weights stream from HBM every token (207x the L2)", "gemm_cta_group": args.ctas or 1},
+        "clocks": clocks,
+        "e2e": {"value": round(total_tok / (ms_e2e * 1e-3), 1), "unit": "tokens/s", "h2d_bytes_per_step": P * 8,
+                "d2h_bytes_per_step": (P + NEW) * 8,
+                "api": "models.llama_xformer.LlamaForCausalLM.generate(pinned ids.to(cuda), max_new_tokens) -> seq.cpu()"},
+        "gpu_launches": int(launches) * args.steps,
+        "roofline": {"kernel": "sb::gemv_kernel (whole cached decode forward)", "bound": "hbm", "achieved": round(ach, 1),
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None,
+                     "peak_source": peaks["source"], "decode_ms_per_token": round(dec_ms, 4),
+                     "algorithmic_bytes_per_token": int(weight_bytes + kv_bytes)},
+        "cpu_baseline": None,
+    }
+
+
+def llama_arm(args, world, rank, local):
+    from transformers.models.llama.configuration_llama import LlamaConfig
+
+    from models.llama_xformer import LlamaForCausalLM
+    from seed_b200 import lib as L, synth
+
+    dev = torch.device("cuda", local)
+    h, nl, nh, ffn, V, S = 4096, 32, 32, 11008, 40194, args.seq
+    model = random_llama(dev, rank, h, nl, nh, ffn, V, S, args.ctas)
     ids_host = synth.prompt_ids(1, S, 1, seed=77 + rank).pin_memory()
     ids = ids_host.to(dev)
     out = {}
@@ -380,6 +455,13 @@ def llama_arm(args, world, rank, local):
     attn_flops = nl * 4.0 * nh * S * S * 128 * 0.5
     ach = lin_flops / (prof["gemm"]["ms"] * 1e-3) / 1e12
     total_tok = S * world * args.steps
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        import copy
+
+        a2 = copy.copy(args); a2.steps, a2.warmup = 1, 1
+        r = reference_arm(a2, 1, 0)
+        cpu = {"value": round(r["value"], 2), "unit": r["unit"], "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     return {
         "metric": "tokens/sec LLaMA-7B prefill", "value": round(total_tok / (ms * 1e-3), 1), "unit": "tokens/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
@@ -400,7 +482,7 @@ def llama_arm(args, world, rank, local):
                      "gemm_ms_per_step": round(prof["gemm"]["ms"], 3),
                      "attention_ms_per_step": round(prof["attention"]["ms"], 3),
                      "whole_step_tflops": round((lin_flops + attn_flops) / (ms / args.steps * 1e-3) / 1e12, 1)},
-        "cpu_baseline": None,
+        "cpu_baseline": cpu,
     }
 
 
@@ -410,9 +492,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="seedb200", choices=["seedb200", "reference"])
-    ap.add_argument("--workload", default="encode", choices=["encode", "llama_prefill"])
+    ap.add_argument("--workload", default="encode", choices=["encode", "llama_prefill", "llama_decode"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (encode)")
     ap.add_argument("--seq", type=int, default=2048, help="prompt length (llama_prefill)")
+    ap.add_argument("--prompt", type=int, default=256, help="prompt length (llama_decode)")
+    ap.add_argument("--new-tokens", type=int, default=128, help="generated tokens (llama_decode)")
     ap.add_argument("--ctas", type=int, default=2, help="tcgen05 cta_group of the GEMMs (1 or 2)")
     ap.add_argument("--vq", default="fp16", choices=["fp16", "fp32"], help="VQ distance arithmetic")
     ap.add_argument("--cpu-images", type=int, default=0, help="images timed by the cpu_baseline leg (0 = ~20 s worth)")
@@ -442,7 +526,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the seedb200 arm has no CPU fallback; use --impl reference)")
     world, rank, local = dist_setup(args.gpus)
-    res = encode_arm(args, world, rank, local) if args.workload == "encode" else llama_arm(args, world, rank, local)
+    arm = {"encode": encode_arm, "llama_prefill": llama_arm, "llama_decode": llama_decode_arm}[args.workload]
+    res = arm(args, world, rank, local)
     if world > 1:
         import torch.distributed as dist
 
