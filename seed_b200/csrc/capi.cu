@@ -46,7 +46,7 @@ void profile_mark_end(int kind, cudaStream_t stream, double flops) {
 }
 
 static std::map<std::string, int>& options() {
-  static std::map<std::string, int> o = {{"vit_attention_tc", 1}, {"causal_attention_tc", 1}, {"gemm_ksub", 0}};
+  static std::map<std::string, int> o = {{"vit_attention_tc", 1}, {"causal_attention_tc", 1}, {"decode_pdl", 1}, {"gemm_ksub", 0}};
   return o;
 }
 static long long g_dbg_ptr = 0;
@@ -64,6 +64,10 @@ int set_option(const char* key, int value) {
   it->second = value;
   return 0;
 }
+
+static thread_local bool g_pdl_scope = false;
+bool pdl_scope_active() { return g_pdl_scope; }
+void pdl_scope_set(bool on) { g_pdl_scope = on; }
 
 int num_sms() {
   static int sms = 0;

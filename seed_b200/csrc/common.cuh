@@ -53,15 +53,44 @@ void count_launch(int n = 1);
 
 int num_sms();
 
+// Programmatic dependent launch (decode chain): a kernel launched through launch_chain() while a PdlScope is active
+// may start while its predecessor is still running; it must execute pdl_wait() before touching anything the
+// predecessor writes, and everything it does earlier (weight prefetch) overlaps the predecessor's tail and the
+// launch gap.  Outside a PdlScope launch_chain() is a plain launch and pdl_wait()/pdl_trigger() are no-ops.
+bool pdl_scope_active();
+void pdl_scope_set(bool on);
+struct PdlScope {
+  bool prev;
+  explicit PdlScope(bool on) : prev(pdl_scope_active()) { pdl_scope_set(on); }
+  ~PdlScope() { pdl_scope_set(prev); }
+};
+
 // per-kernel event timing (seedb200_profile_begin/end); no-ops unless enabled on this thread
 bool profile_enabled();
 void profile_mark_begin(int kind, cudaStream_t stream);
 void profile_mark_end(int kind, cudaStream_t stream, double flops);
 
 #ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (pdl_scope_active()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ----------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

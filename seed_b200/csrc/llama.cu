@@ -120,14 +120,17 @@ static int llama_build(seedb200_llama* m) {
   SB_PROPAGATE(llama_alloc(m, &m->gu, T * ffn));
   SB_PROPAGATE(llama_alloc(m, &m->hn, T * h));
   SB_PROPAGATE(llama_alloc(m, &m->last, (size_t)c.max_batch * h));
-  SB_PROPAGATE(llama_alloc(m, &m->da_ws, (size_t)c.max_batch * c.heads * 32 * (128 + 2)));
+  SB_PROPAGATE(llama_alloc(m, &m->da_ws, (size_t)c.max_batch * c.heads * 64 * (128 + 2)));
   SB_CHECK_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 
+int get_option(const char* key);
+
 static int lin(cudaStream_t st, int ctas, int M, int N, int K, const void* A, const void* W, void* out, int64_t ldo,
-               const void* residual, int mode) {
-  if (M <= 4) return gemv(A, W, K, out, residual, M, N, K, mode, st);
+               const void* residual, int mode, const void* norm_w = nullptr, float eps = 0.0f) {
+  // norm_w: only on the M <= 4 (decode) path, where the GEMV normalises its activations while staging them
+  if (M <= 4) return gemv(A, W, K, out, residual, norm_w, eps, M, N, K, mode, st);
   seedb200_gemm_desc d;
   memset(&d, 0, sizeof(d));
   d.M = M; d.N = N; d.K = K; d.A = A; d.lda = K; d.W = W; d.ldw = K;
@@ -147,10 +150,16 @@ static int llama_forward(seedb200_llama* m, const int64_t* input_ids, const void
     SB_CHECK_CUDA(cudaMemcpyAsync(m->x, inputs_embeds, (size_t)T * h * 2, cudaMemcpyDeviceToDevice, st));
   const float scale = 1.0f / sqrtf((float)D);   // xformers default scale
   const int kv_len = past_len + S;
+  const bool fuse_norm = T <= 4;     // decode: RMSNorm folded into the GEMV that consumes it
+  PdlScope pdl(T <= 4 && get_option("decode_pdl") != 0);   // decode chain: programmatic dependent launches
   for (int l = 0; l < c.layers; ++l) {
     const LlamaLayerW& L = m->layers[l];
-    SB_PROPAGATE(rmsnorm(m->x, h, L.in_ln, m->nb, h, T, h, c.rms_eps, st));
-    SB_PROPAGATE(lin(st, ct, T, 3 * h, h, m->nb, L.qkv_w, m->qkv, 3 * h, nullptr, 0));
+    if (fuse_norm) {
+      SB_PROPAGATE(lin(st, ct, T, 3 * h, h, m->x, L.qkv_w, m->qkv, 3 * h, nullptr, 0, L.in_ln, c.rms_eps));
+    } else {
+      SB_PROPAGATE(rmsnorm(m->x, h, L.in_ln, m->nb, h, T, h, c.rms_eps, st));
+      SB_PROPAGATE(lin(st, ct, T, 3 * h, h, m->nb, L.qkv_w, m->qkv, 3 * h, nullptr, 0));
+    }
     // qkv rows are [q | k | v] per token, each [H, D]
     SB_PROPAGATE(rope_kv_append_tables(m->qkv, position_ids, B, S, H, D, past_len, c.max_seq, m->max_pos, m->cos_t,
                                        m->sin_t, m->q, L.k_cache, L.v_cache, st));
@@ -168,8 +177,12 @@ static int llama_forward(seedb200_llama* m, const int64_t* input_ids, const void
       SB_PROPAGATE(attention(a, st));
     }
     SB_PROPAGATE(lin(st, ct, T, h, h, m->att, L.o_w, m->x, h, m->x, 0));
-    SB_PROPAGATE(rmsnorm(m->x, h, L.post_ln, m->nb, h, T, h, c.rms_eps, st));
-    SB_PROPAGATE(lin(st, ct, T, 2 * ffn, h, m->nb, L.gu_w, m->gu, ffn, nullptr, 1));
+    if (fuse_norm) {
+      SB_PROPAGATE(lin(st, ct, T, 2 * ffn, h, m->x, L.gu_w, m->gu, ffn, nullptr, 1, L.post_ln, c.rms_eps));
+    } else {
+      SB_PROPAGATE(rmsnorm(m->x, h, L.post_ln, m->nb, h, T, h, c.rms_eps, st));
+      SB_PROPAGATE(lin(st, ct, T, 2 * ffn, h, m->nb, L.gu_w, m->gu, ffn, nullptr, 1));
+    }
     SB_PROPAGATE(lin(st, ct, T, h, ffn, m->gu, L.down_w, m->x, h, m->x, 0));
   }
   SB_PROPAGATE(rmsnorm(m->x, h, m->norm_w, m->hn, h, T, h, c.rms_eps, st));

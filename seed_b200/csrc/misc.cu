@@ -9,6 +9,8 @@
 
 namespace sb {
 
+int get_option(const char* key);
+
 __global__ void add_rows_kernel(const __half* a, const __half* b, __half* out, int rows, int cols, int b_rows) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)rows * cols) return;
@@ -26,10 +28,18 @@ int add_rows(const void* a, const void* b, void* out, int rows, int cols, int b_
 }
 
 // ----------------------------------------------------------------------------
-// GEMV: M <= GEMV_MAXM activation rows staged in shared memory; each warp owns output columns and streams
-// the matching weight rows with 16-byte loads (2 rows x 4 vectors in flight per lane).
+// GEMV (M <= 4 activation rows): the batch-1 decode form of every nn.Linear.  HBM-bound: every weight byte is
+// read exactly once.  Each warp owns a PAIR of weight rows and streams both with 16-byte loads (2 rows x 4
+// vectors = 128 bytes in flight per lane; one row per warp left the HBM pipe half empty: 4.4 vs 6.4 TB/s).  The
+// first batch of weight loads is issued before the activations are staged (weights do not depend on them).
+// mode 0: rows (2t, 2t+1) -> out[m, 2t], out[m, 2t+1] (+ residual).
 // mode 1: W rows are [128 gate | 128 up] blocks and out[m,j] = silu(gate_j) * up_j (same rounding points
 // as the GEMM epilogue, llama_xformer.py:186).
+// NORM: the staged activations are RMS-normalised on the way into shared memory (LlamaRMSNorm,
+// llama_xformer.py:105-113: fp32 x * rsqrt(mean(x^2) + eps) -> fp16 -> * weight -> fp16), which removes the
+// separate norm launch in front of the QKV and gate/up projections of the decode step.
+// (A variant that staged the weights through per-warp rings of 1-D cp.async.bulk copies was measured at
+// ~17 B/clk/SM -- 5.0 TB/s chip-wide regardless of ring depth -- and dropped: profiles/r01_summary.md.)
 // ----------------------------------------------------------------------------
 constexpr int GEMV_MAXM = 4;
 
@@ -44,36 +54,89 @@ __device__ __forceinline__ void dot8(const uint4& w, const uint4& x, float& acc)
   }
 }
 
-template <int M, int MODE>
+template <int M, int MODE, bool NORM>
 __global__ void __launch_bounds__(256)
 gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long long ldw, __half* __restrict__ out,
-            const __half* __restrict__ residual, int N, int K) {
+            const __half* __restrict__ residual, const __half* __restrict__ norm_w, float eps, int N, int K) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint4* xs = reinterpret_cast<uint4*>(smem_raw);     // [M][K/8]
+  __shared__ float red[8];
   const int nvec = K / 8;
-  for (int i = threadIdx.x; i < M * nvec; i += 256) xs[i] = reinterpret_cast<const uint4*>(x)[i];
-  __syncthreads();
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_out = (MODE == 1) ? N / 2 : N;
+  const int n_tasks = (MODE == 1) ? N / 2 : (N + 1) / 2;
   const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
-  for (int j = gw; j < n_out; j += nw) {
+  auto rows_of = [&](int t, long long& r0, long long& r1) {
+    if (MODE == 1) { r0 = (long long)(t / 128) * 256 + (t % 128); r1 = r0 + 128; }
+    else { r0 = 2LL * t; r1 = min(r0 + 1, (long long)N - 1); }
+  };
+  // first batch of this warp's first task: in flight while the activations are staged
+  uint4 wa[4], wb[4];
+  if (gw < n_tasks) {
     long long r0, r1;
-    if (MODE == 1) { r0 = (long long)(j / 128) * 256 + (j % 128); r1 = r0 + 128; }
-    else { r0 = j; r1 = j; }
+    rows_of(gw, r0, r1);
+    const uint4* w0 = reinterpret_cast<const uint4*>(W + r0 * ldw);
+    const uint4* w1 = reinterpret_cast<const uint4*>(W + r1 * ldw);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int vi = lane + u * 32;
+      if (vi < nvec) { wa[u] = __ldg(w0 + vi); wb[u] = __ldg(w1 + vi); }
+    }
+  }
+  pdl_trigger();
+  pdl_wait();
+  if constexpr (NORM) {
+#pragma unroll 1
+    for (int m = 0; m < M; ++m) {
+      float ss = 0.0f;
+      for (int i = threadIdx.x; i < nvec; i += 256) {
+        const uint4 raw = reinterpret_cast<const uint4*>(x)[m * nvec + i];
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); ss += f.x * f.x; ss += f.y * f.y; }
+      }
+      ss = warp_sum(ss);
+      __syncthreads();
+      if (lane == 0) red[warp] = ss;
+      __syncthreads();
+      float tot = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tot += red[i];
+      const float rstd = rsqrtf(tot * (1.0f / (float)K) + eps);
+      for (int i = threadIdx.x; i < nvec; i += 256) {
+        const uint4 raw = reinterpret_cast<const uint4*>(x)[m * nvec + i];
+        const uint4 wraw = __ldg(reinterpret_cast<const uint4*>(norm_w) + i);
+        const __half* h = reinterpret_cast<const __half*>(&raw);
+        const __half* wh = reinterpret_cast<const __half*>(&wraw);
+        uint4 o;
+        __half* oh = reinterpret_cast<__half*>(&o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __half n16 = __float2half_rn(__half2float(h[j]) * rstd);
+          oh[j] = __float2half_rn(__half2float(n16) * __half2float(wh[j]));
+        }
+        xs[m * nvec + i] = o;
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < M * nvec; i += 256) xs[i] = reinterpret_cast<const uint4*>(x)[i];
+  }
+  __syncthreads();
+
+  for (int t = gw; t < n_tasks; t += nw) {
+    long long r0, r1;
+    rows_of(t, r0, r1);
     const uint4* w0 = reinterpret_cast<const uint4*>(W + r0 * ldw);
     const uint4* w1 = reinterpret_cast<const uint4*>(W + r1 * ldw);
     float a0[M], a1[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) { a0[m] = 0.0f; a1[m] = 0.0f; }
     for (int v = lane; v < nvec; v += 128) {
-      uint4 wa[4], wb[4];
+      if (t != gw || v != lane) {          // the very first batch is already in registers
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int vi = v + u * 32;
-        if (vi < nvec) {
-          wa[u] = __ldg(w0 + vi);
-          if (MODE == 1) wb[u] = __ldg(w1 + vi);
+        for (int u = 0; u < 4; ++u) {
+          const int vi = v + u * 32;
+          if (vi < nvec) { wa[u] = __ldg(w0 + vi); wb[u] = __ldg(w1 + vi); }
         }
       }
 #pragma unroll
@@ -84,7 +147,7 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
           for (int m = 0; m < M; ++m) {
             const uint4 xv = xs[m * nvec + vi];
             dot8(wa[u], xv, a0[m]);
-            if (MODE == 1) dot8(wb[u], xv, a1[m]);
+            dot8(wb[u], xv, a1[m]);
           }
         }
       }
@@ -92,121 +155,183 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
 #pragma unroll
     for (int m = 0; m < M; ++m) {
       a0[m] = warp_sum(a0[m]);
-      if (MODE == 1) a1[m] = warp_sum(a1[m]);
+      a1[m] = warp_sum(a1[m]);
     }
     if (lane == 0) {
 #pragma unroll
       for (int m = 0; m < M; ++m) {
-        __half h;
         if (MODE == 1) {
           const float g = __half2float(__float2half_rn(a0[m]));
           const float u = __half2float(__float2half_rn(a1[m]));
           const float s = __half2float(__float2half_rn(g / (1.0f + __expf(-g))));
-          h = __float2half_rn(s * u);
+          out[(long long)m * n_out + t] = __float2half_rn(s * u);
         } else {
-          h = __float2half_rn(a0[m]);
-          if (residual != nullptr)
-            h = __float2half_rn(__half2float(h) + __half2float(residual[(long long)m * n_out + j]));
+          __half h0 = __float2half_rn(a0[m]), h1 = __float2half_rn(a1[m]);
+          if (residual != nullptr) {
+            h0 = __float2half_rn(__half2float(h0) + __half2float(residual[(long long)m * n_out + r0]));
+            h1 = __float2half_rn(__half2float(h1) + __half2float(residual[(long long)m * n_out + r1]));
+          }
+          out[(long long)m * n_out + r0] = h0;
+          if (r1 != r0) out[(long long)m * n_out + r1] = h1;
         }
-        out[(long long)m * n_out + j] = h;
       }
     }
   }
 }
 
-int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* residual, int M, int N, int K, int mode,
-         cudaStream_t stream) {
+int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* residual, const void* norm_w, float eps,
+         int M, int N, int K, int mode, cudaStream_t stream) {
   SB_REQUIRE(M >= 1 && M <= GEMV_MAXM, "gemv: M=%d outside [1,%d]", M, GEMV_MAXM);
   SB_REQUIRE(K % 8 == 0 && ldw % 8 == 0, "gemv: K and ldw must be multiples of 8");
   SB_REQUIRE(mode == 0 || (mode == 1 && N % 256 == 0 && residual == nullptr), "gemv: bad mode/shape");
   const size_t smem = (size_t)M * K * 2;
   SB_REQUIRE(smem <= 200 * 1024, "gemv: activation rows do not fit shared memory (M=%d K=%d)", M, K);
-  const int n_out = mode == 1 ? N / 2 : N;
-  int blocks = (n_out + 7) / 8;
-  const int cap = num_sms() * 4;
-  if (blocks > cap) blocks = cap;
+  const int n_tasks = mode == 1 ? N / 2 : (N + 1) / 2;
   const __half* xp = static_cast<const __half*>(x);
   const __half* wp = static_cast<const __half*>(W);
   const __half* rp = static_cast<const __half*>(residual);
+  const __half* np = static_cast<const __half*>(norm_w);
   __half* op = static_cast<__half*>(out);
-#define SB_GEMV(M_, MD_)                                                                                   \
-  if (M == M_ && mode == MD_) {                                                                            \
-    auto kern = gemv_kernel<M_, MD_>;                                                                      \
-    if (smem > 48 * 1024) SB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<blocks, 256, smem, stream>>>(xp, wp, ldw, op, rp, N, K);                                        \
+#define SB_GEMV_LAUNCH(M_, MD_, NM_)                                                                       \
+  {                                                                                                        \
+    auto kern = gemv_kernel<M_, MD_, NM_>;                                                                 \
+    static size_t attr_smem = 48 * 1024;                                                                   \
+    if (smem > attr_smem) {                                                                                \
+      SB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+      attr_smem = smem;                                                                                    \
+    }                                                                                                      \
+    /* one full wave: grid = SMs x resident CTAs (a partial second wave costs a whole task time) */        \
+    static int occ = 0; static size_t occ_smem = (size_t)-1;                                               \
+    if (occ_smem != smem) {                                                                                \
+      SB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));                 \
+      occ_smem = smem;                                                                                     \
+      if (occ < 1) occ = 1;                                                                                \
+    }                                                                                                      \
+    int blocks = (n_tasks + 7) / 8;                                                                        \
+    if (blocks > num_sms() * occ) blocks = num_sms() * occ;                                                \
+    SB_CHECK_CUDA(launch_chain(kern, dim3(blocks), dim3(256), smem, stream, xp, wp, (long long)ldw, op, rp, np, eps, N, K)); \
     SB_LAUNCH_CHECK();                                                                                     \
     return 0;                                                                                              \
+  }
+#define SB_GEMV(M_, MD_)                                                                                   \
+  if (M == M_ && mode == MD_) {                                                                            \
+    if (norm_w != nullptr) SB_GEMV_LAUNCH(M_, MD_, true)                                                   \
+    SB_GEMV_LAUNCH(M_, MD_, false)                                                                         \
   }
   SB_GEMV(1, 0) SB_GEMV(2, 0) SB_GEMV(3, 0) SB_GEMV(4, 0)
   SB_GEMV(1, 1) SB_GEMV(2, 1) SB_GEMV(3, 1) SB_GEMV(4, 1)
 #undef SB_GEMV
+#undef SB_GEMV_LAUNCH
   set_error("gemv: unsupported configuration");
   return SEEDB200_ERR_UNSUPPORTED;
 }
 
 // ----------------------------------------------------------------------------
 // Decode attention: q [B,H,D] (one token), caches [B,H,max_seq,D], D = 128.
-// Kernel 1: CTA (split, h, b) -> 4 warps walk keys split*chunk .. ; lane owns 4 dims; partial (m, l, o).
+// Kernel 1: CTA (split, h, b) of 128 threads walks its keys in blocks of 128.  Scores: one key per thread (the
+// whole 256-byte K row in 16 independent 16-byte loads, q broadcast from shared memory -- no shuffles and one
+// memory latency per block instead of one per key).  P.V: thread (g, c) = (key group of 8, 16-byte dim chunk)
+// loads its 16 V vectors up front, then the 8 key groups are folded through shared memory.  Online softmax
+// across blocks; partial (m, l, o[128]) per split.
 // Kernel 2: merge the splits.
 // ----------------------------------------------------------------------------
 constexpr int DA_D = 128;
-constexpr int DA_MAX_SPLITS = 32;
+constexpr int DA_BLK = 128;
+constexpr int DA_MAX_SPLITS = 64;
 
 __global__ void __launch_bounds__(128)
 decode_attn_partial(const __half* __restrict__ q, const __half* __restrict__ kc, const __half* __restrict__ vc,
                     float* __restrict__ ws, int H, int kv_len, int max_seq, int chunk, float scale_log2) {
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z, nsplit = gridDim.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ float s_m[4], s_l[4], s_o[4][DA_D];
-  const __half* qp = q + ((long long)b * H + h) * DA_D + lane * 4;
-  const float2 q01 = __half22float2(*reinterpret_cast<const __half2*>(qp));
-  const float2 q23 = __half22float2(*reinterpret_cast<const __half2*>(qp + 2));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __shared__ __align__(16) float s_q[DA_D];
+  __shared__ float s_p[DA_BLK];
+  __shared__ float s_red[2][4];
+  __shared__ __align__(16) float s_o[8][DA_D];
+  pdl_trigger();
+  pdl_wait();
+  s_q[tid] = __half2float(q[((long long)b * H + h) * DA_D + tid]);
   const long long base = ((long long)b * H + h) * max_seq * DA_D;
   const int k0 = split * chunk, k1 = min(kv_len, k0 + chunk);
-  float m = -INFINITY, l = 0.0f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-  for (int key = k0 + warp; key < k1; key += 4) {
-    const uint2 kraw = __ldg(reinterpret_cast<const uint2*>(kc + base + (long long)key * DA_D + lane * 4));
-    const uint2 vraw = __ldg(reinterpret_cast<const uint2*>(vc + base + (long long)key * DA_D + lane * 4));
-    const float2 ka = __half22float2(*reinterpret_cast<const __half2*>(&kraw.x));
-    const float2 kb = __half22float2(*reinterpret_cast<const __half2*>(&kraw.y));
-    float s = q01.x * ka.x + q01.y * ka.y + q23.x * kb.x + q23.y * kb.y;
-    s = warp_sum(s) * scale_log2;
-    const float m_new = fmaxf(m, s);
-    const float corr = exp2f(m - m_new);
-    const float p = exp2f(s - m_new);
-    const float2 va = __half22float2(*reinterpret_cast<const __half2*>(&vraw.x));
-    const float2 vb = __half22float2(*reinterpret_cast<const __half2*>(&vraw.y));
-    l = l * corr + p;
-    o0 = o0 * corr + p * va.x; o1 = o1 * corr + p * va.y;
-    o2 = o2 * corr + p * vb.x; o3 = o3 * corr + p * vb.y;
-    m = m_new;
-  }
-  if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
-  s_o[warp][lane * 4 + 0] = o0; s_o[warp][lane * 4 + 1] = o1;
-  s_o[warp][lane * 4 + 2] = o2; s_o[warp][lane * 4 + 3] = o3;
+  const int g = tid >> 4, c = tid & 15;            // P.V role: key group (8 groups), 8-dim chunk
+  float m_run = -INFINITY, l_run = 0.0f, o_run = 0.0f;     // o_run: dim `tid`
   __syncthreads();
-  if (warp == 0) {
-    float mm = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
-    const float mu = (mm == -INFINITY) ? 0.0f : mm;
-    float ll = 0.0f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int kb = k0; kb < k1; kb += DA_BLK) {
+    const int cnt = min(DA_BLK, k1 - kb);
+    // V vectors of this thread: keys g, g+8, ... (16 of them), dims c*8..c*8+7 -- issued before the score math
+    uint4 vv[16];
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const float c = exp2f(s_m[w] - mu);
-      ll += s_l[w] * c;
-      a0 += s_o[w][lane * 4 + 0] * c; a1 += s_o[w][lane * 4 + 1] * c;
-      a2 += s_o[w][lane * 4 + 2] * c; a3 += s_o[w][lane * 4 + 3] * c;
+    for (int i = 0; i < 16; ++i) {
+      const int t = g + 8 * i;
+      vv[i] = t < cnt ? __ldg(reinterpret_cast<const uint4*>(vc + base + (long long)(kb + t) * DA_D) + c)
+                      : make_uint4(0, 0, 0, 0);
     }
-    float* dst = ws + (((long long)b * H + h) * nsplit + split) * (DA_D + 2);
-    if (lane == 0) { dst[0] = mm; dst[1] = ll; }
-    dst[2 + lane * 4 + 0] = a0; dst[2 + lane * 4 + 1] = a1;
-    dst[2 + lane * 4 + 2] = a2; dst[2 + lane * 4 + 3] = a3;
+    float s = -INFINITY;
+    if (tid < cnt) {
+      const uint4* kr = reinterpret_cast<const uint4*>(kc + base + (long long)(kb + tid) * DA_D);
+      uint4 kk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) kk[i] = __ldg(kr + i);
+      float acc = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 qa = *reinterpret_cast<const float4*>(s_q + i * 8);
+        const float4 qb = *reinterpret_cast<const float4*>(s_q + i * 8 + 4);
+        const __half2* kh = reinterpret_cast<const __half2*>(&kk[i]);
+        const float2 f0 = __half22float2(kh[0]), f1 = __half22float2(kh[1]);
+        const float2 f2 = __half22float2(kh[2]), f3 = __half22float2(kh[3]);
+        acc = fmaf(qa.x, f0.x, acc); acc = fmaf(qa.y, f0.y, acc); acc = fmaf(qa.z, f1.x, acc); acc = fmaf(qa.w, f1.y, acc);
+        acc = fmaf(qb.x, f2.x, acc); acc = fmaf(qb.y, f2.y, acc); acc = fmaf(qb.z, f3.x, acc); acc = fmaf(qb.w, f3.y, acc);
+      }
+      s = acc * scale_log2;
+    }
+    const float wm = warp_max(s);
+    if (lane == 0) s_red[0][warp] = wm;
+    __syncthreads();
+    const float bm = fmaxf(fmaxf(s_red[0][0], s_red[0][1]), fmaxf(s_red[0][2], s_red[0][3]));
+    const float m_new = fmaxf(m_run, bm);                   // finite: every block has at least one key
+    const float corr = exp2f(m_run - m_new);                // 0 on the first block
+    const float p = exp2f(s - m_new);                       // 0 for absent keys
+    s_p[tid] = p;
+    const float ws_ = warp_sum(p);
+    if (lane == 0) s_red[1][warp] = ws_;
+    __syncthreads();
+    l_run = l_run * corr + (s_red[1][0] + s_red[1][1] + s_red[1][2] + s_red[1][3]);
+    m_run = m_new;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float pk = s_p[g + 8 * i];
+      const __half2* vh = reinterpret_cast<const __half2*>(&vv[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(vh[j]);
+        acc[2 * j] = fmaf(pk, f.x, acc[2 * j]);
+        acc[2 * j + 1] = fmaf(pk, f.y, acc[2 * j + 1]);
+      }
+    }
+    *reinterpret_cast<float4*>(&s_o[g][c * 8]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(&s_o[g][c * 8 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    __syncthreads();
+    float od = 0.0f;
+#pragma unroll
+    for (int gg = 0; gg < 8; ++gg) od += s_o[gg][tid];
+    o_run = o_run * corr + od;
+    __syncthreads();                                        // s_p / s_o / s_red are rewritten by the next block
   }
+  float* dst = ws + (((long long)b * H + h) * nsplit + split) * (DA_D + 2);
+  if (tid == 0) { dst[0] = m_run; dst[1] = l_run; }
+  dst[2 + tid] = o_run;
 }
 
 __global__ void __launch_bounds__(DA_D)
 decode_attn_merge(const float* __restrict__ ws, __half* __restrict__ out, int nsplit) {
   const long long bh = blockIdx.x;
   const int d = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   const float* src = ws + bh * nsplit * (DA_D + 2);
   float mm = -INFINITY;
   for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, src[s * (DA_D + 2)]);
@@ -224,15 +349,17 @@ int decode_attention(const void* q, const void* k_cache, const void* v_cache, vo
                      int kv_len, int max_seq, float scale, void* workspace, cudaStream_t stream) {
   SB_REQUIRE(D == DA_D, "decode_attention: head_dim %d unsupported (LLaMA uses 128)", D);
   SB_REQUIRE(kv_len >= 1 && kv_len <= max_seq, "decode_attention: kv_len %d outside [1,%d]", kv_len, max_seq);
-  int nsplit = (kv_len + 255) / 256;
+  int nsplit = (kv_len + DA_BLK - 1) / DA_BLK;
   if (nsplit > DA_MAX_SPLITS) nsplit = DA_MAX_SPLITS;
-  const int chunk = (kv_len + nsplit - 1) / nsplit;
+  const int chunk = ((kv_len + nsplit - 1) / nsplit + DA_BLK - 1) / DA_BLK * DA_BLK;    // whole 128-key blocks
+  nsplit = (kv_len + chunk - 1) / chunk;                                               // no empty split
   dim3 grid(nsplit, H, B);
-  decode_attn_partial<<<grid, 128, 0, stream>>>(static_cast<const __half*>(q), static_cast<const __half*>(k_cache),
-                                                static_cast<const __half*>(v_cache), static_cast<float*>(workspace),
-                                                H, kv_len, max_seq, chunk, scale * 1.4426950408889634f);
+  SB_CHECK_CUDA(launch_chain(decode_attn_partial, grid, dim3(128), 0, stream, static_cast<const __half*>(q),
+                             static_cast<const __half*>(k_cache), static_cast<const __half*>(v_cache),
+                             static_cast<float*>(workspace), H, kv_len, max_seq, chunk, scale * 1.4426950408889634f));
   SB_LAUNCH_CHECK();
-  decode_attn_merge<<<B * H, DA_D, 0, stream>>>(static_cast<const float*>(workspace), static_cast<__half*>(out), nsplit);
+  SB_CHECK_CUDA(launch_chain(decode_attn_merge, dim3(B * H), dim3(DA_D), 0, stream, static_cast<const float*>(workspace),
+                             static_cast<__half*>(out), nsplit));
   SB_LAUNCH_CHECK();
   return 0;
 }

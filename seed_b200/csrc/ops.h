@@ -30,8 +30,8 @@ int get_rope_tables(int D, float base, int min_pos, const void** cos_t, const vo
                     cudaStream_t stream);
 // elementwise helpers (misc.cu)
 int add_rows(const void* a, const void* b, void* out, int rows, int cols, int b_rows, cudaStream_t stream);
-int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* residual, int M, int N, int K, int mode,
-         cudaStream_t stream);
+int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* residual, const void* norm_w, float eps,
+         int M, int N, int K, int mode, cudaStream_t stream);
 int decode_attention(const void* q, const void* k_cache, const void* v_cache, void* out, int B, int H, int D,
                      int kv_len, int max_seq, float scale, void* workspace, cudaStream_t stream);
 

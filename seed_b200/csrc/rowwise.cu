@@ -254,6 +254,8 @@ rope_kv_kernel(const __half* __restrict__ qkv, const long long* __restrict__ pos
   const int half_d = D / 2;
   const int vec_per_head = half_d / 8;
   const long long HD = (long long)H * D;
+  pdl_trigger();
+  pdl_wait();
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int vi = (int)(i % vec_per_head);
     long long t = i / vec_per_head;
@@ -311,11 +313,11 @@ int rope_kv_append_tables(const void* qkv, const int64_t* positions, int B, int 
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  rope_kv_kernel<<<blocks, 256, 0, stream>>>(static_cast<const __half*>(qkv),
-                                             reinterpret_cast<const long long*>(positions), S, H, D, past_len,
-                                             max_seq, max_pos, static_cast<const __half*>(cos_t),
-                                             static_cast<const __half*>(sin_t), static_cast<__half*>(q_out),
-                                             static_cast<__half*>(k_cache), static_cast<__half*>(v_cache), total);
+  SB_CHECK_CUDA(launch_chain(rope_kv_kernel, dim3(blocks), dim3(256), 0, stream, static_cast<const __half*>(qkv),
+                             reinterpret_cast<const long long*>(positions), S, H, D, past_len, max_seq, max_pos,
+                             static_cast<const __half*>(cos_t), static_cast<const __half*>(sin_t),
+                             static_cast<__half*>(q_out), static_cast<__half*>(k_cache), static_cast<__half*>(v_cache),
+                             total));
   SB_LAUNCH_CHECK();
   return 0;
 }
