@@ -57,30 +57,39 @@ __device__ __forceinline__ void dot8(const uint4& w, const uint4& x, float& acc)
 template <int M, int MODE, bool NORM>
 __global__ void __launch_bounds__(256)
 gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long long ldw, __half* __restrict__ out,
-            const __half* __restrict__ residual, const __half* __restrict__ norm_w, float eps, int N, int K) {
+            const __half* __restrict__ residual, const __half* __restrict__ norm_w, float eps, int N, int K,
+            int ksplit, int iters) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint4* xs = reinterpret_cast<uint4*>(smem_raw);     // [M][K/8]
   __shared__ float red[8];
+  __shared__ float part[2][8][M][2];                  // [iteration parity][warp][row m][row of the pair]
   const int nvec = K / 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_out = (MODE == 1) ? N / 2 : N;
   const int n_tasks = (MODE == 1) ? N / 2 : (N + 1) / 2;
-  const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
+  // the 8 warps of a CTA work on 8/ksplit row pairs at a time; warp = (pair, K slice).  Short-N projections
+  // (o_proj, down_proj: 2560 row pairs for ~3500 resident warps) would otherwise be one long dependent chain of
+  // load batches per warp.
+  const int tpi = 8 / ksplit;                         // row pairs per CTA iteration
+  const int slice = warp % ksplit, tin = warp / ksplit;
+  const int vps = (((nvec + ksplit - 1) / ksplit) + 31) / 32 * 32;
+  const int v0 = slice * vps, v1 = min(nvec, v0 + vps);
   auto rows_of = [&](int t, long long& r0, long long& r1) {
     if (MODE == 1) { r0 = (long long)(t / 128) * 256 + (t % 128); r1 = r0 + 128; }
     else { r0 = 2LL * t; r1 = min(r0 + 1, (long long)N - 1); }
   };
   // first batch of this warp's first task: in flight while the activations are staged
   uint4 wa[4], wb[4];
-  if (gw < n_tasks) {
+  const int t_first = blockIdx.x * tpi + tin;
+  if (t_first < n_tasks) {
     long long r0, r1;
-    rows_of(gw, r0, r1);
+    rows_of(t_first, r0, r1);
     const uint4* w0 = reinterpret_cast<const uint4*>(W + r0 * ldw);
     const uint4* w1 = reinterpret_cast<const uint4*>(W + r1 * ldw);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int vi = lane + u * 32;
-      if (vi < nvec) { wa[u] = __ldg(w0 + vi); wb[u] = __ldg(w1 + vi); }
+      const int vi = v0 + lane + u * 32;
+      if (vi < v1) { wa[u] = __ldg(w0 + vi); wb[u] = __ldg(w1 + vi); }
     }
   }
   pdl_trigger();
@@ -123,31 +132,35 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
   }
   __syncthreads();
 
-  for (int t = gw; t < n_tasks; t += nw) {
-    long long r0, r1;
-    rows_of(t, r0, r1);
-    const uint4* w0 = reinterpret_cast<const uint4*>(W + r0 * ldw);
-    const uint4* w1 = reinterpret_cast<const uint4*>(W + r1 * ldw);
+  for (int it = 0; it < iters; ++it) {                // trip count is uniform over the CTA (barriers inside)
+    const int t = (blockIdx.x + it * gridDim.x) * tpi + tin;
+    const bool valid = t < n_tasks;
+    long long r0 = 0, r1 = 0;
     float a0[M], a1[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) { a0[m] = 0.0f; a1[m] = 0.0f; }
-    for (int v = lane; v < nvec; v += 128) {
-      if (t != gw || v != lane) {          // the very first batch is already in registers
+    if (valid) {
+      rows_of(t, r0, r1);
+      const uint4* w0 = reinterpret_cast<const uint4*>(W + r0 * ldw);
+      const uint4* w1 = reinterpret_cast<const uint4*>(W + r1 * ldw);
+      for (int v = v0 + lane; v < v1; v += 128) {
+        if (it != 0 || v != v0 + lane) {    // the very first batch is already in registers
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int vi = v + u * 32;
+            if (vi < v1) { wa[u] = __ldg(w0 + vi); wb[u] = __ldg(w1 + vi); }
+          }
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int vi = v + u * 32;
-          if (vi < nvec) { wa[u] = __ldg(w0 + vi); wb[u] = __ldg(w1 + vi); }
-        }
-      }
+          if (vi < v1) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int vi = v + u * 32;
-        if (vi < nvec) {
-#pragma unroll
-          for (int m = 0; m < M; ++m) {
-            const uint4 xv = xs[m * nvec + vi];
-            dot8(wa[u], xv, a0[m]);
-            dot8(wb[u], xv, a1[m]);
+            for (int m = 0; m < M; ++m) {
+              const uint4 xv = xs[m * nvec + vi];
+              dot8(wa[u], xv, a0[m]);
+              dot8(wb[u], xv, a1[m]);
+            }
           }
         }
       }
@@ -157,7 +170,23 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
       a0[m] = warp_sum(a0[m]);
       a1[m] = warp_sum(a1[m]);
     }
-    if (lane == 0) {
+    if (ksplit > 1) {
+      // fold the K slices in slice order (deterministic); double-buffered so one barrier per iteration is enough
+      if (lane == 0) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) { part[it & 1][warp][m][0] = a0[m]; part[it & 1][warp][m][1] = a1[m]; }
+      }
+      __syncthreads();
+      if (slice == 0 && lane == 0) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          float s0 = 0.0f, s1 = 0.0f;
+          for (int k = 0; k < ksplit; ++k) { s0 += part[it & 1][warp + k][m][0]; s1 += part[it & 1][warp + k][m][1]; }
+          a0[m] = s0; a1[m] = s1;
+        }
+      }
+    }
+    if (valid && slice == 0 && lane == 0) {
 #pragma unroll
       for (int m = 0; m < M; ++m) {
         if (MODE == 1) {
@@ -187,6 +216,7 @@ int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* resid
   const size_t smem = (size_t)M * K * 2;
   SB_REQUIRE(smem <= 200 * 1024, "gemv: activation rows do not fit shared memory (M=%d K=%d)", M, K);
   const int n_tasks = mode == 1 ? N / 2 : (N + 1) / 2;
+  const int force_split = get_option("gemv_ksplit");
   const __half* xp = static_cast<const __half*>(x);
   const __half* wp = static_cast<const __half*>(W);
   const __half* rp = static_cast<const __half*>(residual);
@@ -207,9 +237,17 @@ int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* resid
       occ_smem = smem;                                                                                     \
       if (occ < 1) occ = 1;                                                                                \
     }                                                                                                      \
-    int blocks = (n_tasks + 7) / 8;                                                                        \
-    if (blocks > num_sms() * occ) blocks = num_sms() * occ;                                                \
-    SB_CHECK_CUDA(launch_chain(kern, dim3(blocks), dim3(256), smem, stream, xp, wp, (long long)ldw, op, rp, np, eps, N, K)); \
+    const int resident = num_sms() * occ;                                                                  \
+    /* K can be split over 2 or 4 warps per row pair (option gemv_ksplit); measured on the 13B decode step it  */ \
+    /* loses (5.19 ms/token unsplit, 5.44 / 5.62 with 2 / 4 slices), so the default stays one warp per pair */ \
+    int ksplit = 1;                                                                                        \
+    if (force_split == 1 || force_split == 2 || force_split == 4) ksplit = force_split;                    \
+    const int tpi = 8 / ksplit;                                                                            \
+    int blocks = (n_tasks + tpi - 1) / tpi;                                                                \
+    if (blocks > resident) blocks = resident;                                                              \
+    const int iters = (n_tasks + blocks * tpi - 1) / (blocks * tpi);                                       \
+    SB_CHECK_CUDA(launch_chain(kern, dim3(blocks), dim3(256), smem, stream, xp, wp, (long long)ldw, op, rp, np, eps, N, K, \
+                               ksplit, iters));                                                            \
     SB_LAUNCH_CHECK();                                                                                     \
     return 0;                                                                                              \
   }

@@ -26,8 +26,8 @@ print(json.dumps({"path": "python forward", "gpu_ms_per_token": e0.elapsed_time(
 from seed_b200 import lib as L
 llm = model._llm
 pl = 256 + N
-for pdl, per_sm in ((0, 0), (1, 0)):
-    L.set_option("decode_pdl", pdl)
+for pdl, per_sm in ((1, 0), (1, 1), (1, 2), (1, 4), (0, 0)):
+    L.set_option("decode_pdl", pdl); L.set_option("gemv_ksplit", per_sm)
     for i in range(4):
         llm.forward(input_ids=nxt, inputs_embeds=None, position_ids=None, past_len=pl + i, last_only=True)
     torch.cuda.synchronize()
@@ -35,8 +35,8 @@ for pdl, per_sm in ((0, 0), (1, 0)):
     for i in range(N):
         llm.forward(input_ids=nxt, inputs_embeds=None, position_ids=None, past_len=pl + i, last_only=True)
     e1.record(); torch.cuda.synchronize()
-    print(json.dumps({"path": "C handle forward", "pdl": pdl, "gemv_stages": per_sm, "gpu_ms_per_token": round(e0.elapsed_time(e1) / N, 4)}), flush=True)
-L.set_option("decode_pdl", 0)
+    print(json.dumps({"path": "C handle forward", "pdl": pdl, "gemv_ksplit": per_sm, "gpu_ms_per_token": round(e0.elapsed_time(e1) / N, 4)}), flush=True)
+L.set_option("decode_pdl", 1); L.set_option("gemv_ksplit", 0)
 # (c) host cost of one forward with an empty queue
 torch.cuda.synchronize()
 t0 = time.perf_counter()
