@@ -302,7 +302,7 @@ def encode_arm(args, world, rank, local):
                 "attention_ms_per_step": round(prof["attention"]["ms"], 3),
                 "whole_step_tflops": round(ENCODE_FLOPS_PER_IMAGE * B / (ms / args.steps * 1e-3) / 1e12, 1)}
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:      # reported at N=1 only
         v, dt, n_cpu = cpu_encode_images_per_s(sd, args.cpu_images)
         cpu = {"value": round(v, 3), "unit": "images/s", "cores": host_cores(), "kind": "port",
                "sample": f"{n_cpu} of the {B} images, full depth, fp32, oracle/restatement.py, {dt:.1f} s"}
@@ -456,7 +456,7 @@ def llama_arm(args, world, rank, local):
     ach = lin_flops / (prof["gemm"]["ms"] * 1e-3) / 1e12
     total_tok = S * world * args.steps
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:
         import copy
 
         a2 = copy.copy(args); a2.steps, a2.warmup = 1, 1
