@@ -422,6 +422,72 @@ def llama_decode_arm(args, world, rank, local):
     }
 
 
+def preprocess_arm(args, world, rank, local):
+    """uint8 HWC images (640x480, the COCO-style size) -> bicubic resize 224 -> normalise -> fp16 on
+    the GPU (seedb200_preprocess_run), bit-exact with the reference's torchvision+Pillow `processor`."""
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+
+    from seed_b200 import lib as L
+
+    dev = torch.device("cuda", local)
+    B, H, W = args.batch, 480, 640
+    rng = np.random.default_rng(5 + rank)
+    host = torch.from_numpy(rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)).pin_memory()
+    x = host.to(dev)
+    plan = L.Preprocess(H, W, 224, "bicubic", max_batch=B)
+    out = {}
+
+    def step_device():
+        out["y"] = plan(x)
+
+    def step_e2e():
+        out["y"] = plan(host.to(dev, non_blocking=True))
+        out["sum"] = out["y"][:, :, ::56, ::56].float().sum().cpu()      # small device->host read of the result
+
+    step_device(); torch.cuda.synchronize()
+    L.reset_launch_count()
+    with ClockSampler(local) as cs:
+        ms = timed(step_device, args.steps, args.warmup, world)
+    launches = L.launch_count() // (args.steps + args.warmup)
+    clocks = cs.summary()
+    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup), world)
+    peaks = measured_peaks()
+    alg_bytes = B * (H * W * 3 + 3 * 224 * 224 * 2)
+    ach = alg_bytes / (ms / args.steps * 1e-3) / 1e9
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        ref = transforms.Compose([transforms.Resize((224, 224), interpolation=3), transforms.ToTensor(),
+                                  transforms.Normalize((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711))])
+        n_cpu = min(B, 64)
+        pil = [Image.fromarray(host[i].numpy(), "RGB") for i in range(n_cpu)]
+        t0 = time.perf_counter()
+        res = [ref(p).half() for p in pil]
+        dt = time.perf_counter() - t0
+        same = bool(torch.equal(torch.stack(res).view(torch.int16), out["y"][:n_cpu].cpu().view(torch.int16)))
+        cpu = {"value": round(n_cpu / dt, 1), "unit": "images/s", "cores": 1, "kind": "reference",
+               "sample": f"{n_cpu} of the {B} images through torchvision+Pillow (the reference's own processor), one thread",
+               "bit_exact_vs_gpu": same}
+    total = B * world * args.steps
+    return {
+        "metric": "images/sec preprocess (resize+normalise)", "value": round(total / (ms * 1e-3), 1), "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"preprocess_b{B}: uint8 {H}x{W}x3 -> Pillow-exact bicubic 224x224 -> CLIP normalise -> fp16",
+                   "global_batch": B * world, "parallelism": f"dp{world}",
+                   "l2": f"inputs {B * H * W * 3 / 1e6:.0f} MB per step (> L2 at B=256)"},
+        "clocks": clocks,
+        "e2e": {"value": round(total / (ms_e2e * 1e-3), 1), "unit": "images/s", "h2d_bytes_per_step": B * world * H * W * 3,
+                "d2h_bytes_per_step": 4 * world, "api": "seed_b200.lib.Preprocess(pinned uint8.to(cuda)) -> checksum.cpu()"},
+        "gpu_launches": int(launches) * args.steps,
+        "roofline": {"kernel": "sb::resize_h_kernel + sb::resize_v_norm_kernel", "bound": "hbm", "achieved": round(ach, 1),
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None,
+                     "peak_source": peaks["source"], "algorithmic_bytes_per_step": alg_bytes},
+        "cpu_baseline": cpu,
+    }
+
+
 def llama_arm(args, world, rank, local):
     from transformers.models.llama.configuration_llama import LlamaConfig
 
@@ -492,7 +558,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="seedb200", choices=["seedb200", "reference"])
-    ap.add_argument("--workload", default="encode", choices=["encode", "llama_prefill", "llama_decode"])
+    ap.add_argument("--workload", default="encode", choices=["encode", "llama_prefill", "llama_decode", "preprocess"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (encode)")
     ap.add_argument("--seq", type=int, default=2048, help="prompt length (llama_prefill)")
     ap.add_argument("--prompt", type=int, default=256, help="prompt length (llama_decode)")
@@ -526,7 +592,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the seedb200 arm has no CPU fallback; use --impl reference)")
     world, rank, local = dist_setup(args.gpus)
-    arm = {"encode": encode_arm, "llama_prefill": llama_arm, "llama_decode": llama_decode_arm}[args.workload]
+    arm = {"encode": encode_arm, "llama_prefill": llama_arm, "llama_decode": llama_decode_arm, "preprocess": preprocess_arm}[args.workload]
     res = arm(args, world, rank, local)
     if world > 1:
         import torch.distributed as dist

@@ -236,6 +236,23 @@ int seedb200_llama_kv_load(seedb200_llama* llm, int layer, const void* k, const 
 /* tap: final hidden states (after model.norm) of the last forward [B*S,hidden] */
 int64_t seedb200_llama_tap(seedb200_llama* llm, int what, void* dst, int64_t max_elems, void* stream);
 
+/* ---- image preprocessing (the caller side of encode) -------------------------------------
+ * Replaces the CPU pipeline in front of the tokenizer, bit for bit:
+ *   models/transforms.py:4-19             Resize((S,S)) [PIL BILINEAR = filter 2] -> ToTensor -> Normalize(CLIP)
+ *   models/seed_llama_tokenizer.py:50-56  Resize((S,S), interpolation=3) [PIL BICUBIC = filter 3] -> ToTensor -> Normalize
+ * plus the .half() of ImageTokenizer.encode (:84-85).  Input: n RGB images of one size, uint8 [n,in_h,in_w,3]
+ * (interleaved, as np.asarray(pil_image)) in device memory; output fp16 [n,3,S,S] ready for
+ * seedb200_encoder_encode.  The resize is Pillow's 8-bit two-pass fixed-point resampling (weights built on the
+ * host in double exactly as Pillow does, 22 fractional bits, 8-bit intermediate image); the normalisation is
+ * IEEE fp32 ((v/255 - mean)/std), so the result equals torchvision's on the same bytes.
+ * A plan owns the weight tables and the intermediate buffer for one (in_h, in_w, S, filter); run() allocates
+ * nothing and only enqueues on `stream`.                                                                        */
+typedef struct seedb200_preprocess seedb200_preprocess;
+int seedb200_preprocess_create(int in_h, int in_w, int out_size, int filter, int max_batch,
+                               seedb200_preprocess** out);
+void seedb200_preprocess_destroy(seedb200_preprocess* plan);
+int seedb200_preprocess_run(seedb200_preprocess* plan, const void* images_u8, int n, void* out_f16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

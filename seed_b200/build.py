@@ -18,7 +18,7 @@ LIB = os.path.join(ROOT, "libseedb200.so")
 ORACLE_DIR = os.path.join(REPO, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "libvq_oracle.so")
 
-SOURCES = ["capi.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "attention_causal_tc.cu", "rowwise.cu", "vq.cu", "misc.cu", "encoder.cu", "llama.cu"]
+SOURCES = ["capi.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "attention_causal_tc.cu", "rowwise.cu", "vq.cu", "misc.cu", "encoder.cu", "llama.cu", "preprocess.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "ops.h"), os.path.join(REPO, "include", "seedb200.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -70,10 +70,10 @@ def NVCC_FLAGS_CMD(src: str, obj: str) -> list[str]:
 
 
 def build_oracle(force: bool = False) -> str:
-    src = os.path.join(ORACLE_DIR, "vq_oracle.c")
-    if force or not _newer(ORACLE_LIB, [src]):
+    srcs = [os.path.join(ORACLE_DIR, "vq_oracle.c"), os.path.join(ORACLE_DIR, "resize_oracle.c")]
+    if force or not _newer(ORACLE_LIB, srcs):
         # -ffp-contract=off: the oracle's arithmetic is pinned operation by operation
-        _run(["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-o", ORACLE_LIB, src, "-lm"])
+        _run(["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-o", ORACLE_LIB] + srcs + ["-lm"])
     return ORACLE_LIB
 
 

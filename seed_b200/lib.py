@@ -28,6 +28,7 @@ EXPORTS = [
     "seedb200_encoder_encode_host", "seedb200_encoder_detokenize", "seedb200_encoder_tap",
     "seedb200_llama_create", "seedb200_llama_destroy", "seedb200_llama_forward", "seedb200_llama_kv_ptrs",
     "seedb200_llama_kv_load", "seedb200_llama_tap",
+    "seedb200_preprocess_create", "seedb200_preprocess_destroy", "seedb200_preprocess_run",
 ]
 
 
@@ -106,6 +107,10 @@ def load() -> C.CDLL:
                                             C.POINTER(C.c_void_p)]
     lib.seedb200_encoder_destroy.argtypes = [C.c_void_p]
     lib.seedb200_encoder_destroy.restype = None
+    lib.seedb200_preprocess_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.seedb200_preprocess_destroy.argtypes = [C.c_void_p]
+    lib.seedb200_preprocess_destroy.restype = None
+    lib.seedb200_preprocess_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.seedb200_encoder_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p]
     lib.seedb200_encoder_encode_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -281,6 +286,44 @@ def embedding(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
                                     table.shape[1], out.data_ptr(), out.stride(0), table.shape[0], stream_ptr()),
           "seedb200_embedding")
     return out
+
+
+class Preprocess:
+    """seedb200_preprocess plan: uint8 [n,H,W,3] (device) -> fp16 [n,3,S,S], bit-exact with torchvision + Pillow."""
+
+    FILTERS = {"bilinear": 2, "bicubic": 3, 2: 2, 3: 3}
+
+    def __init__(self, in_h: int, in_w: int, out_size: int = 224, filter="bilinear", max_batch: int = 256):
+        if not torch.cuda.is_available():
+            raise RuntimeError("seedb200 preprocessing needs a CUDA device: there is no CPU path")
+        self.in_h, self.in_w, self.out, self.max_batch = in_h, in_w, out_size, max_batch
+        self._h = C.c_void_p()
+        check(load().seedb200_preprocess_create(in_h, in_w, out_size, self.FILTERS[filter], max_batch, C.byref(self._h)),
+              "seedb200_preprocess_create")
+
+    def __call__(self, images_u8: torch.Tensor) -> torch.Tensor:
+        if images_u8.dtype != torch.uint8 or not images_u8.is_cuda:
+            raise RuntimeError("preprocess: expected a CUDA uint8 tensor [n,H,W,3]")
+        if images_u8.dim() == 3:
+            images_u8 = images_u8[None]
+        n = images_u8.shape[0]
+        if tuple(images_u8.shape[1:]) != (self.in_h, self.in_w, 3):
+            raise ValueError(f"preprocess: plan is for {self.in_h}x{self.in_w}x3 images, got {tuple(images_u8.shape)}")
+        images_u8 = images_u8.contiguous()
+        out = torch.empty((n, 3, self.out, self.out), dtype=torch.float16, device=images_u8.device)
+        for i in range(0, n, self.max_batch):
+            m = min(self.max_batch, n - i)
+            check(load().seedb200_preprocess_run(self._h, images_u8[i:i + m].data_ptr(), m, out[i:i + m].data_ptr(),
+                                                 stream_ptr()), "seedb200_preprocess_run")
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h:
+                load().seedb200_preprocess_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 # --------------------------------------------------------------------------------------------------

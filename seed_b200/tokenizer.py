@@ -58,7 +58,11 @@ class ImageTokenizer(nn.Module):
                 raise RuntimeError("load_diffusion=True needs the `diffusers` package (not installed here)") from e
             self.diffusion_model = StableUnCLIPImg2ImgPipeline.from_pretrained(
                 diffusion_model_path, torch_dtype=torch.float16).to(device)
-        self.processor = _make_processor(image_size)
+        self.processor = _make_processor(image_size)          # the reference's CPU pipeline (attribute kept)
+        # its device-side twin: same bytes in, bit-identical fp16 tensor out (seed_b200/csrc/preprocess.cu)
+        from .preprocess import GpuClipTransform
+
+        self.gpu_processor = GpuClipTransform(image_size, "bicubic", device=device)
         # fixed latents / noise for the diffusion decoder (seed_llama_tokenizer.py:61-65)
         self.latents = torch.randn(torch.Size([1, 4, 96, 96]), generator=None, device=device, dtype=torch.float16)
         self.noise = torch.randn(torch.Size([1, 1024]), generator=None, device=device, dtype=torch.float16)
@@ -153,8 +157,9 @@ class SeedImageTokenMixin:
 
             image_pil = Image.open(image_path).convert("RGB")
         if image_pil is not None:
-            image_torch = self.image_tokenizer.processor(image_pil)
-            image_torch = image_torch.to(self.device)
+            # same arithmetic as `self.image_tokenizer.processor(image_pil)` (Pillow bicubic resize, ToTensor,
+            # Normalize, then the .half() of encode), computed by seedb200_preprocess_run on the raw bytes
+            image_torch = self.image_tokenizer.gpu_processor(image_pil)
         return self.image_tokenizer.encode(image_torch)
 
     def decode_image(self, indices, negative_indices=None, guidance_scale=10):

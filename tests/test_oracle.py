@@ -156,3 +156,28 @@ def test_synth_is_deterministic_and_fp16_representable():
     ids = synth.prompt_ids(2, 64, n_image_spans=1)
     assert ids[0, 1] == 32000 + 8192 and ids[0, 34] == 32000 + 8193
     assert ((ids[0, 2:34] >= 32000) & (ids[0, 2:34] < 32000 + 8192)).all()
+
+
+# ----------------------------------------------------------------------------------------------
+# resize oracle (oracle/resize_oracle.c) pinned against the installed Pillow -- the third-party code the
+# reference's transforms actually execute (models/transforms.py:4-19, seed_llama_tokenizer.py:50-56)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("filt", [2, 3])
+@pytest.mark.parametrize("h,w", [(224, 224), (300, 400), (1000, 800), (64, 48), (225, 223), (1, 1), (7, 1000),
+                                 (500, 333), (100, 224), (449, 448)])
+def test_resize_oracle_matches_pillow(h, w, filt):
+    from PIL import Image
+
+    from seed_b200.build import ORACLE_LIB, build_oracle
+
+    build_oracle()
+    lib = C.CDLL(ORACLE_LIB)
+    rng = np.random.default_rng(h * 31 + w + filt)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    if h > 4:
+        img[: h // 3] = (img[: h // 3] // 128) * 255
+    ref = np.asarray(Image.fromarray(img, "RGB").resize((224, 224), Image.BILINEAR if filt == 2 else Image.BICUBIC))
+    out = np.zeros((224, 224, 3), np.uint8)
+    rc = lib.resize_oracle_u8(img.ctypes.data_as(C.c_void_p), h, w, 224, 224, filt, out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    assert np.array_equal(out, ref)
