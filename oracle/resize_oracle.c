@@ -12,6 +12,11 @@
  *   - weights are converted to fixed point with 22 fractional bits, rounding half away from zero;
  *   - horizontal pass over the rows the vertical pass needs, then vertical pass; each pass accumulates in int32
  *     starting from 1 << 21 and stores clip8(acc >> 22) -- the intermediate image is 8-bit.
+ *   - pass order: horizontal first, EXCEPT (Pillow >= 11, PIL/Image.py `resize`: "if self.size[1] > self.size[0] * 100
+ *     and size[1] < self.size[1]") for images more than 100 times taller than wide that shrink vertically, which
+ *     are resized vertically first.  Older Pillow releases (the ones contemporary with the reference's
+ *     requirements.txt) always ran horizontal first; the two orders differ by up to 19 grey levels on such images.
+ *     The oracle follows the Pillow that is installed next to it, because that is what it is pinned against.
  * Pinned by tests/test_oracle.py::test_resize_oracle_matches_pillow against the installed Pillow itself
  * (random images, up- and down-scaling, both filters): bit-exact.
  */
@@ -98,9 +103,7 @@ int resize_oracle_coeffs(int in_size, int out_size, int filter, int* bounds, int
   return ksize;
 }
 
-/* src [H, W, 3] uint8 (RGB, interleaved) -> dst [out_h, out_w, 3] uint8 */
-int resize_oracle_u8(const uint8_t* src, int H, int W, int out_h, int out_w, int filter, uint8_t* dst) {
-  if (!src || !dst || H <= 0 || W <= 0 || out_h <= 0 || out_w <= 0 || (filter != 2 && filter != 3)) return 1;
+static int resize_two_pass(const uint8_t* src, int H, int W, int out_h, int out_w, int filter, uint8_t* dst) {
   int *bh, *bv; int32_t *kh, *kv;
   const int ksh = precompute(W, out_w, filter, &bh, &kh);
   const int ksv = precompute(H, out_h, filter, &bv, &kv);
@@ -138,4 +141,18 @@ int resize_oracle_u8(const uint8_t* src, int H, int W, int out_h, int out_w, int
   }
   free(tmp); free(bh); free(bv); free(kh); free(kv);
   return 0;
+}
+
+/* src [H, W, 3] uint8 (RGB, interleaved) -> dst [out_h, out_w, 3] uint8 */
+int resize_oracle_u8(const uint8_t* src, int H, int W, int out_h, int out_w, int filter, uint8_t* dst) {
+  if (!src || !dst || H <= 0 || W <= 0 || out_h <= 0 || out_w <= 0 || (filter != 2 && filter != 3)) return 1;
+  if ((long long)H > (long long)W * 100 && out_h < H) {
+    /* PIL/Image.py: vertical resize to (W, out_h) first, then the horizontal one */
+    uint8_t* mid = (uint8_t*)malloc((size_t)out_h * W * 3);
+    resize_two_pass(src, H, W, out_h, W, filter, mid);      /* width unchanged: identity horizontal weights */
+    const int rc = resize_two_pass(mid, out_h, W, out_h, out_w, filter, dst);
+    free(mid);
+    return rc;
+  }
+  return resize_two_pass(src, H, W, out_h, out_w, filter, dst);
 }

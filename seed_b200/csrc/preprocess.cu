@@ -27,6 +27,7 @@
 struct seedb200_preprocess {
   int in_h, in_w, out, filter, max_batch;
   int ksh, ksv, y_first, tmp_rows;
+  int vertical_first;        // Pillow's Image.resize: images more than 100x taller than wide that shrink vertically
   int2* bh; int32_t* kh;     // horizontal bounds [out], weights [ksh][out]
   int2* bv; int32_t* kv;     // vertical bounds [out] (ymin relative to y_first), weights [ksv][out]
   uint8_t* tmp;              // [max_batch][tmp_rows][out][3]
@@ -90,72 +91,120 @@ __device__ __forceinline__ uint8_t pp_clip8(int v) {
   return (uint8_t)min(255, max(0, v));
 }
 
+// torchvision: ToTensor -> float32 / 255; Normalize -> (x - mean) / std with float32 mean/std (transforms.py:15-16);
+// then the .half() of ImageTokenizer.encode.  IEEE fp32 division and subtraction, round-to-nearest-even to fp16.
+__device__ __forceinline__ __half pp_normalize(uint8_t v, int c) {
+  const float mean = c == 0 ? 0.48145466f : (c == 1 ? 0.4578275f : 0.40821073f);
+  const float stdv = c == 0 ? 0.26862954f : (c == 1 ? 0.26130258f : 0.27577711f);
+  const float x = __fdiv_rn((float)v, 255.0f);
+  return __float2half_rn(__fdiv_rn(__fsub_rn(x, mean), stdv));
+}
+
+constexpr int PP_ROWS = 4;       // source rows per CTA of the horizontal pass
+constexpr int PP_MAX_TAPS = 24;  // taps kept in registers; wider windows (downscale > ~5.5x bicubic) re-read the table
+
+// Horizontal pass: rows [row0, row0 + PP_ROWS) of image blockIdx.y.  NORM = false: 8-bit intermediate
+// dst8 [img][row][out][3]; NORM = true (vertical-first order): normalised fp16 planar dstf [img][3][rows][out].
+template <bool NORM>
 __global__ void __launch_bounds__(256)
-resize_h_kernel(const uint8_t* __restrict__ src, long long image_stride, int in_w, int out, int y_first, int tmp_rows,
-                const int2* __restrict__ bounds, const int32_t* __restrict__ kk_t, uint8_t* __restrict__ tmp) {
+resize_h_kernel(const uint8_t* __restrict__ src, long long image_stride, int in_w, int out, int row_first, int rows,
+                const int2* __restrict__ bounds, const int32_t* __restrict__ kk_t, uint8_t* __restrict__ dst8,
+                __half* __restrict__ dstf) {
   extern __shared__ __align__(16) uint8_t pp_smem[];
-  const int y = blockIdx.x, img = blockIdx.y;
-  const uint8_t* row = src + (long long)img * image_stride + (long long)(y + y_first) * in_w * 3;
+  const int img = blockIdx.y, row0 = blockIdx.x * PP_ROWS;
+  const int nrows = min(PP_ROWS, rows - row0);
   const int nbytes = in_w * 3;
-  const int mis = (int)(reinterpret_cast<uintptr_t>(row) & 15);   // keep shared offsets congruent to the global address
-  uint8_t* srow = pp_smem + mis;
-  uint8_t* sout = pp_smem + ((16 + nbytes + 15) & ~15);
-  {
+  const int rstride = (nbytes + 16 + 15) & ~15;          // per-row shared-memory slot (16 bytes of alignment slack)
+  const int obytes = out * 3;
+  const int ostride = (obytes + 15) & ~15;
+  uint8_t* sout = pp_smem + PP_ROWS * rstride;
+  for (int r = 0; r < nrows; ++r) {
+    const uint8_t* row = src + (long long)img * image_stride + (long long)(row0 + r + row_first) * nbytes;
+    const int mis = (int)(reinterpret_cast<uintptr_t>(row) & 15);   // shared offset congruent to the global address
+    uint8_t* srow = pp_smem + r * rstride + mis;
     const int head = min(nbytes, (16 - mis) & 15);
     for (int i = threadIdx.x; i < head; i += 256) srow[i] = row[i];
     const int body = (nbytes - head) >> 4;
     const uint4* g = reinterpret_cast<const uint4*>(row + head);
-    uint4* s = reinterpret_cast<uint4*>(srow + head);
-    for (int i = threadIdx.x; i < body; i += 256) s[i] = __ldg(g + i);
+    uint4* s4 = reinterpret_cast<uint4*>(srow + head);
+    for (int i = threadIdx.x; i < body; i += 256) s4[i] = __ldg(g + i);
     for (int i = head + body * 16 + threadIdx.x; i < nbytes; i += 256) srow[i] = row[i];
   }
   __syncthreads();
   for (int xx = threadIdx.x; xx < out; xx += 256) {
     const int2 b = bounds[xx];
-    int s0 = 1 << (PP_PRECISION_BITS - 1), s1 = s0, s2 = s0;
-    const uint8_t* p = srow + b.x * 3;
-    for (int x = 0; x < b.y; ++x) {
-      const int k = __ldg(kk_t + (long long)x * out + xx);
-      s0 += p[3 * x + 0] * k;
-      s1 += p[3 * x + 1] * k;
-      s2 += p[3 * x + 2] * k;
+    int kreg[PP_MAX_TAPS];
+#pragma unroll
+    for (int x = 0; x < PP_MAX_TAPS; ++x) kreg[x] = x < b.y ? __ldg(kk_t + (long long)x * out + xx) : 0;
+    for (int r = 0; r < nrows; ++r) {
+      const uint8_t* row = src + (long long)img * image_stride + (long long)(row0 + r + row_first) * nbytes;
+      const uint8_t* p = pp_smem + r * rstride + (int)(reinterpret_cast<uintptr_t>(row) & 15) + b.x * 3;
+      int s0 = 1 << (PP_PRECISION_BITS - 1), s1 = s0, s2 = s0;
+#pragma unroll
+      for (int x = 0; x < PP_MAX_TAPS; ++x) {
+        if (x < b.y) {
+          s0 += p[3 * x + 0] * kreg[x];
+          s1 += p[3 * x + 1] * kreg[x];
+          s2 += p[3 * x + 2] * kreg[x];
+        }
+      }
+      for (int x = PP_MAX_TAPS; x < b.y; ++x) {
+        const int k = __ldg(kk_t + (long long)x * out + xx);
+        s0 += p[3 * x + 0] * k;
+        s1 += p[3 * x + 1] * k;
+        s2 += p[3 * x + 2] * k;
+      }
+      if (NORM) {
+        const long long o = ((long long)img * 3 * rows + (row0 + r)) * out + xx;
+        dstf[o] = pp_normalize(pp_clip8(s0), 0);
+        dstf[o + (long long)rows * out] = pp_normalize(pp_clip8(s1), 1);
+        dstf[o + 2LL * rows * out] = pp_normalize(pp_clip8(s2), 2);
+      } else {
+        uint8_t* so = sout + r * ostride + xx * 3;
+        so[0] = pp_clip8(s0); so[1] = pp_clip8(s1); so[2] = pp_clip8(s2);
+      }
     }
-    sout[xx * 3 + 0] = pp_clip8(s0);
-    sout[xx * 3 + 1] = pp_clip8(s1);
-    sout[xx * 3 + 2] = pp_clip8(s2);
   }
-  __syncthreads();
-  uint8_t* dst = tmp + ((long long)img * tmp_rows + y) * out * 3;
-  const int obytes = out * 3;
-  if ((obytes & 15) == 0) {
-    for (int i = threadIdx.x; i < (obytes >> 4); i += 256)
-      reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(sout)[i];
-  } else {
-    for (int i = threadIdx.x; i < obytes; i += 256) dst[i] = sout[i];
+  if (!NORM) {
+    __syncthreads();
+    for (int r = 0; r < nrows; ++r) {
+      uint8_t* dst = dst8 + ((long long)img * rows + row0 + r) * obytes;
+      const uint8_t* so = sout + r * ostride;
+      if ((obytes & 15) == 0) {
+        for (int i = threadIdx.x; i < (obytes >> 4); i += 256)
+          reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(so)[i];
+      } else {
+        for (int i = threadIdx.x; i < obytes; i += 256) dst[i] = so[i];
+      }
+    }
   }
 }
 
+// Vertical pass over rows of `width` pixels: output row blockIdx.x of image blockIdx.y.  NORM = true (horizontal-
+// first order, width == out): normalised fp16 planar; NORM = false: 8-bit intermediate [img][out_rows][width][3].
+template <bool NORM>
 __global__ void __launch_bounds__(256)
-resize_v_norm_kernel(const uint8_t* __restrict__ tmp, int out, int tmp_rows, const int2* __restrict__ bounds,
-                     const int32_t* __restrict__ kk_t, __half* __restrict__ dst) {
+resize_v_kernel(const uint8_t* __restrict__ src, long long image_stride, int width, int out_rows,
+                const int2* __restrict__ bounds, const int32_t* __restrict__ kk_t, uint8_t* __restrict__ dst8,
+                __half* __restrict__ dstf) {
   const int yy = blockIdx.x, img = blockIdx.y;
   const int2 b = bounds[yy];
-  const uint8_t* base = tmp + ((long long)img * tmp_rows + b.x) * out * 3;
-  // torchvision: ToTensor -> float32 / 255; Normalize -> (x - mean) / std with float32 mean/std (transforms.py:16)
-  const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
-  const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
-  for (int xx = threadIdx.x; xx < out; xx += 256) {
-    int s[3] = {1 << (PP_PRECISION_BITS - 1), 1 << (PP_PRECISION_BITS - 1), 1 << (PP_PRECISION_BITS - 1)};
+  const uint8_t* base = src + (long long)img * image_stride + (long long)b.x * width * 3;
+  for (int xx = threadIdx.x; xx < width; xx += 256) {
+    int s0 = 1 << (PP_PRECISION_BITS - 1), s1 = s0, s2 = s0;
     for (int y = 0; y < b.y; ++y) {
-      const int k = __ldg(kk_t + (long long)y * out + yy);
-      const uint8_t* p = base + ((long long)y * out + xx) * 3;
-      s[0] += p[0] * k; s[1] += p[1] * k; s[2] += p[2] * k;
+      const int k = __ldg(kk_t + (long long)y * out_rows + yy);
+      const uint8_t* p = base + ((long long)y * width + xx) * 3;
+      s0 += p[0] * k; s1 += p[1] * k; s2 += p[2] * k;
     }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float v = __fdiv_rn((float)pp_clip8(s[c]), 255.0f);
-      const float nrm = __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);
-      dst[(((long long)img * 3 + c) * out + yy) * out + xx] = __float2half_rn(nrm);
+    if (NORM) {
+      const long long o = ((long long)img * 3 * out_rows + yy) * width + xx;
+      dstf[o] = pp_normalize(pp_clip8(s0), 0);
+      dstf[o + (long long)out_rows * width] = pp_normalize(pp_clip8(s1), 1);
+      dstf[o + 2LL * out_rows * width] = pp_normalize(pp_clip8(s2), 2);
+    } else {
+      uint8_t* o = dst8 + (((long long)img * out_rows + yy) * width + xx) * 3;
+      o[0] = pp_clip8(s0); o[1] = pp_clip8(s1); o[2] = pp_clip8(s2);
     }
   }
 }
@@ -170,7 +219,7 @@ int seedb200_preprocess_create(int in_h, int in_w, int out_size, int filter, int
   *out = nullptr;
   SB_REQUIRE(in_h > 0 && in_w > 0 && out_size > 0 && max_batch > 0, "preprocess_create: non-positive size");
   SB_REQUIRE(filter == 2 || filter == 3, "preprocess_create: filter %d (2 = PIL BILINEAR, 3 = PIL BICUBIC)", filter);
-  SB_REQUIRE((long long)in_w * 3 + out_size * 3 + 64 <= 200 * 1024, "preprocess_create: image width %d too large", in_w);
+  SB_REQUIRE((long long)sb::PP_ROWS * (in_w * 3 + 48 + out_size * 3) <= 200 * 1024, "preprocess_create: image width %d too large", in_w);
   std::vector<int2> bh, bv;
   std::vector<int32_t> kh, kv;
   seedb200_preprocess* p = new seedb200_preprocess();
@@ -178,9 +227,16 @@ int seedb200_preprocess_create(int in_h, int in_w, int out_size, int filter, int
   p->in_h = in_h; p->in_w = in_w; p->out = out_size; p->filter = filter; p->max_batch = max_batch;
   p->ksh = pp_coeffs(in_w, out_size, filter, bh, kh);
   p->ksv = pp_coeffs(in_h, out_size, filter, bv, kv);
-  p->y_first = bv[0].x;
-  p->tmp_rows = bv[out_size - 1].x + bv[out_size - 1].y - p->y_first;
-  for (auto& b : bv) b.x -= p->y_first;
+  // PIL/Image.py resize(): "if self.size[1] > self.size[0] * 100 and size[1] < self.size[1]" -> vertical pass first
+  p->vertical_first = ((long long)in_h > (long long)in_w * 100 && out_size < in_h) ? 1 : 0;
+  if (p->vertical_first) {
+    p->y_first = 0;
+    p->tmp_rows = out_size;                                  // intermediate [out][in_w][3]
+  } else {
+    p->y_first = bv[0].x;
+    p->tmp_rows = bv[out_size - 1].x + bv[out_size - 1].y - p->y_first;   // intermediate [tmp_rows][out][3]
+    for (auto& b : bv) b.x -= p->y_first;
+  }
   auto fail = [&](const char* what) {
     set_error("preprocess_create: %s failed", what);
     seedb200_preprocess_destroy(p);
@@ -190,7 +246,8 @@ int seedb200_preprocess_create(int in_h, int in_w, int out_size, int filter, int
   if (cudaMalloc(&p->bv, sizeof(int2) * out_size) != cudaSuccess) return fail("cudaMalloc");
   if (cudaMalloc(&p->kh, sizeof(int32_t) * kh.size()) != cudaSuccess) return fail("cudaMalloc");
   if (cudaMalloc(&p->kv, sizeof(int32_t) * kv.size()) != cudaSuccess) return fail("cudaMalloc");
-  if (cudaMalloc(&p->tmp, (size_t)max_batch * p->tmp_rows * out_size * 3) != cudaSuccess) return fail("cudaMalloc");
+  const size_t tmp_bytes = (size_t)max_batch * p->tmp_rows * (p->vertical_first ? in_w : out_size) * 3;
+  if (cudaMalloc(&p->tmp, tmp_bytes) != cudaSuccess) return fail("cudaMalloc");
   if (cudaMemcpy(p->bh, bh.data(), sizeof(int2) * out_size, cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(p->bv, bv.data(), sizeof(int2) * out_size, cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(p->kh, kh.data(), sizeof(int32_t) * kh.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
@@ -211,19 +268,33 @@ int seedb200_preprocess_run(seedb200_preprocess* p, const void* images_u8, int n
   SB_REQUIRE(p && images_u8 && out_f16, "preprocess_run: null argument");
   SB_REQUIRE(n > 0 && n <= p->max_batch, "preprocess_run: batch %d outside [1,%d]", n, p->max_batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t smem = (size_t)((16 + p->in_w * 3 + 15) & ~15) + (size_t)((p->out * 3 + 15) & ~15) + 16;
-  static size_t attr_smem = 48 * 1024;
-  if (smem > attr_smem) {
-    SB_CHECK_CUDA(cudaFuncSetAttribute(resize_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+  const uint8_t* src = static_cast<const uint8_t*>(images_u8);
+  __half* dst = static_cast<__half*>(out_f16);
+  const size_t smem = (size_t)PP_ROWS * (((size_t)p->in_w * 3 + 16 + 15) & ~(size_t)15) +
+                      (size_t)PP_ROWS * (((size_t)p->out * 3 + 15) & ~(size_t)15);
+  static size_t attr_smem[2] = {48 * 1024, 48 * 1024};
+  if (smem > attr_smem[p->vertical_first]) {
+    if (p->vertical_first)
+      SB_CHECK_CUDA(cudaFuncSetAttribute(resize_h_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      SB_CHECK_CUDA(cudaFuncSetAttribute(resize_h_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[p->vertical_first] = smem;
   }
-  resize_h_kernel<<<dim3(p->tmp_rows, n), 256, smem, st>>>(static_cast<const uint8_t*>(images_u8),
-                                                          (long long)p->in_h * p->in_w * 3, p->in_w, p->out, p->y_first,
-                                                          p->tmp_rows, p->bh, p->kh, p->tmp);
-  SB_LAUNCH_CHECK();
-  resize_v_norm_kernel<<<dim3(p->out, n), 256, 0, st>>>(p->tmp, p->out, p->tmp_rows, p->bv, p->kv,
-                                                        static_cast<__half*>(out_f16));
-  SB_LAUNCH_CHECK();
+  const long long in_stride = (long long)p->in_h * p->in_w * 3;
+  if (!p->vertical_first) {
+    resize_h_kernel<false><<<dim3((p->tmp_rows + PP_ROWS - 1) / PP_ROWS, n), 256, smem, st>>>(
+        src, in_stride, p->in_w, p->out, p->y_first, p->tmp_rows, p->bh, p->kh, p->tmp, nullptr);
+    SB_LAUNCH_CHECK();
+    resize_v_kernel<true><<<dim3(p->out, n), 256, 0, st>>>(p->tmp, (long long)p->tmp_rows * p->out * 3, p->out, p->out,
+                                                           p->bv, p->kv, nullptr, dst);
+    SB_LAUNCH_CHECK();
+  } else {
+    resize_v_kernel<false><<<dim3(p->out, n), 256, 0, st>>>(src, in_stride, p->in_w, p->out, p->bv, p->kv, p->tmp, nullptr);
+    SB_LAUNCH_CHECK();
+    resize_h_kernel<true><<<dim3((p->out + PP_ROWS - 1) / PP_ROWS, n), 256, smem, st>>>(
+        p->tmp, (long long)p->out * p->in_w * 3, p->in_w, p->out, 0, p->out, p->bh, p->kh, nullptr, dst);
+    SB_LAUNCH_CHECK();
+  }
   return 0;
 }
 

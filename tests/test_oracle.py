@@ -164,7 +164,7 @@ def test_synth_is_deterministic_and_fp16_representable():
 # ----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("filt", [2, 3])
 @pytest.mark.parametrize("h,w", [(224, 224), (300, 400), (1000, 800), (64, 48), (225, 223), (1, 1), (7, 1000),
-                                 (500, 333), (100, 224), (449, 448)])
+                                 (500, 333), (100, 224), (449, 448), (3000, 17), (501, 5), (500, 5), (5, 3000)])
 def test_resize_oracle_matches_pillow(h, w, filt):
     from PIL import Image
 

@@ -28,7 +28,7 @@ def rand_image(h, w, seed):
 
 
 SIZES = [(224, 224), (480, 640), (1000, 800), (64, 48), (225, 223), (1, 1), (7, 1000), (333, 500), (1536, 2048),
-         (100, 224), (449, 448), (3000, 17)]
+         (100, 224), (449, 448), (3000, 17), (501, 5), (500, 5), (5, 3000), (2300, 1700)]
 
 
 @pytest.mark.parametrize("interp", ["bilinear", "bicubic"])
