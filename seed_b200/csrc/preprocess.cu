@@ -101,7 +101,7 @@ __device__ __forceinline__ __half pp_normalize(uint8_t v, int c) {
 }
 
 constexpr int PP_ROWS = 4;       // source rows per CTA of the horizontal pass
-constexpr int PP_MAX_TAPS = 24;  // taps kept in registers; wider windows (downscale > ~5.5x bicubic) re-read the table
+constexpr int PP_MAX_TAPS = 16;  // taps on the register/word path; wider windows (bicubic downscale > 3.5x) finish on a byte loop
 
 // Horizontal pass: rows [row0, row0 + PP_ROWS) of image blockIdx.y.  NORM = false: 8-bit intermediate
 // dst8 [img][row][out][3]; NORM = true (vertical-first order): normalised fp16 planar dstf [img][3][rows][out].
@@ -140,12 +140,23 @@ resize_h_kernel(const uint8_t* __restrict__ src, long long image_stride, int in_
       const uint8_t* row = src + (long long)img * image_stride + (long long)(row0 + r + row_first) * nbytes;
       const uint8_t* p = pp_smem + r * rstride + (int)(reinterpret_cast<uintptr_t>(row) & 15) + b.x * 3;
       int s0 = 1 << (PP_PRECISION_BITS - 1), s1 = s0, s2 = s0;
+      {
+        // the window's 3 * taps bytes as aligned 32-bit shared loads + funnel shifts (one byte load per tap and
+        // channel made the shared-memory pipe the bottleneck: 39 loads -> 13 for a 13-tap bicubic window)
+        constexpr int NW = (3 * PP_MAX_TAPS + 3) / 4;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~static_cast<uintptr_t>(3));
+        const uint32_t sh = (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p)) & 3u) * 8u;
+        uint32_t w[NW + 1];
 #pragma unroll
-      for (int x = 0; x < PP_MAX_TAPS; ++x) {
-        if (x < b.y) {
-          s0 += p[3 * x + 0] * kreg[x];
-          s1 += p[3 * x + 1] * kreg[x];
-          s2 += p[3 * x + 2] * kreg[x];
+        for (int k = 0; k <= NW; ++k) w[k] = (4 * k < 3 * b.y + 4) ? wp[k] : 0u;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) w[k] = __funnelshift_r(w[k], w[k + 1], sh);
+#pragma unroll
+        for (int x = 0; x < PP_MAX_TAPS; ++x) {
+          const int i0 = 3 * x, i1 = 3 * x + 1, i2 = 3 * x + 2;
+          s0 += (int)((w[i0 >> 2] >> ((i0 & 3) * 8)) & 0xffu) * kreg[x];
+          s1 += (int)((w[i1 >> 2] >> ((i1 & 3) * 8)) & 0xffu) * kreg[x];
+          s2 += (int)((w[i2 >> 2] >> ((i2 & 3) * 8)) & 0xffu) * kreg[x];
         }
       }
       for (int x = PP_MAX_TAPS; x < b.y; ++x) {
@@ -190,8 +201,37 @@ resize_v_kernel(const uint8_t* __restrict__ src, long long image_stride, int wid
   const int yy = blockIdx.x, img = blockIdx.y;
   const int2 b = bounds[yy];
   const uint8_t* base = src + (long long)img * image_stride + (long long)b.x * width * 3;
+  const int rowbytes = width * 3;
+  if ((rowbytes & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 3) == 0) {
+    // one thread per 32-bit word of the row: the vertical weights are the same for every byte of a row
+    for (int j = threadIdx.x; j < (rowbytes >> 2); j += 256) {
+      int s[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[i] = 1 << (PP_PRECISION_BITS - 1);
+#pragma unroll 4
+      for (int y = 0; y < b.y; ++y) {     // unrolled: the loads of 4 taps are in flight together (L2 latency bound)
+        const int k = __ldg(kk_t + (long long)y * out_rows + yy);
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(base + (long long)y * rowbytes + 4 * j));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[i] += (int)((w >> (8 * i)) & 0xffu) * k;
+      }
+      if (NORM) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int bi = 4 * j + i, xx = bi / 3, c = bi - 3 * xx;
+          dstf[(((long long)img * 3 + c) * out_rows + yy) * width + xx] = pp_normalize(pp_clip8(s[i]), c);
+        }
+      } else {
+        const uint32_t o = (uint32_t)pp_clip8(s[0]) | ((uint32_t)pp_clip8(s[1]) << 8) | ((uint32_t)pp_clip8(s[2]) << 16) |
+                           ((uint32_t)pp_clip8(s[3]) << 24);
+        *reinterpret_cast<uint32_t*>(dst8 + ((long long)img * out_rows + yy) * rowbytes + 4 * j) = o;
+      }
+    }
+    return;
+  }
   for (int xx = threadIdx.x; xx < width; xx += 256) {
     int s0 = 1 << (PP_PRECISION_BITS - 1), s1 = s0, s2 = s0;
+#pragma unroll 4
     for (int y = 0; y < b.y; ++y) {
       const int k = __ldg(kk_t + (long long)y * out_rows + yy);
       const uint8_t* p = base + ((long long)y * width + xx) * 3;
@@ -271,7 +311,7 @@ int seedb200_preprocess_run(seedb200_preprocess* p, const void* images_u8, int n
   const uint8_t* src = static_cast<const uint8_t*>(images_u8);
   __half* dst = static_cast<__half*>(out_f16);
   const size_t smem = (size_t)PP_ROWS * (((size_t)p->in_w * 3 + 16 + 15) & ~(size_t)15) +
-                      (size_t)PP_ROWS * (((size_t)p->out * 3 + 15) & ~(size_t)15);
+                      (size_t)PP_ROWS * (((size_t)p->out * 3 + 15) & ~(size_t)15) + 64;   // + word over-read slack
   static size_t attr_smem[2] = {48 * 1024, 48 * 1024};
   if (smem > attr_smem[p->vertical_first]) {
     if (p->vertical_first)
