@@ -158,25 +158,80 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def cpu_encode_images_per_s(sd, n_images: int, target_s: float = 20.0):
-    """Times oracle/restatement.py on a bounded sample: `n_images` (0 = sized from a one-image probe to ~target_s)."""
+def tune_cpu_threads(sd) -> int:
+    """The oracle port is plain torch on the host; on many-core boxes torch with every hardware thread is far from
+    its best (measured: 8 threads of an 8-core container 1.08 images/s, 128 threads of the GPU box 0.02-0.47).  Give
+    the CPU baseline its best thread count: time a 4-block slice at a few counts and keep the fastest."""
     from oracle import restatement as R
     from seed_b200 import synth
 
-    torch.set_num_threads(host_cores())
+    n = host_cores()
+    cands = sorted({c for c in (n, n // 2, n // 4, 32, 16, 8) if 1 <= c <= n}, reverse=True)
+    x = synth.images(2, seed=3)
+    best, best_t = n, float("inf")
+    with torch.no_grad():
+        for c in cands:
+            torch.set_num_threads(c)
+            R.encode(x, sd, 2, 2)
+            t0 = time.perf_counter()
+            R.encode(x, sd, 4, 2)
+            t = time.perf_counter() - t0
+            if t < best_t:
+                best, best_t = c, t
+    torch.set_num_threads(best)
+    return best
+
+
+def tune_cpu_threads_gemm() -> int:
+    """same idea for the LLaMA port (GEMM dominated): fastest thread count on a 2048 x 4096 x 4096 fp32 matmul"""
+    n = host_cores()
+    cands = sorted({c for c in (n, n // 2, n // 4, 32, 16, 8) if 1 <= c <= n}, reverse=True)
+    a, b = torch.randn(2048, 4096), torch.randn(4096, 4096)
+    best, best_t = n, float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.mm(a, b)
+        t0 = time.perf_counter()
+        torch.mm(a, b); torch.mm(a, b)
+        t = time.perf_counter() - t0
+        if t < best_t:
+            best, best_t = c, t
+    torch.set_num_threads(best)
+    return best
+
+
+ENC_GFLOP_FIXED = 0.424 + 12.75 + 0.056          # patch embed + Q-Former + heads/VQ (SURVEY 8d), per image
+ENC_GFLOP_PER_BLOCK = 13.342
+
+
+def cpu_encode_images_per_s(sd, n_images: int, target_s: float = 20.0):
+    """Times oracle/restatement.py on a bounded sample of the workload.  `n_images` > 0 forces the sample size;
+    0 sizes it from the (timed) warm-up image so that the leg costs ~target_s even on a slow or contended host:
+    batches of 4 images (1 if an image takes > 6 s) until target_s has elapsed, at most 32 images."""
+    from oracle import restatement as R
+    from seed_b200 import synth
+
+    tune_cpu_threads(sd)
     with torch.no_grad():
         x1 = synth.images(1, seed=4241)
-        R.encode(x1, sd, VIT_DEPTH, QF_LAYERS)          # warm-up
         t0 = time.perf_counter()
-        R.encode(x1, sd, VIT_DEPTH, QF_LAYERS)
+        R.encode(x1, sd, VIT_DEPTH, QF_LAYERS)          # warm-up, also the probe
         probe = time.perf_counter() - t0
-        if n_images <= 0:
-            n_images = max(1, min(32, int(target_s / max(probe, 1e-3))))
-        x = synth.images(n_images, seed=4242)
-        t0 = time.perf_counter()
-        R.encode(x, sd, VIT_DEPTH, QF_LAYERS)
+        if n_images > 0:
+            x = synth.images(n_images, seed=4242)
+            t0 = time.perf_counter()
+            R.encode(x, sd, VIT_DEPTH, QF_LAYERS)
+            dt = time.perf_counter() - t0
+            return n_images / dt, dt, n_images
+        bs = 4 if probe < 6.0 else 1
+        done, t0 = 0, time.perf_counter()
+        while done < 32:
+            R.encode(synth.images(bs, seed=4242 + done), sd, VIT_DEPTH, QF_LAYERS)
+            done += bs
+            if time.perf_counter() - t0 >= target_s:
+                break
         dt = time.perf_counter() - t0
-    return n_images / dt, dt, n_images
+    return done / dt, dt, done
 
 
 def reference_arm(args, world, rank):
@@ -192,26 +247,37 @@ def reference_arm(args, world, rank):
         from oracle import restatement as R
 
         sd = synth.encoder_state_dict(VIT_DEPTH, QF_LAYERS, 0)
-        x = synth.images(2, seed=1)
+        cores = tune_cpu_threads(sd)
+        x = synth.images(1, seed=1)
         with torch.no_grad():
-            t0 = time.perf_counter(); R.encode(x, sd, VIT_DEPTH, QF_LAYERS); probe = (time.perf_counter() - t0) / 2
-        budget = 150.0 / max(1, args.steps + args.warmup)
-        nb = max(1, min(args.batch, int(budget / max(probe, 1e-3))))
+            t0 = time.perf_counter(); R.encode(x, sd, VIT_DEPTH, QF_LAYERS); probe = time.perf_counter() - t0
+        n_calls = max(1, args.steps + args.warmup)
+        budget = 150.0 / n_calls                      # seconds per step so that the whole run ends within minutes
+        depth, nb = VIT_DEPTH, max(1, min(args.batch, int(budget / max(probe, 1e-3))))
+        if probe > budget:
+            # even one full-depth image does not fit the per-step budget on this host: time a depth-truncated
+            # ViT (same blocks, fewer of them) and scale by the algorithmic FLOPs of the missing blocks
+            per_block = probe * ENC_GFLOP_PER_BLOCK / (ENC_GFLOP_FIXED + VIT_DEPTH * ENC_GFLOP_PER_BLOCK)
+            depth = max(2, min(VIT_DEPTH, int((budget - probe * ENC_GFLOP_FIXED / (ENC_GFLOP_FIXED + VIT_DEPTH * ENC_GFLOP_PER_BLOCK)) / max(per_block, 1e-6))))
+        scale_full = (ENC_GFLOP_FIXED + VIT_DEPTH * ENC_GFLOP_PER_BLOCK) / (ENC_GFLOP_FIXED + depth * ENC_GFLOP_PER_BLOCK)
         x = synth.images(nb, seed=1234)
         with torch.no_grad():
             for _ in range(args.warmup):
-                R.encode(x, sd, VIT_DEPTH, QF_LAYERS)
+                R.encode(x, sd, depth, QF_LAYERS)
             t0 = time.perf_counter()
             for _ in range(args.steps):
-                R.encode(x, sd, VIT_DEPTH, QF_LAYERS)
-            dt = time.perf_counter() - t0
+                R.encode(x, sd, depth, QF_LAYERS)
+            dt = (time.perf_counter() - t0) * scale_full
         value = nb * args.steps / dt
         sample = f"{nb} images/step (of the {args.batch}-image batch), fp32, torch {torch.get_num_threads()} threads"
+        if depth != VIT_DEPTH:
+            sample += f"; ViT truncated to {depth} of {VIT_DEPTH} blocks and the time scaled x{scale_full:.2f} by algorithmic FLOPs (host too slow for a full-depth image per step)"
         return dict(metric="images/sec SEED encode+VQ", value=value, unit="images/s", ms_per_step=1e3 * dt / args.steps,
                     sample=sample, cores=cores, workload=f"encode_b{args.batch}")
     else:
         from oracle import restatement as R
 
+        cores = tune_cpu_threads_gemm()
         layers = 2       # layer-truncated 7B (fp32 7B = 26.6 GB of weights and minutes per prompt on the host)
         sd = synth.llama_state_dict(4096, layers, 11008, 40194)
         ids = synth.prompt_ids(1, args.seq, 1)
@@ -304,8 +370,9 @@ def encode_arm(args, world, rank, local):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:      # reported at N=1 only
         v, dt, n_cpu = cpu_encode_images_per_s(sd, args.cpu_images)
-        cpu = {"value": round(v, 3), "unit": "images/s", "cores": host_cores(), "kind": "port",
-               "sample": f"{n_cpu} of the {B} images, full depth, fp32, oracle/restatement.py, {dt:.1f} s"}
+        cpu = {"value": round(v, 3), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{n_cpu} of the {B} images, full depth, fp32, oracle/restatement.py, {dt:.1f} s, "
+                         f"{torch.get_num_threads()} of {host_cores()} host threads (fastest of a short sweep)"}
     total = B * world * args.steps
     res = {
         "metric": "images/sec SEED encode+VQ", "value": round(total / (ms * 1e-3), 2), "unit": "images/s",
