@@ -252,7 +252,7 @@ def reference_arm(args, world, rank):
         with torch.no_grad():
             t0 = time.perf_counter(); R.encode(x, sd, VIT_DEPTH, QF_LAYERS); probe = time.perf_counter() - t0
         n_calls = max(1, args.steps + args.warmup)
-        budget = 150.0 / n_calls                      # seconds per step so that the whole run ends within minutes
+        budget = args.ref_seconds / n_calls           # seconds per step so that the whole run ends within minutes
         depth, nb = VIT_DEPTH, max(1, min(args.batch, int(budget / max(probe, 1e-3))))
         if probe > budget:
             # even one full-depth image does not fit the per-step budget on this host: time a depth-truncated
@@ -634,6 +634,7 @@ def main():
     ap.add_argument("--vq", default="fp16", choices=["fp16", "fp32"], help="VQ distance arithmetic")
     ap.add_argument("--cpu-images", type=int, default=0, help="images timed by the cpu_baseline leg (0 = ~20 s worth)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-seconds", type=float, default=150.0, help="wall-clock budget of the --impl reference run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "seedb200" else args.warmup
 
