@@ -100,7 +100,9 @@ __device__ __forceinline__ __half pp_normalize(uint8_t v, int c) {
   return __float2half_rn(__fdiv_rn(__fsub_rn(x, mean), stdv));
 }
 
-constexpr int PP_ROWS = 4;       // source rows per CTA of the horizontal pass
+constexpr int PP_ROWS = 16;      // max source rows per CTA of the horizontal pass (fewer, fatter CTAs: the
+                                 // block scheduler was the limit at 4 rows / 1 row per CTA)
+constexpr int PP_VROWS = 8;      // output rows per CTA of the vertical pass
 constexpr int PP_MAX_TAPS = 16;  // taps on the register/word path; wider windows (bicubic downscale > 3.5x) finish on a byte loop
 
 // Horizontal pass: rows [row0, row0 + PP_ROWS) of image blockIdx.y.  NORM = false: 8-bit intermediate
@@ -108,16 +110,16 @@ constexpr int PP_MAX_TAPS = 16;  // taps on the register/word path; wider window
 template <bool NORM>
 __global__ void __launch_bounds__(256)
 resize_h_kernel(const uint8_t* __restrict__ src, long long image_stride, int in_w, int out, int row_first, int rows,
-                const int2* __restrict__ bounds, const int32_t* __restrict__ kk_t, uint8_t* __restrict__ dst8,
+                int rpc, const int2* __restrict__ bounds, const int32_t* __restrict__ kk_t, uint8_t* __restrict__ dst8,
                 __half* __restrict__ dstf) {
   extern __shared__ __align__(16) uint8_t pp_smem[];
-  const int img = blockIdx.y, row0 = blockIdx.x * PP_ROWS;
-  const int nrows = min(PP_ROWS, rows - row0);
+  const int img = blockIdx.y, row0 = blockIdx.x * rpc;
+  const int nrows = min(rpc, rows - row0);
   const int nbytes = in_w * 3;
   const int rstride = (nbytes + 16 + 15) & ~15;          // per-row shared-memory slot (16 bytes of alignment slack)
   const int obytes = out * 3;
   const int ostride = (obytes + 15) & ~15;
-  uint8_t* sout = pp_smem + PP_ROWS * rstride;
+  uint8_t* sout = pp_smem + rpc * rstride;
   for (int r = 0; r < nrows; ++r) {
     const uint8_t* row = src + (long long)img * image_stride + (long long)(row0 + r + row_first) * nbytes;
     const int mis = (int)(reinterpret_cast<uintptr_t>(row) & 15);   // shared offset congruent to the global address
@@ -198,10 +200,11 @@ __global__ void __launch_bounds__(256)
 resize_v_kernel(const uint8_t* __restrict__ src, long long image_stride, int width, int out_rows,
                 const int2* __restrict__ bounds, const int32_t* __restrict__ kk_t, uint8_t* __restrict__ dst8,
                 __half* __restrict__ dstf) {
-  const int yy = blockIdx.x, img = blockIdx.y;
+  const int img = blockIdx.y;
+  const int rowbytes = width * 3;
+  for (int yy = blockIdx.x * PP_VROWS; yy < min(out_rows, (blockIdx.x + 1) * PP_VROWS); ++yy) {
   const int2 b = bounds[yy];
   const uint8_t* base = src + (long long)img * image_stride + (long long)b.x * width * 3;
-  const int rowbytes = width * 3;
   if ((rowbytes & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 3) == 0) {
     // one thread per 32-bit word of the row: the vertical weights are the same for every byte of a row
     for (int j = threadIdx.x; j < (rowbytes >> 2); j += 256) {
@@ -227,7 +230,7 @@ resize_v_kernel(const uint8_t* __restrict__ src, long long image_stride, int wid
         *reinterpret_cast<uint32_t*>(dst8 + ((long long)img * out_rows + yy) * rowbytes + 4 * j) = o;
       }
     }
-    return;
+    continue;
   }
   for (int xx = threadIdx.x; xx < width; xx += 256) {
     int s0 = 1 << (PP_PRECISION_BITS - 1), s1 = s0, s2 = s0;
@@ -247,6 +250,7 @@ resize_v_kernel(const uint8_t* __restrict__ src, long long image_stride, int wid
       o[0] = pp_clip8(s0); o[1] = pp_clip8(s1); o[2] = pp_clip8(s2);
     }
   }
+  }
 }
 
 }  // namespace sb
@@ -259,7 +263,7 @@ int seedb200_preprocess_create(int in_h, int in_w, int out_size, int filter, int
   *out = nullptr;
   SB_REQUIRE(in_h > 0 && in_w > 0 && out_size > 0 && max_batch > 0, "preprocess_create: non-positive size");
   SB_REQUIRE(filter == 2 || filter == 3, "preprocess_create: filter %d (2 = PIL BILINEAR, 3 = PIL BICUBIC)", filter);
-  SB_REQUIRE((long long)sb::PP_ROWS * (in_w * 3 + 48 + out_size * 3) <= 200 * 1024, "preprocess_create: image width %d too large", in_w);
+  SB_REQUIRE((long long)(in_w * 3 + 48 + out_size * 3) + 64 <= 200 * 1024, "preprocess_create: image width %d too large", in_w);
   std::vector<int2> bh, bv;
   std::vector<int32_t> kh, kv;
   seedb200_preprocess* p = new seedb200_preprocess();
@@ -310,8 +314,11 @@ int seedb200_preprocess_run(seedb200_preprocess* p, const void* images_u8, int n
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint8_t* src = static_cast<const uint8_t*>(images_u8);
   __half* dst = static_cast<__half*>(out_f16);
-  const size_t smem = (size_t)PP_ROWS * (((size_t)p->in_w * 3 + 16 + 15) & ~(size_t)15) +
-                      (size_t)PP_ROWS * (((size_t)p->out * 3 + 15) & ~(size_t)15) + 64;   // + word over-read slack
+  const size_t row_slot = (((size_t)p->in_w * 3 + 16 + 15) & ~(size_t)15) + (((size_t)p->out * 3 + 15) & ~(size_t)15);
+  int rpc = (int)((200 * 1024 - 64) / row_slot);            // source rows per CTA that fit shared memory
+  if (rpc > PP_ROWS) rpc = PP_ROWS;
+  if (rpc < 1) rpc = 1;
+  const size_t smem = (size_t)rpc * row_slot + 64;          // + word over-read slack
   static size_t attr_smem[2] = {48 * 1024, 48 * 1024};
   if (smem > attr_smem[p->vertical_first]) {
     if (p->vertical_first)
@@ -322,17 +329,17 @@ int seedb200_preprocess_run(seedb200_preprocess* p, const void* images_u8, int n
   }
   const long long in_stride = (long long)p->in_h * p->in_w * 3;
   if (!p->vertical_first) {
-    resize_h_kernel<false><<<dim3((p->tmp_rows + PP_ROWS - 1) / PP_ROWS, n), 256, smem, st>>>(
-        src, in_stride, p->in_w, p->out, p->y_first, p->tmp_rows, p->bh, p->kh, p->tmp, nullptr);
+    resize_h_kernel<false><<<dim3((p->tmp_rows + rpc - 1) / rpc, n), 256, smem, st>>>(
+        src, in_stride, p->in_w, p->out, p->y_first, p->tmp_rows, rpc, p->bh, p->kh, p->tmp, nullptr);
     SB_LAUNCH_CHECK();
-    resize_v_kernel<true><<<dim3(p->out, n), 256, 0, st>>>(p->tmp, (long long)p->tmp_rows * p->out * 3, p->out, p->out,
+    resize_v_kernel<true><<<dim3((p->out + PP_VROWS - 1) / PP_VROWS, n), 256, 0, st>>>(p->tmp, (long long)p->tmp_rows * p->out * 3, p->out, p->out,
                                                            p->bv, p->kv, nullptr, dst);
     SB_LAUNCH_CHECK();
   } else {
-    resize_v_kernel<false><<<dim3(p->out, n), 256, 0, st>>>(src, in_stride, p->in_w, p->out, p->bv, p->kv, p->tmp, nullptr);
+    resize_v_kernel<false><<<dim3((p->out + PP_VROWS - 1) / PP_VROWS, n), 256, 0, st>>>(src, in_stride, p->in_w, p->out, p->bv, p->kv, p->tmp, nullptr);
     SB_LAUNCH_CHECK();
-    resize_h_kernel<true><<<dim3((p->out + PP_ROWS - 1) / PP_ROWS, n), 256, smem, st>>>(
-        p->tmp, (long long)p->out * p->in_w * 3, p->in_w, p->out, 0, p->out, p->bh, p->kh, nullptr, dst);
+    resize_h_kernel<true><<<dim3((p->out + rpc - 1) / rpc, n), 256, smem, st>>>(
+        p->tmp, (long long)p->out * p->in_w * 3, p->in_w, p->out, 0, p->out, rpc, p->bh, p->kh, nullptr, dst);
     SB_LAUNCH_CHECK();
   }
   return 0;
