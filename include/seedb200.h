@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SEEDB200_VERSION 100
+#define SEEDB200_VERSION 200
 
 enum seedb200_status {
   SEEDB200_OK = 0,
@@ -160,6 +160,49 @@ int seedb200_rope_kv_append(const void* qkv, const int64_t* positions, int B, in
 int seedb200_embedding(const void* table, int64_t ld, const int64_t* ids, int n, int cols,
                        void* out, int64_t ldo, int64_t n_rows, void* stream);
 
+/* y[m,:] = x[m,:] . W^T for M <= 4 activation rows: the batch-1 decode form of every nn.Linear of
+ * LlamaDecoderLayer (llama_xformer.py:186,223-225,258) and of lm_head (:718); HBM-bound, every weight byte read
+ * once.  x [M,K], W [N,K] (row stride ldw), out [M,N] fp16.  mode 0: plain (+ residual [M,N] when non-NULL);
+ * mode 1: W rows are blocks of [128 gate | 128 up] and out [M,N/2] = silu(gate) * up (llama_xformer.py:186).
+ * norm_w != NULL: x is RMS-normalised while it is staged (LlamaRMSNorm, llama_xformer.py:105-113, eps).        */
+int seedb200_gemv(const void* x, const void* W, int64_t ldw, void* out, const void* residual, const void* norm_w,
+                  float eps, int M, int N, int K, int mode, void* stream);
+
+/* LlamaAttention.forward with q_len == 1 (llama_xformer.py:240-256, attn_bias=None): q [B,H,D] against the first
+ * kv_len rows of caches laid out [B,H,max_seq,D]; out [B,H*D] fp16; D must be 128.  workspace: at least
+ * seedb200_decode_attention_workspace_bytes(B, H, max_seq) bytes of device memory (split-KV partials).          */
+int64_t seedb200_decode_attention_workspace_bytes(int B, int H, int max_seq);
+int seedb200_decode_attention(const void* q, const void* k_cache, const void* v_cache, void* out, int B, int H, int D,
+                              int kv_len, int max_seq, float scale, void* workspace, void* stream);
+
+/* Next-token selection, on the device.  Replaces what the reference gets from HF GenerationMixin at its call
+ * site scripts/seed_llama_inference_8B.py:33 / gradio_demo/seed_llama_flask.py:172 (temperature, top_p,
+ * do_sample, num_beams=1): logits / temperature (TemperatureLogitsWarper), nucleus filtering (TopPLogitsWarper,
+ * min_tokens_to_keep = 1), softmax, one multinomial draw; do_sample = 0 is argmax with ties to the lowest id
+ * (torch.argmax).  The draw for (sequence b, step t) uses one Philox4x32-10 uniform with key = seed and counter
+ * (offset + t, b), inverting the CDF of the kept tokens in index order -- reproducible, and independent of how
+ * the steps are batched or replayed.  Sampled ids are not comparable with torch's RNG stream; logits are the
+ * parity contract, the sampler is checked against its own restatement (oracle/sampler_oracle.py). */
+typedef struct seedb200_sample_params {
+  int32_t do_sample;
+  float temperature;
+  float top_p;
+  uint64_t seed;
+  uint64_t offset;
+} seedb200_sample_params;
+/* logits [B, ld] fp16 (first V columns valid) -> tokens_out [B] int64. */
+int seedb200_sample(const void* logits, int64_t ld, int B, int V, const seedb200_sample_params* sp, uint64_t step,
+                    int64_t* tokens_out, void* stream);
+/* the uniform in (0,1] the sampler draws for (seed, offset + step, row) -- host function, for tests */
+float seedb200_philox_uniform(uint64_t seed, uint64_t offset, uint32_t row);
+
+/* Codebook ids -> LLaMA token ids without the '<img_%05d>' string round trip of
+ * scripts/seed_llama_inference_8B.py:16-23,60,98-100 and gradio_demo/seed_llama_flask.py:144-150:
+ * ids [n,32] int64 -> tokens_out[i*out_stride + 0..33] = boi, image_id_shift + id (x32), eoi.  out_stride >= 34
+ * lets the spans land directly inside a prompt buffer.                                                         */
+int seedb200_image_ids_to_tokens(const int64_t* ids, int n, int64_t image_id_shift, int64_t boi, int64_t eoi,
+                                 int64_t* tokens_out, int64_t out_stride, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* Image tokenizer: Blip2QformerQuantizer (qformer_quantizer.py:143-338)       */
 /* ------------------------------------------------------------------------- */
@@ -189,6 +232,11 @@ int seedb200_encoder_encode(seedb200_encoder* enc, const void* images, int B, in
 /* Same, with pinned HOST buffers; copies ride the same stream (bench e2e).     */
 int seedb200_encoder_encode_host(seedb200_encoder* enc, const void* images_host, int B,
                                  int64_t* ids_host, void* stream);
+/* encode fused with the id -> token arithmetic of seedb200_image_ids_to_tokens: images [B,3,224,224] fp16 ->
+ * tokens_out[i*out_stride + 0..33] = boi, image_id_shift + id (x32), eoi, ready to be spliced into a LLaMA prompt
+ * (scripts/seed_llama_inference_8B.py:98-100) without leaving the device.  ids_out [B,32] optional.            */
+int seedb200_encoder_encode_tokens(seedb200_encoder* enc, const void* images, int B, int64_t image_id_shift, int64_t boi,
+                                   int64_t eoi, int64_t* tokens_out, int64_t out_stride, int64_t* ids_out, void* stream);
 /* Blip2QformerQuantizer.get_codebook_entry (qformer_quantizer.py:309-338):
  * ids [B,32] int64 -> image_embeds [B,1024] fp16.                              */
 int seedb200_encoder_detokenize(seedb200_encoder* enc, const int64_t* ids, int B, void* embeds_out,
@@ -226,6 +274,27 @@ void seedb200_llama_destroy(seedb200_llama* llm);
 int seedb200_llama_forward(seedb200_llama* llm, const int64_t* input_ids, const void* inputs_embeds,
                            const int64_t* position_ids, int B, int S, int past_len, int logits_mode,
                            void* logits_out, void* stream);
+/* Same with an explicit row stride for the logits (elements, >= vocab): a stride that is a multiple of 8 lets
+ * the lm_head epilogue use 16-byte stores when vocab (40194) is not; the caller views [..., :vocab].           */
+int seedb200_llama_forward_ld(seedb200_llama* llm, const int64_t* input_ids, const void* inputs_embeds,
+                              const int64_t* position_ids, int B, int S, int past_len, int logits_mode,
+                              void* logits_out, int64_t logits_ld, void* stream);
+
+/* The generation loop of scripts/seed_llama_inference_8B.py:26-38 (model.generate -> HF sample / greedy_search with
+ * llama_xformer.py:745-776 prepare_inputs_for_generation) as ONE call that never leaves the device: prefill of
+ * prompt_ids [B,S] (device int64, cache reset), then max_new_tokens x (sampler -> cached q_len-1 forward).  The
+ * cache position and the step counter live in device memory, so the decode step is position independent: it is
+ * captured once per batch size into a CUDA graph (use_graph != 0) and replayed; use_graph == 0 enqueues the same
+ * launches eagerly.  Sequences that emitted eos_id (>= 0) produce pad_id afterwards (HF semantics).  With an
+ * eos_id the call synchronises the stream every 32 steps to stop early once every sequence has finished;
+ * without one it only enqueues.  tokens_out [B, max_new_tokens] int64 (device); *n_generated_host (may be NULL)
+ * receives the number of valid columns.  Returns an error when B > 4 (the decode step uses the <= 4-row GEMV). */
+int seedb200_llama_generate(seedb200_llama* llm, const int64_t* prompt_ids, int B, int S, int max_new_tokens,
+                            const seedb200_sample_params* sp, int64_t eos_id, int64_t pad_id, int use_graph,
+                            int64_t* tokens_out, int* n_generated_host, void* stream);
+/* 1 when the last generate() replayed a captured graph, 0 when it ran eagerly, -1 before any call */
+int seedb200_llama_generate_used_graph(seedb200_llama* llm);
+
 /* Views of the KV cache of one layer: [max_batch, heads, max_seq, head_dim]
  * fp16; the first past_len+S rows per (batch, head) are valid.  Used to build
  * the past_key_values tuple the reference returns (llama_xformer.py:239).      */
@@ -250,6 +319,12 @@ int64_t seedb200_llama_tap(seedb200_llama* llm, int what, void* dst, int64_t max
 typedef struct seedb200_preprocess seedb200_preprocess;
 int seedb200_preprocess_create(int in_h, int in_w, int out_size, int filter, int max_batch,
                                seedb200_preprocess** out);
+/* keep_ratio=True of models/transforms.py:6-9 (the reference default): Resize(S) [shorter side -> S, the other
+ * int(S * long / short)] -> CenterCrop(S).  The caller passes the resize size and the crop origin exactly as
+ * torchvision computes them; only the crop window of the resample is evaluated.  create() is create_ex() with
+ * resize = out_size x out_size and no crop.                                                                     */
+int seedb200_preprocess_create_ex(int in_h, int in_w, int resize_h, int resize_w, int crop_top, int crop_left,
+                                  int out_size, int filter, int max_batch, seedb200_preprocess** out);
 void seedb200_preprocess_destroy(seedb200_preprocess* plan);
 int seedb200_preprocess_run(seedb200_preprocess* plan, const void* images_u8, int n, void* out_f16, void* stream);
 

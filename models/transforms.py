@@ -1,7 +1,7 @@
 """`models.transforms.get_transform` -- the hydra target of configs/transform/clip_transform.yaml
 (reference models/transforms.py:4-19).  Same contract: a callable PIL image -> float32 [3, S, S] tensor, resized
 (optionally aspect preserving + centre crop) and normalised with the CLIP statistics.  `get_gpu_transform` is the
-device-side twin for the `keep_ratio=False` case (bit-identical output, seed_b200/csrc/preprocess.cu)."""
+device-side twin (both `keep_ratio` settings, bit-identical output, seed_b200/csrc/preprocess.cu)."""
 from torchvision import transforms as _T
 
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
@@ -29,11 +29,12 @@ def get_transform(type="clip", keep_ratio=True, image_size=224):
     return builder(image_size, keep_ratio)
 
 
-def get_gpu_transform(type="clip", keep_ratio=False, image_size=224, device="cuda"):
+def get_gpu_transform(type="clip", keep_ratio=True, image_size=224, device="cuda", **kwargs):
     """PIL image(s) / uint8 HWC arrays -> fp16 [n, 3, S, S] on `device`, equal bit for bit to
-    `get_transform(type, False, image_size)(img).half()` (Pillow bilinear resize + ToTensor + Normalize)."""
-    if type != "clip" or keep_ratio:
-        raise NotImplementedError("the GPU twin covers type='clip', keep_ratio=False (configs/transform/clip_transform.yaml)")
+    `get_transform(type, keep_ratio, image_size)(img).half()` (Pillow bilinear resize [+ centre crop] + ToTensor +
+    Normalize); same defaults as get_transform (reference models/transforms.py:4: keep_ratio=True)."""
+    if type != "clip":
+        raise NotImplementedError
     from seed_b200.preprocess import GpuClipTransform
 
-    return GpuClipTransform(image_size, "bilinear", device=device)
+    return GpuClipTransform(image_size, "bilinear", device=device, keep_ratio=keep_ratio, **kwargs)

@@ -301,7 +301,8 @@ static int launch_attn(const seedb200_attn_desc& d, cudaStream_t stream) {
   constexpr int BQ = NW * 16, LDS = DPAD + 8;
   constexpr int smem = (BQ + 4 * ATT_BK) * LDS * 2;
   auto kern = attn_fwd_kernel<DPAD, NW>;
-  static bool attr_set = false;
+  static bool attr_set_dev[SB_MAX_DEVICES] = {};   // cudaFuncSetAttribute is per device
+  bool& attr_set = attr_set_dev[cur_device()];
   if (!attr_set) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     // ask for the full shared-memory carve-out so that two CTAs of the 83 KB ViT tile are co-resident

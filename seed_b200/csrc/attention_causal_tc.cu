@@ -375,7 +375,8 @@ bool causal_attention_tc_applicable(const seedb200_attn_desc& d) {
 }
 
 int causal_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_set_dev[SB_MAX_DEVICES] = {};   // cudaFuncSetAttribute is per device
+  bool& attr_set = attr_set_dev[cur_device()];
   if (!attr_set) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(causal_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CA_SMEM));
     attr_set = true;

@@ -507,7 +507,8 @@ bool vit_attention_tc_applicable(const seedb200_attn_desc& d) {
 }
 
 int vit_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_set_dev[SB_MAX_DEVICES] = {};   // cudaFuncSetAttribute is per device
+  bool& attr_set = attr_set_dev[cur_device()];
   if (!attr_set) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VA_SMEM));
     attr_set = true;

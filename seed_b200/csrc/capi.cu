@@ -69,13 +69,18 @@ static thread_local bool g_pdl_scope = false;
 bool pdl_scope_active() { return g_pdl_scope; }
 void pdl_scope_set(bool on) { g_pdl_scope = on; }
 
+int cur_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= SB_MAX_DEVICES) dev = 0;
+  return dev;
+}
+
 int num_sms() {
-  static int sms = 0;
+  static int sms_dev[SB_MAX_DEVICES] = {};
+  const int dev = cur_device();
+  int& sms = sms_dev[dev];
   if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-        sms <= 0)
-      sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
   return sms;
 }
@@ -102,6 +107,8 @@ int get_rope_tables(int D, float base, int min_pos, const void** cos_t, const vo
   SB_CHECK_CUDA(cudaMalloc(&t.cos_t, (size_t)n * (D / 2) * 2));
   SB_CHECK_CUDA(cudaMalloc(&t.sin_t, (size_t)n * (D / 2) * 2));
   SB_PROPAGATE(build_rope_tables(t.cos_t, t.sin_t, n, D, base, stream));
+  // later callers may use the table from other streams: publish it only once the build has finished
+  SB_CHECK_CUDA(cudaStreamSynchronize(stream));
   g_rope_cache[key] = t;   // an older, smaller table (if any) stays alive: in-flight kernels may still read it
   *cos_t = t.cos_t; *sin_t = t.sin_t; *max_pos = n;
   return 0;

@@ -51,7 +51,19 @@ void count_launch(int n = 1);
     if (_s != 0) return _s;                                                              \
   } while (0)
 
-int num_sms();
+constexpr int SB_MAX_DEVICES = 64;
+int cur_device();     // cudaGetDevice(), clamped to [0, SB_MAX_DEVICES)
+int num_sms();        // of the current device
+// A handle lives on the device that was current at *_create; every handle-level entry point runs under this guard,
+// so a caller whose current device differs (reference pattern: tokenizer_device != llm_device in one process,
+// gradio_demo/seed_llama_flask.py:51-52,69,78) still launches next to the handle's weights and workspace.
+struct DeviceGuard {
+  int prev; bool switched;
+  explicit DeviceGuard(int dev) : prev(0), switched(false) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 // Programmatic dependent launch (decode chain): a kernel launched through launch_chain() while a PdlScope is active
 // may start while its predecessor is still running; it must execute pdl_wait() before touching anything the

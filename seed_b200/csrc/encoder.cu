@@ -66,6 +66,7 @@ struct seedb200_encoder {
   int64_t* ids_buf;
   __half* img_in;                  // staging for the host entry point
   int last_B;
+  int device;                      // the device that was current at create (weights + workspace live there)
 };
 
 namespace sb {
@@ -447,6 +448,7 @@ int seedb200_encoder_create(const seedb200_encoder_config* cfg, const seedb200_t
   seedb200_encoder* e = new seedb200_encoder();
   e->cfg = *cfg;
   e->last_B = 0;
+  e->device = sb::cur_device();
   for (int i = 0; i < n_weights; ++i) e->w[std::string(weights[i].name)] = weights[i];
   int s = sb::build(e);
   if (s != 0) {
@@ -468,6 +470,7 @@ int seedb200_encoder_encode(seedb200_encoder* enc, const void* images, int B, in
                             void* query_up_out, void* stream) {
   SB_REQUIRE(enc && images && ids, "encoder_encode: null argument");
   SB_REQUIRE(B >= 1, "encoder_encode: empty batch");
+  sb::DeviceGuard guard(enc->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int mb = enc->cfg.max_batch;
   for (int b0 = 0; b0 < B; b0 += mb) {
@@ -484,6 +487,7 @@ int seedb200_encoder_encode_host(seedb200_encoder* enc, const void* images_host,
                                  void* stream) {
   SB_REQUIRE(enc && images_host && ids_host, "encoder_encode_host: null argument");
   SB_REQUIRE(B >= 1, "encoder_encode_host: empty batch");
+  sb::DeviceGuard guard(enc->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int mb = enc->cfg.max_batch;
   const size_t img_elems = (size_t)3 * 224 * 224;
@@ -498,10 +502,29 @@ int seedb200_encoder_encode_host(seedb200_encoder* enc, const void* images_host,
   return 0;
 }
 
+int seedb200_encoder_encode_tokens(seedb200_encoder* enc, const void* images, int B, int64_t image_id_shift, int64_t boi,
+                                   int64_t eoi, int64_t* tokens_out, int64_t out_stride, int64_t* ids_out, void* stream) {
+  SB_REQUIRE(enc && images && tokens_out, "encoder_encode_tokens: null argument");
+  SB_REQUIRE(B >= 1 && out_stride >= 34, "encoder_encode_tokens: bad sizes");
+  sb::DeviceGuard guard(enc->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int mb = enc->cfg.max_batch;
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int nb = (B - b0) < mb ? (B - b0) : mb;
+    const __half* img = static_cast<const __half*>(images) + (size_t)b0 * 3 * 224 * 224;
+    int64_t* ids = ids_out ? ids_out + (size_t)b0 * sb::QF_NQ : enc->ids_buf;
+    SB_PROPAGATE(sb::encode_chunk(enc, img, nb, ids, nullptr, nullptr, st));
+    SB_PROPAGATE(sb::image_ids_to_tokens(ids, nb, image_id_shift, boi, eoi, tokens_out + (size_t)b0 * out_stride,
+                                         out_stride, st));
+  }
+  return 0;
+}
+
 int seedb200_encoder_detokenize(seedb200_encoder* enc, const int64_t* ids, int B, void* embeds_out, void* stream) {
   SB_REQUIRE(enc && ids && embeds_out, "encoder_detokenize: null argument");
   SB_REQUIRE(enc->cfg.detok_depth > 0 || enc->down0 != nullptr, "encoder_detokenize: handle was created without the de-tokenizer head");
   SB_REQUIRE(B >= 1, "encoder_detokenize: empty batch");
+  sb::DeviceGuard guard(enc->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int mb = enc->cfg.max_batch;
   for (int b0 = 0; b0 < B; b0 += mb) {
@@ -514,6 +537,7 @@ int seedb200_encoder_detokenize(seedb200_encoder* enc, const int64_t* ids, int B
 
 int64_t seedb200_encoder_tap(seedb200_encoder* enc, int what, void* dst, int64_t max_elems, void* stream) {
   if (!enc || !dst || enc->last_B <= 0) return -1;
+  sb::DeviceGuard guard(enc->device);
   const __half* src = nullptr;
   int64_t n = 0;
   if (what == 0) { src = enc->x; n = (int64_t)enc->last_B * sb::VIT_TOK * sb::VIT_D; }

@@ -459,7 +459,8 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t col
 template <int BN, int CTAS, int MODE, int KSUB>
 static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CTAS, KSUB>;
-  static bool attr_set = false;
+  static bool attr_set_dev[SB_MAX_DEVICES] = {};   // cudaFuncSetAttribute is per device
+  bool& attr_set = attr_set_dev[cur_device()];
   auto kern = gemm_tcgen05_kernel<BN, CTAS, MODE, KSUB>;
   if (!attr_set) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_REQUEST));

@@ -39,6 +39,20 @@ struct seedb200_llama {
   __half *x, *nb, *qkv, *q, *att, *gu, *hn, *last;
   float* da_ws;
   int last_T;
+  int device;
+  // ---- device-resident generation loop (seedb200_llama_generate) ----
+  int vpad;                       // logits row stride: vocab rounded up to a multiple of 8
+  int* gstate;                    // {cache length, step, arrive counter, valid steps, any-unfinished flag}
+  int* gfinished;                 // [max_batch]
+  int64_t* gtok;                  // [max_batch] token fed to the next decode forward
+  int64_t* gout;                  // [max_batch, max_seq] generated tokens
+  __half* glogits;                // [max_batch, vpad]
+  sb::GenParams* gparams;         // sampling parameters + eos/pad, read by the sampler at run time
+  int* gstate_host;               // pinned mirror of gstate (early-stop polling)
+  cudaGraphExec_t gexec[5];       // decode-step graph per batch size (1..4)
+  int gunit_launches[5];          // kernels inside one captured unit (launch accounting of graph replays)
+  int used_graph;
+  int gen_cache_len;
 };
 
 namespace sb {
@@ -121,6 +135,14 @@ static int llama_build(seedb200_llama* m) {
   SB_PROPAGATE(llama_alloc(m, &m->hn, T * h));
   SB_PROPAGATE(llama_alloc(m, &m->last, (size_t)c.max_batch * h));
   SB_PROPAGATE(llama_alloc(m, &m->da_ws, (size_t)c.max_batch * c.heads * 64 * (128 + 2)));
+  m->vpad = (c.vocab + 7) / 8 * 8;
+  SB_PROPAGATE(llama_alloc(m, &m->gstate, 8));
+  SB_PROPAGATE(llama_alloc(m, &m->gfinished, (size_t)c.max_batch));
+  SB_PROPAGATE(llama_alloc(m, &m->gtok, (size_t)c.max_batch));
+  SB_PROPAGATE(llama_alloc(m, &m->gout, (size_t)c.max_batch * c.max_seq));
+  SB_PROPAGATE(llama_alloc(m, &m->glogits, (size_t)c.max_batch * m->vpad));
+  SB_PROPAGATE(llama_alloc(m, &m->gparams, 1));
+  SB_CHECK_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->gstate_host), 8 * sizeof(int)));
   SB_CHECK_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
@@ -130,7 +152,7 @@ int get_option(const char* key);
 static int lin(cudaStream_t st, int ctas, int M, int N, int K, const void* A, const void* W, void* out, int64_t ldo,
                const void* residual, int mode, const void* norm_w = nullptr, float eps = 0.0f) {
   // norm_w: only on the M <= 4 (decode) path, where the GEMV normalises its activations while staging them
-  if (M <= 4) return gemv(A, W, K, out, residual, norm_w, eps, M, N, K, mode, st);
+  if (M <= 4) return gemv(A, W, K, out, residual, norm_w, eps, M, N, K, mode, st, ldo);
   seedb200_gemm_desc d;
   memset(&d, 0, sizeof(d));
   d.M = M; d.N = N; d.K = K; d.A = A; d.lda = K; d.W = W; d.ldw = K;
@@ -138,9 +160,11 @@ static int lin(cudaStream_t st, int ctas, int M, int N, int K, const void* A, co
   return gemm(d, st);
 }
 
+// dyn (device, optional): {cache length, ...} read by the RoPE/append and decode-attention kernels instead of the
+// host value `past_len` -- what makes a captured decode step position independent (S must be 1).
 static int llama_forward(seedb200_llama* m, const int64_t* input_ids, const void* inputs_embeds,
                          const int64_t* position_ids, int B, int S, int past_len, int logits_mode, void* logits,
-                         cudaStream_t st) {
+                         int64_t logits_ld, cudaStream_t st, const int* dyn = nullptr) {
   const seedb200_llama_config& c = m->cfg;
   const int h = c.hidden, H = c.heads, D = c.head_dim, ffn = c.ffn, V = c.vocab, ct = c.gemm_ctas;
   const int T = B * S;
@@ -162,9 +186,9 @@ static int llama_forward(seedb200_llama* m, const int64_t* input_ids, const void
     }
     // qkv rows are [q | k | v] per token, each [H, D]
     SB_PROPAGATE(rope_kv_append_tables(m->qkv, position_ids, B, S, H, D, past_len, c.max_seq, m->max_pos, m->cos_t,
-                                       m->sin_t, m->q, L.k_cache, L.v_cache, st));
+                                       m->sin_t, m->q, L.k_cache, L.v_cache, st, dyn));
     if (S == 1) {
-      SB_PROPAGATE(decode_attention(m->q, L.k_cache, L.v_cache, m->att, B, H, D, kv_len, c.max_seq, scale, m->da_ws, st));
+      SB_PROPAGATE(decode_attention(m->q, L.k_cache, L.v_cache, m->att, B, H, D, kv_len, c.max_seq, scale, m->da_ws, st, dyn));
     } else {
       seedb200_attn_desc a;
       memset(&a, 0, sizeof(a));
@@ -189,7 +213,7 @@ static int llama_forward(seedb200_llama* m, const int64_t* input_ids, const void
   m->last_T = T;
   if (logits == nullptr) return 0;
   if (logits_mode == 0) {
-    SB_PROPAGATE(lin(st, ct, T, V, h, m->hn, m->lm_head, logits, V, nullptr, 0));
+    SB_PROPAGATE(lin(st, ct, T, V, h, m->hn, m->lm_head, logits, logits_ld, nullptr, 0));
   } else {
     const __half* src = m->hn;
     if (S > 1) {   // gather the last position of every sequence
@@ -197,8 +221,126 @@ static int llama_forward(seedb200_llama* m, const int64_t* input_ids, const void
                                       (size_t)h * 2, B, cudaMemcpyDeviceToDevice, st));
       src = m->last;
     }
-    SB_PROPAGATE(lin(st, ct, B, V, h, src, m->lm_head, logits, V, nullptr, 0));
+    SB_PROPAGATE(lin(st, ct, B, V, h, src, m->lm_head, logits, logits_ld, nullptr, 0));
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// generation loop on the device (scripts/seed_llama_inference_8B.py:26-38 -> HF sample/greedy_search +
+// llama_xformer.py:745-776): prefill, then max_new_tokens x (sampler -> cached decode forward).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void gen_reset_kernel(GenParams gp, GenParams* dst, int* state, int* finished, int past_len, int B) {
+  if (threadIdx.x == 0) {
+    *dst = gp;
+    state[0] = past_len; state[1] = 0; state[2] = 0; state[3] = 0; state[4] = 0;
+  }
+  if (threadIdx.x < B) finished[threadIdx.x] = 0;
+}
+
+// one unit of the loop: cached forward of the tokens in m->gtok, then the sampler (which also advances the device
+// counters).  Every launch argument is a handle-owned pointer or a constant: the unit can be captured once.
+static int gen_unit(seedb200_llama* m, int B, cudaStream_t st) {
+  PdlScope pdl(get_option("decode_pdl") != 0);
+  SB_PROPAGATE(llama_forward(m, m->gtok, nullptr, nullptr, B, 1, 0, 1, m->glogits, m->vpad, st, m->gstate));
+  SB_PROPAGATE(sample(m->glogits, m->vpad, B, m->cfg.vocab, nullptr, m->gparams, 0, m->gstate, /*advance_cache=*/1,
+                      m->gtok, m->gout, m->cfg.max_seq, m->gfinished, st));
+  return 0;
+}
+
+static int gen_capture(seedb200_llama* m, int B, cudaStream_t st) {
+  cudaGraph_t graph = nullptr;
+  SB_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int64_t before = seedb200_launch_count();
+  const int s = gen_unit(m, B, st);
+  const int unit = (int)(seedb200_launch_count() - before);
+  count_launch(-unit);                        // captured, not executed
+  const cudaError_t e = cudaStreamEndCapture(st, &graph);
+  if (s != 0) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return s;
+  }
+  if (e != cudaSuccess || graph == nullptr) {
+    set_error("llama_generate: stream capture of the decode step failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return SEEDB200_ERR_CUDA;
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ei != cudaSuccess) {
+    set_error("llama_generate: cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+    cudaGetLastError();
+    return SEEDB200_ERR_CUDA;
+  }
+  m->gexec[B] = exec;
+  m->gunit_launches[B] = unit;
+  return 0;
+}
+
+static int llama_generate(seedb200_llama* m, const int64_t* prompt_ids, int B, int S, int max_new,
+                          const seedb200_sample_params* sp, int64_t eos, int64_t pad, int use_graph,
+                          int64_t* tokens_out, int* n_generated_host, cudaStream_t st) {
+  const seedb200_llama_config& c = m->cfg;
+  GenParams gp;
+  gp.sp = *sp; gp.eos = eos; gp.pad = pad;
+  gen_reset_kernel<<<1, 32, 0, st>>>(gp, m->gparams, m->gstate, m->gfinished, S, B);
+  SB_LAUNCH_CHECK();
+  // prefill: cache rows [0, S), logits of the last position only (what the sampler needs)
+  SB_PROPAGATE(llama_forward(m, prompt_ids, nullptr, nullptr, B, S, 0, 1, m->glogits, m->vpad, st));
+  // token 0 comes from the prefill logits: the step counter advances, the cache length does not
+  SB_PROPAGATE(sample(m->glogits, m->vpad, B, c.vocab, nullptr, m->gparams, 0, m->gstate, /*advance_cache=*/0, m->gtok,
+                      m->gout, c.max_seq, m->gfinished, st));
+  int units = max_new - 1, done = 0;
+  m->used_graph = 0;
+  auto all_finished = [&](bool* stop) -> int {   // early stop: poll the device counters (only with an eos id)
+    SB_CHECK_CUDA(cudaMemcpyAsync(m->gstate_host, m->gstate, 5 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    SB_CHECK_CUDA(cudaStreamSynchronize(st));
+    *stop = m->gstate_host[3] < m->gstate_host[1];      // a step ran with every sequence already finished
+    return 0;
+  };
+  if (units > 0) {   // first unit eagerly (also resolves every lazily-set function attribute before a capture)
+    SB_PROPAGATE(gen_unit(m, B, st));
+    done = 1;
+  }
+  if (units > done && use_graph) {
+    if (m->gexec[B] == nullptr) {
+      int s = gen_capture(m, B, st);
+      if (s != 0 && get_option("decode_pdl") != 0) {   // retry without programmatic launches inside the graph
+        seedb200_set_option("decode_pdl", 0);
+        s = gen_capture(m, B, st);
+        seedb200_set_option("decode_pdl", 1);
+      }
+      if (s != 0) return s;
+    }
+    m->used_graph = 1;
+  }
+  bool stop = false;
+  while (done < units && !stop) {
+    int chunk = units - done;
+    if (eos >= 0 && chunk > 32) chunk = 32;
+    for (int i = 0; i < chunk; ++i) {
+      if (m->used_graph) {
+        SB_CHECK_CUDA(cudaGraphLaunch(m->gexec[B], st));
+        count_launch(m->gunit_launches[B]);
+      } else {
+        SB_PROPAGATE(gen_unit(m, B, st));
+      }
+    }
+    done += chunk;
+    if (eos >= 0 && done < units) SB_PROPAGATE(all_finished(&stop));
+  }
+  int n_valid = done + 1;
+  if (eos >= 0) {
+    SB_PROPAGATE(all_finished(&stop));
+    n_valid = m->gstate_host[3];
+  }
+  if (tokens_out != nullptr)
+    SB_CHECK_CUDA(cudaMemcpy2DAsync(tokens_out, (size_t)max_new * 8, m->gout, (size_t)c.max_seq * 8, (size_t)n_valid * 8, B,
+                                    cudaMemcpyDeviceToDevice, st));
+  if (n_generated_host != nullptr) *n_generated_host = n_valid;
+  m->gen_cache_len = S + done;     // tokens whose K/V are in the cache
   return 0;
 }
 
@@ -222,6 +364,11 @@ int seedb200_llama_create(const seedb200_llama_config* cfg, const seedb200_tenso
   if (m->cfg.rope_base <= 0.0f) m->cfg.rope_base = 10000.0f;
   if (m->cfg.rms_eps <= 0.0f) m->cfg.rms_eps = 1e-6f;
   m->last_T = 0;
+  m->device = sb::cur_device();
+  m->gstate_host = nullptr;
+  m->used_graph = -1;
+  m->gen_cache_len = 0;
+  for (int i = 0; i < 5; ++i) { m->gexec[i] = nullptr; m->gunit_launches[i] = 0; }
   for (int i = 0; i < n_weights; ++i) m->w[std::string(weights[i].name)] = weights[i];
   int s = sb::llama_build(m);
   if (s != 0) {
@@ -235,13 +382,16 @@ int seedb200_llama_create(const seedb200_llama_config* cfg, const seedb200_tenso
 
 void seedb200_llama_destroy(seedb200_llama* llm) {
   if (!llm) return;
+  for (int i = 0; i < 5; ++i)
+    if (llm->gexec[i]) cudaGraphExecDestroy(llm->gexec[i]);
+  if (llm->gstate_host) cudaFreeHost(llm->gstate_host);
   for (void* p : llm->owned) cudaFree(p);
   delete llm;
 }
 
-int seedb200_llama_forward(seedb200_llama* llm, const int64_t* input_ids, const void* inputs_embeds,
-                           const int64_t* position_ids, int B, int S, int past_len, int logits_mode, void* logits_out,
-                           void* stream) {
+int seedb200_llama_forward_ld(seedb200_llama* llm, const int64_t* input_ids, const void* inputs_embeds,
+                              const int64_t* position_ids, int B, int S, int past_len, int logits_mode,
+                              void* logits_out, int64_t logits_ld, void* stream) {
   SB_REQUIRE(llm != nullptr, "llama_forward: null handle");
   SB_REQUIRE((input_ids != nullptr) != (inputs_embeds != nullptr),
              "llama_forward: specify exactly one of input_ids / inputs_embeds (llama_xformer.py:516-523)");
@@ -249,9 +399,35 @@ int seedb200_llama_forward(seedb200_llama* llm, const int64_t* input_ids, const 
   SB_REQUIRE(S >= 1 && past_len >= 0 && past_len + S <= llm->cfg.max_seq,
              "llama_forward: past_len %d + S %d exceeds max_seq %d", past_len, S, llm->cfg.max_seq);
   SB_REQUIRE(logits_mode == 0 || logits_mode == 1, "llama_forward: logits_mode must be 0 or 1");
+  SB_REQUIRE(logits_out == nullptr || logits_ld >= llm->cfg.vocab, "llama_forward: logits_ld %lld < vocab %d",
+             (long long)logits_ld, llm->cfg.vocab);
+  sb::DeviceGuard guard(llm->device);
   return sb::llama_forward(llm, input_ids, inputs_embeds, position_ids, B, S, past_len, logits_mode, logits_out,
-                           static_cast<cudaStream_t>(stream));
+                           logits_ld, static_cast<cudaStream_t>(stream));
 }
+
+int seedb200_llama_forward(seedb200_llama* llm, const int64_t* input_ids, const void* inputs_embeds,
+                           const int64_t* position_ids, int B, int S, int past_len, int logits_mode, void* logits_out,
+                           void* stream) {
+  return seedb200_llama_forward_ld(llm, input_ids, inputs_embeds, position_ids, B, S, past_len, logits_mode, logits_out,
+                                   llm ? llm->cfg.vocab : 0, stream);
+}
+
+int seedb200_llama_generate(seedb200_llama* llm, const int64_t* prompt_ids, int B, int S, int max_new_tokens,
+                            const seedb200_sample_params* sp, int64_t eos_id, int64_t pad_id, int use_graph,
+                            int64_t* tokens_out, int* n_generated_host, void* stream) {
+  SB_REQUIRE(llm && prompt_ids && sp, "llama_generate: null argument");
+  SB_REQUIRE(B >= 1 && B <= llm->cfg.max_batch && B <= 4, "llama_generate: batch %d outside [1,%d] (decode GEMV: <= 4 rows)",
+             B, llm->cfg.max_batch < 4 ? llm->cfg.max_batch : 4);
+  SB_REQUIRE(S >= 1 && max_new_tokens >= 1 && S + max_new_tokens <= llm->cfg.max_seq,
+             "llama_generate: prompt %d + %d new tokens exceeds max_seq %d", S, max_new_tokens, llm->cfg.max_seq);
+  SB_REQUIRE(!sp->do_sample || (sp->temperature > 0.0f && sp->top_p > 0.0f), "llama_generate: temperature and top_p must be > 0");
+  sb::DeviceGuard guard(llm->device);
+  return sb::llama_generate(llm, prompt_ids, B, S, max_new_tokens, sp, eos_id, pad_id, use_graph, tokens_out,
+                            n_generated_host, static_cast<cudaStream_t>(stream));
+}
+
+int seedb200_llama_generate_used_graph(seedb200_llama* llm) { return llm ? llm->used_graph : -1; }
 
 int seedb200_llama_kv_ptrs(seedb200_llama* llm, int layer, void** k, void** v) {
   SB_REQUIRE(llm && k && v && layer >= 0 && layer < (int)llm->layers.size(), "llama_kv_ptrs: bad arguments");
@@ -265,6 +441,7 @@ int seedb200_llama_kv_load(seedb200_llama* llm, int layer, const void* k, const 
   SB_REQUIRE(llm && k && v && layer >= 0 && layer < (int)llm->layers.size(), "llama_kv_load: bad arguments");
   SB_REQUIRE(B >= 1 && B <= llm->cfg.max_batch && past_len >= 0 && past_len <= llm->cfg.max_seq, "llama_kv_load: bad sizes");
   if (past_len == 0) return 0;
+  sb::DeviceGuard guard(llm->device);
   const size_t D = llm->cfg.head_dim, H = llm->cfg.heads;
   const size_t w = (size_t)past_len * D * 2, dp = (size_t)llm->cfg.max_seq * D * 2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -276,6 +453,7 @@ int seedb200_llama_kv_load(seedb200_llama* llm, int layer, const void* k, const 
 
 int64_t seedb200_llama_tap(seedb200_llama* llm, int what, void* dst, int64_t max_elems, void* stream) {
   if (!llm || !dst || llm->last_T <= 0 || what != 0) return -1;
+  sb::DeviceGuard guard(llm->device);
   int64_t n = (int64_t)llm->last_T * llm->cfg.hidden;
   if (n > max_elems) n = max_elems;
   if (cudaMemcpyAsync(dst, llm->hn, (size_t)n * 2, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)) != cudaSuccess)

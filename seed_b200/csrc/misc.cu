@@ -58,7 +58,7 @@ template <int M, int MODE, bool NORM>
 __global__ void __launch_bounds__(256)
 gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long long ldw, __half* __restrict__ out,
             const __half* __restrict__ residual, const __half* __restrict__ norm_w, float eps, int N, int K,
-            int ksplit, int iters) {
+            int ksplit, int iters, long long ldo) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint4* xs = reinterpret_cast<uint4*>(smem_raw);     // [M][K/8]
   __shared__ float red[8];
@@ -193,15 +193,15 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
           const float g = __half2float(__float2half_rn(a0[m]));
           const float u = __half2float(__float2half_rn(a1[m]));
           const float s = __half2float(__float2half_rn(g / (1.0f + __expf(-g))));
-          out[(long long)m * n_out + t] = __float2half_rn(s * u);
+          out[(long long)m * ldo + t] = __float2half_rn(s * u);
         } else {
           __half h0 = __float2half_rn(a0[m]), h1 = __float2half_rn(a1[m]);
           if (residual != nullptr) {
             h0 = __float2half_rn(__half2float(h0) + __half2float(residual[(long long)m * n_out + r0]));
             h1 = __float2half_rn(__half2float(h1) + __half2float(residual[(long long)m * n_out + r1]));
           }
-          out[(long long)m * n_out + r0] = h0;
-          if (r1 != r0) out[(long long)m * n_out + r1] = h1;
+          out[(long long)m * ldo + r0] = h0;
+          if (r1 != r0) out[(long long)m * ldo + r1] = h1;
         }
       }
     }
@@ -209,7 +209,8 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
 }
 
 int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* residual, const void* norm_w, float eps,
-         int M, int N, int K, int mode, cudaStream_t stream) {
+         int M, int N, int K, int mode, cudaStream_t stream, int64_t ldo) {
+  if (ldo <= 0) ldo = mode == 1 ? N / 2 : N;
   SB_REQUIRE(M >= 1 && M <= GEMV_MAXM, "gemv: M=%d outside [1,%d]", M, GEMV_MAXM);
   SB_REQUIRE(K % 8 == 0 && ldw % 8 == 0, "gemv: K and ldw must be multiples of 8");
   SB_REQUIRE(mode == 0 || (mode == 1 && N % 256 == 0 && residual == nullptr), "gemv: bad mode/shape");
@@ -225,13 +226,18 @@ int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* resid
 #define SB_GEMV_LAUNCH(M_, MD_, NM_)                                                                       \
   {                                                                                                        \
     auto kern = gemv_kernel<M_, MD_, NM_>;                                                                 \
-    static size_t attr_smem = 48 * 1024;                                                                   \
+    static size_t attr_smem_dev[SB_MAX_DEVICES] = {};   /* per device: cudaFuncSetAttribute is */          \
+    const int dev_ = cur_device();                                                                         \
+    size_t& attr_smem = attr_smem_dev[dev_];                                                               \
+    if (attr_smem == 0) attr_smem = 48 * 1024;                                                             \
     if (smem > attr_smem) {                                                                                \
       SB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
       attr_smem = smem;                                                                                    \
     }                                                                                                      \
     /* one full wave: grid = SMs x resident CTAs (a partial second wave costs a whole task time) */        \
-    static int occ = 0; static size_t occ_smem = (size_t)-1;                                               \
+    static int occ_dev[SB_MAX_DEVICES] = {}; static size_t occ_smem_dev[SB_MAX_DEVICES] = {};              \
+    int& occ = occ_dev[dev_]; size_t& occ_smem = occ_smem_dev[dev_];                                       \
+    if (occ == 0) occ_smem = (size_t)-1;                                                                   \
     if (occ_smem != smem) {                                                                                \
       SB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));                 \
       occ_smem = smem;                                                                                     \
@@ -247,7 +253,7 @@ int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* resid
     if (blocks > resident) blocks = resident;                                                              \
     const int iters = (n_tasks + blocks * tpi - 1) / (blocks * tpi);                                       \
     SB_CHECK_CUDA(launch_chain(kern, dim3(blocks), dim3(256), smem, stream, xp, wp, (long long)ldw, op, rp, np, eps, N, K, \
-                               ksplit, iters));                                                            \
+                               ksplit, iters, (long long)ldo));                                            \
     SB_LAUNCH_CHECK();                                                                                     \
     return 0;                                                                                              \
   }
@@ -277,10 +283,20 @@ constexpr int DA_D = 128;
 constexpr int DA_BLK = 128;
 constexpr int DA_MAX_SPLITS = 64;
 
+// key-axis split of a cache of kv_len keys: whole 128-key blocks per split, at most DA_MAX_SPLITS, no empty split
+__host__ __device__ inline void da_split(int kv_len, int& nsplit, int& chunk) {
+  nsplit = (kv_len + DA_BLK - 1) / DA_BLK;
+  if (nsplit > DA_MAX_SPLITS) nsplit = DA_MAX_SPLITS;
+  chunk = ((kv_len + nsplit - 1) / nsplit + DA_BLK - 1) / DA_BLK * DA_BLK;
+  nsplit = (kv_len + chunk - 1) / chunk;
+}
+
 __global__ void __launch_bounds__(128)
 decode_attn_partial(const __half* __restrict__ q, const __half* __restrict__ kc, const __half* __restrict__ vc,
-                    float* __restrict__ ws, int H, int kv_len, int max_seq, int chunk, float scale_log2) {
-  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z, nsplit = gridDim.x;
+                    float* __restrict__ ws, int H, int kv_len, int max_seq, int chunk, float scale_log2,
+                    const int* __restrict__ dyn) {
+  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  int nsplit = gridDim.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   __shared__ __align__(16) float s_q[DA_D];
   __shared__ float s_p[DA_BLK];
@@ -288,6 +304,13 @@ decode_attn_partial(const __half* __restrict__ q, const __half* __restrict__ kc,
   __shared__ __align__(16) float s_o[8][DA_D];
   pdl_trigger();
   pdl_wait();
+  if (dyn != nullptr) {
+    // graph-replayed decode step: the cache length lives in device memory (dyn[0] = tokens already cached, this
+    // step's token has just been appended); the grid was sized for max_seq keys, surplus splits exit
+    kv_len = dyn[0] + 1;
+    da_split(kv_len, nsplit, chunk);
+    if (split >= nsplit) return;
+  }
   s_q[tid] = __half2float(q[((long long)b * H + h) * DA_D + tid]);
   const long long base = ((long long)b * H + h) * max_seq * DA_D;
   const int k0 = split * chunk, k1 = min(kv_len, k0 + chunk);
@@ -365,11 +388,12 @@ decode_attn_partial(const __half* __restrict__ q, const __half* __restrict__ kc,
 }
 
 __global__ void __launch_bounds__(DA_D)
-decode_attn_merge(const float* __restrict__ ws, __half* __restrict__ out, int nsplit) {
+decode_attn_merge(const float* __restrict__ ws, __half* __restrict__ out, int nsplit, const int* __restrict__ dyn) {
   const long long bh = blockIdx.x;
   const int d = threadIdx.x;
   pdl_trigger();
   pdl_wait();
+  if (dyn != nullptr) { int chunk; da_split(dyn[0] + 1, nsplit, chunk); }
   const float* src = ws + bh * nsplit * (DA_D + 2);
   float mm = -INFINITY;
   for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, src[s * (DA_D + 2)]);
@@ -383,23 +407,50 @@ decode_attn_merge(const float* __restrict__ ws, __half* __restrict__ out, int ns
   out[bh * DA_D + d] = __float2half_rn(ll > 0.0f ? acc / ll : 0.0f);
 }
 
+int decode_attention_max_splits(int max_seq) {
+  int nsplit, chunk;
+  da_split(max_seq < 1 ? 1 : max_seq, nsplit, chunk);
+  return nsplit;
+}
+
 int decode_attention(const void* q, const void* k_cache, const void* v_cache, void* out, int B, int H, int D,
-                     int kv_len, int max_seq, float scale, void* workspace, cudaStream_t stream) {
+                     int kv_len, int max_seq, float scale, void* workspace, cudaStream_t stream, const int* dyn) {
   SB_REQUIRE(D == DA_D, "decode_attention: head_dim %d unsupported (LLaMA uses 128)", D);
-  SB_REQUIRE(kv_len >= 1 && kv_len <= max_seq, "decode_attention: kv_len %d outside [1,%d]", kv_len, max_seq);
-  int nsplit = (kv_len + DA_BLK - 1) / DA_BLK;
-  if (nsplit > DA_MAX_SPLITS) nsplit = DA_MAX_SPLITS;
-  const int chunk = ((kv_len + nsplit - 1) / nsplit + DA_BLK - 1) / DA_BLK * DA_BLK;    // whole 128-key blocks
-  nsplit = (kv_len + chunk - 1) / chunk;                                               // no empty split
+  SB_REQUIRE(dyn != nullptr || (kv_len >= 1 && kv_len <= max_seq), "decode_attention: kv_len %d outside [1,%d]", kv_len, max_seq);
+  int nsplit, chunk;
+  da_split(dyn != nullptr ? max_seq : kv_len, nsplit, chunk);    // dyn: grid for the longest cache, trimmed in-kernel
+  // the partial results of (b, h) are laid out with the split count the kernels derive for the ACTUAL length
   dim3 grid(nsplit, H, B);
   SB_CHECK_CUDA(launch_chain(decode_attn_partial, grid, dim3(128), 0, stream, static_cast<const __half*>(q),
                              static_cast<const __half*>(k_cache), static_cast<const __half*>(v_cache),
-                             static_cast<float*>(workspace), H, kv_len, max_seq, chunk, scale * 1.4426950408889634f));
+                             static_cast<float*>(workspace), H, kv_len, max_seq, chunk, scale * 1.4426950408889634f, dyn));
   SB_LAUNCH_CHECK();
   SB_CHECK_CUDA(launch_chain(decode_attn_merge, dim3(B * H), dim3(DA_D), 0, stream, static_cast<const float*>(workspace),
-                             static_cast<__half*>(out), nsplit));
+                             static_cast<__half*>(out), nsplit, dyn));
   SB_LAUNCH_CHECK();
   return 0;
 }
 
 }  // namespace sb
+
+extern "C" {
+
+/* y[m,:] = epilogue(x[m,:] . W^T) for M <= 4 rows (the decode form of nn.Linear, llama_xformer.py:186,223-225,258,718) */
+int seedb200_gemv(const void* x, const void* W, int64_t ldw, void* out, const void* residual, const void* norm_w,
+                  float eps, int M, int N, int K, int mode, void* stream) {
+  SB_REQUIRE(x && W && out, "seedb200_gemv: null operand");
+  return sb::gemv(x, W, ldw, out, residual, norm_w, eps, M, N, K, mode, static_cast<cudaStream_t>(stream));
+}
+
+int64_t seedb200_decode_attention_workspace_bytes(int B, int H, int max_seq) {
+  return (int64_t)B * H * sb::decode_attention_max_splits(max_seq) * (sb::DA_D + 2) * (int64_t)sizeof(float);
+}
+
+int seedb200_decode_attention(const void* q, const void* k_cache, const void* v_cache, void* out, int B, int H, int D,
+                              int kv_len, int max_seq, float scale, void* workspace, void* stream) {
+  SB_REQUIRE(q && k_cache && v_cache && out && workspace, "seedb200_decode_attention: null operand");
+  return sb::decode_attention(q, k_cache, v_cache, out, B, H, D, kv_len, max_seq, scale, workspace,
+                              static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -31,6 +31,7 @@ struct seedb200_preprocess {
   int2* bh; int32_t* kh;     // horizontal bounds [out], weights [ksh][out]
   int2* bv; int32_t* kv;     // vertical bounds [out] (ymin relative to y_first), weights [ksv][out]
   uint8_t* tmp;              // [max_batch][tmp_rows][out][3]
+  int device;
 };
 
 namespace sb {
@@ -258,10 +259,19 @@ resize_v_kernel(const uint8_t* __restrict__ src, long long image_stride, int wid
 extern "C" {
 
 int seedb200_preprocess_create(int in_h, int in_w, int out_size, int filter, int max_batch, seedb200_preprocess** out) {
+  return seedb200_preprocess_create_ex(in_h, in_w, out_size, out_size, 0, 0, out_size, filter, max_batch, out);
+}
+
+int seedb200_preprocess_create_ex(int in_h, int in_w, int resize_h, int resize_w, int crop_top, int crop_left,
+                                  int out_size, int filter, int max_batch, seedb200_preprocess** out) {
   using namespace sb;
   if (!out) { set_error("preprocess_create: null output"); return SEEDB200_ERR_INVALID; }
   *out = nullptr;
   SB_REQUIRE(in_h > 0 && in_w > 0 && out_size > 0 && max_batch > 0, "preprocess_create: non-positive size");
+  SB_REQUIRE(resize_h >= out_size && resize_w >= out_size && crop_top >= 0 && crop_left >= 0 &&
+                 crop_top + out_size <= resize_h && crop_left + out_size <= resize_w,
+             "preprocess_create: crop window %d+%d x %d+%d outside the %dx%d resize", crop_top, out_size, crop_left,
+             out_size, resize_h, resize_w);
   SB_REQUIRE(filter == 2 || filter == 3, "preprocess_create: filter %d (2 = PIL BILINEAR, 3 = PIL BICUBIC)", filter);
   SB_REQUIRE((long long)(in_w * 3 + 48 + out_size * 3) + 64 <= 200 * 1024, "preprocess_create: image width %d too large", in_w);
   std::vector<int2> bh, bv;
@@ -269,10 +279,23 @@ int seedb200_preprocess_create(int in_h, int in_w, int out_size, int filter, int
   seedb200_preprocess* p = new seedb200_preprocess();
   memset(p, 0, sizeof(*p));
   p->in_h = in_h; p->in_w = in_w; p->out = out_size; p->filter = filter; p->max_batch = max_batch;
-  p->ksh = pp_coeffs(in_w, out_size, filter, bh, kh);
-  p->ksv = pp_coeffs(in_h, out_size, filter, bv, kv);
+  p->device = cur_device();
+  // coefficients of the full resize_w x resize_h resample, then only the crop window's columns / rows are kept: a
+  // centre crop of a separable resample is the same resample evaluated on fewer output coordinates
+  // (models/transforms.py:6-9 keep_ratio=True: Resize(S) -> CenterCrop(S))
+  auto window = [&](int in_size, int full, int first, std::vector<int2>& b, std::vector<int32_t>& k) {
+    std::vector<int2> fb; std::vector<int32_t> fk;
+    const int ks = pp_coeffs(in_size, full, filter, fb, fk);
+    b.assign(fb.begin() + first, fb.begin() + first + out_size);
+    k.assign((size_t)ks * out_size, 0);
+    for (int t = 0; t < ks; ++t)
+      for (int i = 0; i < out_size; ++i) k[(size_t)t * out_size + i] = fk[(size_t)t * full + first + i];
+    return ks;
+  };
+  p->ksh = window(in_w, resize_w, crop_left, bh, kh);
+  p->ksv = window(in_h, resize_h, crop_top, bv, kv);
   // PIL/Image.py resize(): "if self.size[1] > self.size[0] * 100 and size[1] < self.size[1]" -> vertical pass first
-  p->vertical_first = ((long long)in_h > (long long)in_w * 100 && out_size < in_h) ? 1 : 0;
+  p->vertical_first = ((long long)in_h > (long long)in_w * 100 && resize_h < in_h) ? 1 : 0;
   if (p->vertical_first) {
     p->y_first = 0;
     p->tmp_rows = out_size;                                  // intermediate [out][in_w][3]
@@ -311,6 +334,7 @@ int seedb200_preprocess_run(seedb200_preprocess* p, const void* images_u8, int n
   using namespace sb;
   SB_REQUIRE(p && images_u8 && out_f16, "preprocess_run: null argument");
   SB_REQUIRE(n > 0 && n <= p->max_batch, "preprocess_run: batch %d outside [1,%d]", n, p->max_batch);
+  DeviceGuard guard(p->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint8_t* src = static_cast<const uint8_t*>(images_u8);
   __half* dst = static_cast<__half*>(out_f16);
@@ -319,7 +343,9 @@ int seedb200_preprocess_run(seedb200_preprocess* p, const void* images_u8, int n
   if (rpc > PP_ROWS) rpc = PP_ROWS;
   if (rpc < 1) rpc = 1;
   const size_t smem = (size_t)rpc * row_slot + 64;          // + word over-read slack
-  static size_t attr_smem[2] = {48 * 1024, 48 * 1024};
+  static size_t attr_smem_dev[SB_MAX_DEVICES][2] = {};     // per device: cudaFuncSetAttribute is
+  size_t* attr_smem = attr_smem_dev[cur_device()];
+  if (attr_smem[0] == 0) attr_smem[0] = attr_smem[1] = 48 * 1024;
   if (smem > attr_smem[p->vertical_first]) {
     if (p->vertical_first)
       SB_CHECK_CUDA(cudaFuncSetAttribute(resize_h_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

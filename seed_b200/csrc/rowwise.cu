@@ -267,12 +267,13 @@ __global__ void __launch_bounds__(256)
 rope_kv_kernel(const __half* __restrict__ qkv, const long long* __restrict__ positions, int S, int H, int D,
                int past_len, int max_seq, int max_pos, const __half* __restrict__ cos_t,
                const __half* __restrict__ sin_t, __half* __restrict__ q_out, __half* __restrict__ k_cache,
-               __half* __restrict__ v_cache, long long total) {
+               __half* __restrict__ v_cache, long long total, const int* __restrict__ dyn) {
   const int half_d = D / 2;
   const int vec_per_head = half_d / 8;
   const long long HD = (long long)H * D;
   pdl_trigger();
   pdl_wait();
+  if (dyn != nullptr) past_len = dyn[0];     // graph-replayed decode step: the cache length lives in device memory
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int vi = (int)(i % vec_per_head);
     long long t = i / vec_per_head;
@@ -287,7 +288,9 @@ rope_kv_kernel(const __half* __restrict__ qkv, const long long* __restrict__ pos
     const __half* ch = reinterpret_cast<const __half*>(&craw);
     const __half* sh = reinterpret_cast<const __half*>(&sraw);
     const __half* row = qkv + t * 3 * HD + (long long)h * D;
-    const long long cache_row = (((long long)b * H + h) * max_seq + past_len + s) * D;
+    int crow = past_len + s;
+    if (crow >= max_seq) crow = max_seq - 1;           // only reachable through dyn (host-checked otherwise)
+    const long long cache_row = (((long long)b * H + h) * max_seq + crow) * D;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {          // 0 = q, 1 = k
       const uint4 lo_raw = *reinterpret_cast<const uint4*>(row + which * HD + vi * 8);
@@ -322,7 +325,7 @@ rope_kv_kernel(const __half* __restrict__ qkv, const long long* __restrict__ pos
 
 int rope_kv_append_tables(const void* qkv, const int64_t* positions, int B, int S, int H, int D, int past_len,
                           int max_seq, int max_pos, const void* cos_t, const void* sin_t, void* q_out,
-                          void* k_cache, void* v_cache, cudaStream_t stream) {
+                          void* k_cache, void* v_cache, cudaStream_t stream, const int* dyn) {
   SB_REQUIRE(qkv && q_out && k_cache && v_cache && cos_t && sin_t, "rope_kv_append: null operand");
   SB_REQUIRE(D % 16 == 0, "rope_kv_append: head_dim %d must be a multiple of 16", D);
   SB_REQUIRE(past_len + S <= max_seq, "rope_kv_append: past_len %d + S %d exceeds max_seq %d", past_len, S, max_seq);
@@ -334,7 +337,7 @@ int rope_kv_append_tables(const void* qkv, const int64_t* positions, int B, int 
                              reinterpret_cast<const long long*>(positions), S, H, D, past_len, max_seq, max_pos,
                              static_cast<const __half*>(cos_t), static_cast<const __half*>(sin_t),
                              static_cast<__half*>(q_out), static_cast<__half*>(k_cache), static_cast<__half*>(v_cache),
-                             total));
+                             total, dyn));
   SB_LAUNCH_CHECK();
   return 0;
 }

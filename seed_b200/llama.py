@@ -1,8 +1,8 @@
 """Host-side mirror of models/llama_xformer.py (LlamaForCausalLM) on top of libseedb200.
 
 `forward()` keeps the reference signature and returns transformers' CausalLMOutputWithPast
-(llama_xformer.py:661-743); `generate()` is a thin greedy / top-p loop standing in for HF GenerationMixin
-(scripts/seed_llama_inference_8B.py:33).  The decoder stack itself is one C call per forward.
+(llama_xformer.py:661-743); `generate()` stands in for HF GenerationMixin (scripts/seed_llama_inference_8B.py:33):
+by default one C call that keeps prefill, sampling and the graph-replayed decode steps on the device.
 
 Reference behaviours kept on purpose (SURVEY.md section 7 "quirks"):
   * padding in `attention_mask` is ignored by attention -- the reference only tests `attention_mask.sum() == 0`
@@ -59,6 +59,7 @@ class LlamaForCausalLM(nn.Module):
         del weights
         self._cache_len = 0          # tokens currently valid in the internal KV cache
         self._cache_batch = 0
+        self._draws = 0              # Philox counter: sampling draws made so far (successive generate() calls differ)
 
     # ---- construction --------------------------------------------------------------------------
     @classmethod
@@ -176,10 +177,10 @@ class LlamaForCausalLM(nn.Module):
 
     __call__ = forward
 
-    # ---- generation (stand-in for HF GenerationMixin.sample / greedy) ------------------------------------
+    # ---- generation (stand-in for HF GenerationMixin.sample / greedy_search) -------------------------------
     def prepare_inputs_for_generation(self, input_ids, past_key_values=None, attention_mask=None, inputs_embeds=None,
                                       **kwargs):
-        """llama_xformer.py:745-776."""
+        """llama_xformer.py:745-776: last token only once a past exists; position_ids from the mask's cumsum."""
         if past_key_values:
             input_ids = input_ids[:, -1:]
         position_ids = kwargs.get("position_ids", None)
@@ -196,57 +197,75 @@ class LlamaForCausalLM(nn.Module):
                              "use_cache": kwargs.get("use_cache"), "attention_mask": attention_mask})
         return model_inputs
 
-    @staticmethod
-    def _reorder_cache(past_key_values, beam_idx):
-        """llama_xformer.py:778-783."""
-        return tuple(tuple(p.index_select(0, beam_idx) for p in layer_past) for layer_past in past_key_values)
+    def _next_seed(self, generator: Optional[torch.Generator], seed: Optional[int]) -> int:
+        if seed is not None:
+            return int(seed)
+        if generator is not None:
+            return int(generator.initial_seed())
+        return int(torch.initial_seed())
 
     @torch.no_grad()
     def generate(self, input_ids=None, inputs=None, max_new_tokens: int = 20, do_sample: bool = False,
                  temperature: float = 1.0, top_p: float = 1.0, num_beams: int = 1, eos_token_id=None,
-                 pad_token_id=None, attention_mask=None, generator: Optional[torch.Generator] = None, **_):
-        """Token loop with the call pattern of scripts/seed_llama_inference_8B.py:33
-        (temperature=1.0, num_beams=1, max_new_tokens=512, top_p=0.5, do_sample=True).
-        Returns [B, S + n_new] like HF generate.  Sampling parity with HF is RNG dependent; logits are the
-        contract that is tested."""
+                 pad_token_id=None, attention_mask=None, generator: Optional[torch.Generator] = None,
+                 seed: Optional[int] = None, use_graph: bool = True, device_loop: Optional[bool] = None, **_):
+        """Call pattern of scripts/seed_llama_inference_8B.py:33 (temperature=1.0, num_beams=1, max_new_tokens=512,
+        top_p=0.5, do_sample=True); returns [B, S + n_new] like HF generate.
+
+        Default path (`device_loop`): ONE C call -- prefill, on-device sampler, CUDA-graph-replayed decode steps
+        (seedb200_llama_generate); no per-token host work.  With a padding `attention_mask` (position ids that are
+        not past + arange) or more than one eos id, the loop runs from Python through
+        `prepare_inputs_for_generation` exactly as HF drives the reference, still sampling with the device kernel.
+        Sampled ids depend on the RNG (Philox keyed by `seed`, counter = draws made so far), not on torch's stream;
+        logits are the parity contract."""
         if num_beams != 1:
             raise NotImplementedError("beam search is not used by the SEED scripts")
         if input_ids is None:
             input_ids = inputs
         input_ids = input_ids.to(self._device, torch.int64)
         B, S = input_ids.shape
+        if S + max_new_tokens > self.max_seq:
+            max_new_tokens = self.max_seq - S          # HF stops at max_length; here the cache is the limit
+            if max_new_tokens < 1:
+                raise ValueError(f"prompt of {S} tokens leaves no room in max_seq={self.max_seq}")
         eos = eos_token_id if eos_token_id is not None else getattr(self.config, "eos_token_id", None)
-        eos_set = set(eos) if isinstance(eos, (list, tuple)) else ({eos} if eos is not None else set())
-        pad = pad_token_id if pad_token_id is not None else (next(iter(eos_set)) if eos_set else 0)
-        out = self.forward(input_ids=input_ids, use_cache=True, last_logits_only=True)
-        seq = input_ids
+        eos_list = list(eos) if isinstance(eos, (list, tuple)) else ([eos] if eos is not None else [])
+        pad = pad_token_id if pad_token_id is not None else (eos_list[0] if eos_list else 0)
+        rng_seed = self._next_seed(generator, seed)
+        offset = self._draws
+        padded = attention_mask is not None and not bool(attention_mask.to(torch.bool).all())
+        if device_loop is None:
+            device_loop = (not padded) and len(eos_list) <= 1 and B <= 4
+        if device_loop:
+            if padded or len(eos_list) > 1 or B > 4:
+                raise ValueError("device_loop needs an unpadded batch of <= 4 sequences and at most one eos id")
+            new = self._llm.generate(input_ids, max_new_tokens, do_sample=do_sample, temperature=temperature,
+                                     top_p=top_p, seed=rng_seed, offset=offset,
+                                     eos_token_id=eos_list[0] if eos_list else -1, pad_token_id=pad,
+                                     use_graph=use_graph)
+            self._draws += max_new_tokens
+            self._cache_len, self._cache_batch = 0, 0       # the handle's cache now belongs to that generation
+            return torch.cat([input_ids, new], dim=1)
+        # ---- HF-shaped loop (padding masks, several eos ids): one forward per token from Python ----
+        mask = attention_mask.to(self._device) if attention_mask is not None else None
+        seq, past = input_ids, None
         unfinished = torch.ones(B, dtype=torch.bool, device=self._device)
-        past = out.past_key_values
-        logits = out.logits[:, -1].float()
         for step in range(max_new_tokens):
-            if do_sample:
-                probs = torch.softmax(logits / max(temperature, 1e-6), dim=-1)
-                if top_p < 1.0:   # nucleus filtering as HF TopPLogitsWarper
-                    sp, si = torch.sort(probs, descending=True)
-                    keep = (sp.cumsum(-1) - sp) < top_p
-                    sp = sp * keep
-                    probs = torch.zeros_like(probs).scatter_(1, si, sp)
-                    probs = probs / probs.sum(-1, keepdim=True)
-                nxt = torch.multinomial(probs, 1, generator=generator).squeeze(1)
-            else:
-                nxt = logits.argmax(-1)
+            mi = self.prepare_inputs_for_generation(seq, past_key_values=past, attention_mask=mask, use_cache=True)
+            out = self.forward(input_ids=mi["input_ids"], position_ids=mi["position_ids"],
+                               past_key_values=mi["past_key_values"], use_cache=True, last_logits_only=True)
+            past = out.past_key_values
+            nxt = L.sample(out.logits[:, -1], do_sample=do_sample, temperature=temperature, top_p=top_p,
+                           seed=rng_seed, offset=offset, step=step)
             nxt = torch.where(unfinished, nxt, torch.full_like(nxt, pad))
             seq = torch.cat([seq, nxt[:, None]], dim=1)
-            if eos_set:
-                for e in eos_set:
-                    unfinished = unfinished & (nxt != e)
-                if not bool(unfinished.any()):
-                    break
-            if step + 1 == max_new_tokens or S + step + 1 >= self.max_seq:
+            if mask is not None:
+                mask = torch.cat([mask, mask.new_ones((B, 1))], dim=1)
+            for e in eos_list:
+                unfinished = unfinished & (nxt != e)
+            if eos_list and not bool(unfinished.any()):
                 break
-            out = self.forward(input_ids=nxt[:, None], past_key_values=past, use_cache=True, last_logits_only=True)
-            past = out.past_key_values
-            logits = out.logits[:, -1].float()
+        self._draws += max_new_tokens
         return seq
 
 

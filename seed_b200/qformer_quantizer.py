@@ -94,6 +94,11 @@ class Blip2QformerQuantizer(nn.Module):
         ids, z, _ = self._enc.encode(image, return_z=return_z)
         return (ids, z) if return_z else ids
 
+    def encode_tokens(self, image: torch.Tensor, image_id_shift: int, boi: int, eoi: int, out=None):
+        """encode_ids fused with `<img>` + (shift + id) x 32 + `</img>` (seedb200_encoder_encode_tokens): [B,34] int64."""
+        image = self._check_image(image)
+        return self._enc.encode_tokens(image, image_id_shift, boi, eoi, out=out)
+
     def get_codebook_entry(self, indices: torch.Tensor) -> torch.Tensor:
         """qformer_quantizer.py:309-338: ids [B,32] -> image embeds [B,1024] (input of the unCLIP decoder)."""
         if self.detok_depth == 0:

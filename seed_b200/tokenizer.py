@@ -182,17 +182,56 @@ class SeedImageTokenMixin:
         return all_gather_ids(ids, group)
 
     @staticmethod
-    def image_ids_to_tokens(ids, image_id_shift: int = 32000, boi: Optional[int] = None, eoi: Optional[int] = None):
+    def image_ids_to_tokens(ids, image_id_shift: int = 32000, boi: Optional[int] = None, eoi: Optional[int] = None,
+                            out: Optional[torch.Tensor] = None):
         """[B,32] codebook ids -> [B,34] LLaMA token ids `<img> <img_xxxxx>*32 </img>` by arithmetic
-        (scripts/seed_llama_inference_8B.py:16-23,60,98-100 build the same ids through a string round trip)."""
+        (scripts/seed_llama_inference_8B.py:16-23,60,98-100 build the same ids through a string round trip).
+        CUDA ids go through seedb200_image_ids_to_tokens (the span can land inside a prompt buffer via `out`);
+        host ids are host-side bookkeeping like the reference's string formatting.  The defaults assume the
+        added-token order of the released checkpoints (`<img_00000>` = 32000 ... `<img>` = 40192, `</img>` = 40193);
+        `image_token_ids()` on a tokenizer instance resolves the three ids through the vocabulary instead."""
         boi = image_id_shift + 8192 if boi is None else boi
         eoi = image_id_shift + 8193 if eoi is None else eoi
+        if ids.is_cuda:
+            from . import lib as L
+
+            return L.image_ids_to_tokens(ids, image_id_shift, boi, eoi, out=out)
         B = ids.shape[0]
-        out = torch.empty((B, 34), dtype=torch.int64, device=ids.device)
-        out[:, 0] = boi
-        out[:, 1:33] = ids + image_id_shift
-        out[:, 33] = eoi
-        return out
+        res = torch.empty((B, 34), dtype=torch.int64, device=ids.device) if out is None else out
+        res[:, 0] = boi
+        res[:, 1:33] = ids + image_id_shift
+        res[:, 33] = eoi
+        return res
+
+    def image_token_ids(self):
+        """(image_id_shift, boi, eoi) looked up in the text vocabulary the way the reference scripts do
+        (`tokenizer(BOI_TOKEN).input_ids[0]`, scripts/seed_llama_inference_8B.py:42-43), cached; falls back to the
+        released layout only when this object carries no vocabulary (bare SeedImageTokenMixin)."""
+        cached = getattr(self, "_image_token_ids", None)
+        if cached is not None:
+            return cached
+        shift, boi, eoi = 32000, 40192, 40193
+        conv = getattr(self, "convert_tokens_to_ids", None)
+        if callable(conv):
+            unk = getattr(self, "unk_token_id", None)
+            got = [conv(t) for t in ("<img_00000>", "<img>", "</img>")]
+            if any(g is None or g == unk for g in got):
+                raise KeyError("the tokenizer vocabulary lacks '<img_00000>', '<img>' or '</img>' "
+                               "(added tokens of the SEED-LLaMA checkpoints)")
+            shift, boi, eoi = (int(g) for g in got)
+            last = conv("<img_%05d>" % (self.num_image_tokens - 1))
+            if last != shift + self.num_image_tokens - 1:
+                raise ValueError("image tokens are not contiguous in the vocabulary: id arithmetic does not apply")
+        self._image_token_ids = (shift, boi, eoi)
+        return self._image_token_ids
+
+    def encode_image_tokens(self, image_torch, out: Optional[torch.Tensor] = None):
+        """images -> [B,34] LLaMA token ids without leaving the device (encode fused with the id arithmetic)."""
+        shift, boi, eoi = self.image_token_ids()
+        tok = self.image_tokenizer
+        if len(image_torch.shape) == 3:
+            image_torch = image_torch.unsqueeze(0)
+        return tok.model.encode_tokens(image_torch, shift, boi, eoi, out=out)
 
 
 def all_gather_ids(ids: torch.Tensor, group=None) -> torch.Tensor:

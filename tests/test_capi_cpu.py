@@ -30,7 +30,7 @@ def test_header_symbols_are_all_exported(L):
     handle = L.load()
     for sym in sorted(declared):
         assert hasattr(handle, sym), f"libseedb200.so does not export {sym}"
-    assert handle.seedb200_version() == 100
+    assert handle.seedb200_version() == 200
 
 
 def test_errors_are_reported_not_thrown(L):
