@@ -10,6 +10,8 @@ One "step" is one pass of the hot path over one batch of synthetic input:
   encode        : 256 images/GPU -> [256,32] ids (config #2 of BASELINE.json); at N > 1 every rank encodes its own
                   shard and one NCCL all-gather returns all ids to every rank (config #4's data-parallel pattern);
   llama_prefill : one S=2048 prompt (with a 34-token image span) through random-init LLaMA-7B (config #3).
+With the default workload the line also carries `secondary` records for the LLaMA half of BASELINE.json's metric
+(llama_prefill, llama_decode) and for the chained config #4 (pipeline), measured at the same N by the same rules.
 `value` is timed with CUDA events with the inputs already resident in HBM; `e2e` is the same metric through the
 reference-facing Python API (models.seed_llama_tokenizer.ImageTokenizer.encode / models.llama_xformer
 .LlamaForCausalLM.forward) starting from PINNED HOST buffers and ending with the ids / last-token logits on
@@ -134,8 +136,12 @@ def max_over_ranks(ms: float, world: int) -> float:
     return float(t.item())
 
 
+LAST_LOCAL_MS = [0.0]
+
+
 def timed(fn, steps, warmup, world):
-    """W untimed + K timed calls bracketed by barrier + synchronize; CUDA events; max over ranks (ms)."""
+    """W untimed + K timed calls bracketed by barrier + synchronize; CUDA events; max over ranks (ms).
+    The rank-local duration of the last call is left in LAST_LOCAL_MS[0] (per-rank statistics at N > 1)."""
     for _ in range(warmup):
         fn()
     barrier_sync(world)
@@ -145,7 +151,55 @@ def timed(fn, steps, warmup, world):
         fn()
     e.record()
     barrier_sync(world)
-    return max_over_ranks(s.elapsed_time(e), world)
+    LAST_LOCAL_MS[0] = s.elapsed_time(e)
+    return max_over_ranks(LAST_LOCAL_MS[0], world)
+
+
+def workload_config(args, world):
+    """`config` of the JSON line -- built by ONE function for both arms (--impl seedb200 / reference), so the two
+    lines name the same workload key for key; arm-specific facts (CPU sample size, kernel options) live outside it."""
+    B = args.batch
+    if args.workload == "encode":
+        return {"workload": f"encode_b{B}_per_gpu", "global_batch": B * world, "vq_arithmetic": args.vq,
+                "detail": "224x224 -> ViT-g/14 (39 blocks) + causal Q-Former (12 layers) + 8192-way VQ -> 32 ids/image",
+                "weights": "seeded synthetic (seed_b200/synth.py; codebook N(0,0.28) instead of U(+-1/8192))",
+                "parallelism": f"dp{world}" + (" + NCCL all-gather of ids" if world > 1 else ""),
+                "l2": "inputs not flushed explicitly: each step streams ~2 GB of activations, 16x the 126 MB L2"}
+    if args.workload == "llama_prefill":
+        return {"workload": f"llama7b_prefill_s{args.seq}", "global_batch": world, "seq_len": args.seq,
+                "detail": "random-init h4096/L32/H32/FFN11008/V40194, B=1, one 34-token image span, logits for all positions",
+                "parallelism": f"dp{world} (independent replicas, no collective)",
+                "l2": "13.5 GB of weights stream through L2 every step"}
+    if args.workload == "llama_decode":
+        return {"workload": f"llama13b_p{args.prompt}_decode{args.new_tokens}", "global_batch": world,
+                "seq_len": args.prompt + args.new_tokens,
+                "detail": f"random-init h5120/L40/H40/FFN13824/V40194, B=1, {args.prompt}-token prompt with 4 image spans, "
+                          f"{args.new_tokens} greedy tokens (1 prefill + {args.new_tokens - 1} cached decode steps)",
+                "parallelism": f"dp{world} (independent replicas, no collective)",
+                "l2": "26 GB of weights stream from HBM every token (207x the L2)"}
+    if args.workload == "pipeline":
+        return {"workload": f"pipeline_encode_b{B}_to_llama7b_prefill_s{args.seq}", "global_batch": B * world,
+                "seq_len": args.seq,
+                "detail": "config #4: encode B images/GPU -> all-gather ids -> id->token arithmetic -> 60 image spans + text "
+                          "-> one 7B prefill per rank, ids never leave the device",
+                "parallelism": f"dp{world} + NCCL all-gather of ids", "l2": "activations >> L2"}
+    return {"workload": f"preprocess_b{B}", "global_batch": B * world, "parallelism": f"dp{world}",
+            "detail": "uint8 480x640x3 -> Pillow-exact bicubic 224x224 -> CLIP normalise -> fp16",
+            "l2": f"inputs {B * 480 * 640 * 3 / 1e6:.0f} MB per step (> L2 at B=256)"}
+
+
+def per_rank_stats(ms: float, world: int):
+    """min / median / max over ranks of one rank-local duration (ms): shows whether an N>1 efficiency loss is skew
+    between ranks (power capping) or a uniformly slower step (the collective)."""
+    if world == 1:
+        return None
+    import torch.distributed as dist
+
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    allv = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allv, t)
+    v = sorted(float(x.item()) for x in allv)
+    return {"min": round(v[0], 3), "median": round(v[len(v) // 2], 3), "max": round(v[-1], 3)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -273,7 +327,7 @@ def reference_arm(args, world, rank):
         if depth != VIT_DEPTH:
             sample += f"; ViT truncated to {depth} of {VIT_DEPTH} blocks and the time scaled x{scale_full:.2f} by algorithmic FLOPs (host too slow for a full-depth image per step)"
         return dict(metric="images/sec SEED encode+VQ", value=value, unit="images/s", ms_per_step=1e3 * dt / args.steps,
-                    sample=sample, cores=cores, workload=f"encode_b{args.batch}")
+                    sample=sample, cores=cores)
     else:
         from oracle import restatement as R
 
@@ -296,13 +350,13 @@ def reference_arm(args, world, rank):
         sample = (f"{layers}-layer slice of LLaMA-7B, S={args.seq}, fp32, scaled to 32 layers by measured time per layer "
                   f"(lm_head+embedding counted as 0.8 layer)")
         return dict(metric="tokens/sec LLaMA-7B prefill", value=value, unit="tokens/s", ms_per_step=1e3 * full,
-                    sample=sample, cores=cores, workload=f"llama7b_prefill_s{args.seq}")
+                    sample=sample, cores=cores)
 
 
 # --------------------------------------------------------------------------------------------------
 # GPU arms
 # --------------------------------------------------------------------------------------------------
-def encode_arm(args, world, rank, local):
+def encode_arm(args, world, rank, local, keep=None):
     from models.seed_llama_tokenizer import ImageTokenizer, all_gather_ids
     from seed_b200 import lib as L, synth
 
@@ -311,6 +365,8 @@ def encode_arm(args, world, rank, local):
     sd = synth.encoder_state_dict(VIT_DEPTH, QF_LAYERS, 0)
     tok = ImageTokenizer(model_path=sd, device=dev, fp16=True, max_batch=B, gemm_ctas=args.ctas,
                          vq_mode=L.VQ_FP32 if args.vq == "fp32" else L.VQ_FP16)
+    if keep is not None:
+        keep["tok"], keep["sd"] = tok, sd
     # id parity against the reference's own output (tests/golden/encoder_full.pt), same weights
     parity = None
     gpath = os.path.join(REPO, "tests", "golden", "encoder_full.pt")
@@ -342,6 +398,7 @@ def encode_arm(args, world, rank, local):
     L.reset_launch_count()
     with ClockSampler(local) as cs:
         ms = timed(step_device, args.steps, args.warmup, world)
+    rank_ms = per_rank_stats(LAST_LOCAL_MS[0] / args.steps, world)
     launches = L.launch_count() // (args.steps + args.warmup)
     clocks = cs.summary()
     ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup), world)
@@ -355,13 +412,17 @@ def encode_arm(args, world, rank, local):
     gemm_ms, gemm_n = prof["gemm"]["ms"], prof["gemm"]["launches"]
     gemm_flops = GEMM_FLOPS_PER_IMAGE * B
     ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
-    traffic = None
-    tp = os.path.join(REPO, "profiles", "r01_gemm_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch_avg")
+    traffic, traffic_src = None, None
+    for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+        tp = os.path.join(REPO, "profiles", name)
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch_avg")
+            traffic_src = f"static: ncu --set full capture committed as profiles/{name} (dram__bytes_read.sum + dram__bytes_write.sum per launch, average over the ViT shapes); not measured in this run"
+            break
     roofline = {"kernel": "sb::gemm_tcgen05_kernel", "bound": "tensor", "achieved": round(ach, 1),
                 "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / peaks["tflops_sustained"], 4),
-                "traffic": traffic, "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                 "launches_per_step": gemm_n, "gemm_ms_per_step": round(gemm_ms, 3),
                 "algorithmic_gflop_per_launch": round(gemm_flops / gemm_n / 1e9, 2),
                 "avg_launch_ms": round(gemm_ms / gemm_n, 4), "share_of_step": round(gemm_ms / (ms / args.steps), 3),
@@ -378,12 +439,7 @@ def encode_arm(args, world, rank, local):
         "metric": "images/sec SEED encode+VQ", "value": round(total / (ms * 1e-3), 2), "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"encode_b{B}_per_gpu: 224x224 -> ViT-g/14 (39 blocks) + causal Q-Former (12 layers) + "
-                               f"8192-way VQ -> 32 ids/image", "global_batch": B * world, "vq_arithmetic": args.vq,
-                   "weights": "seeded synthetic (seed_b200/synth.py; codebook N(0,0.28) instead of U(+-1/8192))",
-                   "parallelism": f"dp{world}" + (" + NCCL all-gather of ids" if world > 1 else ""),
-                   "l2": "inputs not flushed explicitly: each step streams ~2 GB of activations, 16x the 126 MB L2",
-                   "gemm_cta_group": args.ctas or 1},
+        "config": workload_config(args, world), "kernel_options": {"gemm_cta_group": args.ctas or 1},
         "clocks": clocks,
         "e2e": {"value": round(total / (ms_e2e * 1e-3), 2), "unit": "images/s",
                 "h2d_bytes_per_step": B * world * 3 * 224 * 224 * 2, "d2h_bytes_per_step": B * world * 32 * 8 * world,
@@ -391,6 +447,8 @@ def encode_arm(args, world, rank, local):
         "gpu_launches": int(launches) * args.steps,
         "roofline": roofline, "cpu_baseline": cpu, "id_parity": parity,
     }
+    if rank_ms is not None:
+        res["per_rank_ms_per_step"] = rank_ms
     return res
 
 
@@ -425,7 +483,8 @@ def random_llama(dev, rank, h, nl, nh, ffn, V, max_seq, ctas):
 
 def llama_decode_arm(args, world, rank, local):
     """BASELINE.json config #5: random-init 13B llama_xformer, interleaved 4-image prompt, prefill + 128 generated
-    tokens (greedy), batch 1.  A step = one generate() call; value = generated tokens/s over prefill+decode."""
+    tokens (greedy), batch 1.  A step = one generate() call = ONE C call (prefill, on-device sampler, CUDA-graph
+    replayed decode steps); value = generated tokens/s over prefill+decode."""
     from seed_b200 import lib as L, synth
 
     dev = torch.device("cuda", local)
@@ -435,58 +494,61 @@ def llama_decode_arm(args, world, rank, local):
     ids_host = synth.prompt_ids(1, P, 4, seed=99 + rank).pin_memory()
     ids = ids_host.to(dev)
     out = {}
+    gen = dict(max_new_tokens=NEW, do_sample=False, eos_token_id=-1)       # fixed length: no early stop on eos
 
     def step_device():
-        out["seq"] = model.generate(input_ids=ids, max_new_tokens=NEW, do_sample=False)
+        out["seq"] = model.generate(input_ids=ids, **gen)
 
     def step_e2e():
-        out["host"] = model.generate(input_ids=ids_host.to(dev, non_blocking=True), max_new_tokens=NEW, do_sample=False).cpu()
+        out["host"] = model.generate(input_ids=ids_host.to(dev, non_blocking=True), **gen).cpu()
 
     step_device(); torch.cuda.synchronize()
+    used_graph = model._llm.used_graph
     L.reset_launch_count()
     with ClockSampler(local) as cs:
         ms = timed(step_device, args.steps, args.warmup, world)
+    rank_ms = per_rank_stats(LAST_LOCAL_MS[0] / args.steps, world)
     launches = L.launch_count() // (args.steps + args.warmup)
     clocks = cs.summary()
     ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup), world)
-    # decode-only forwards (q_len 1 over the cache) between CUDA events: the HBM roofline of the token loop
-    o = model.forward(input_ids=ids, use_cache=True, last_logits_only=True)
-    nxt = o.logits[:, -1].float().argmax(-1)[:, None]
-    past = o.past_key_values
+    # decode-only time per token: whole generate minus the prefill forward, both between CUDA events
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_dec = min(64, NEW)
     e0.record()
-    for _ in range(n_dec):
-        o = model.forward(input_ids=nxt, past_key_values=past, use_cache=True, last_logits_only=True)
-        past = o.past_key_values
-    e1.record(); torch.cuda.synchronize()
-    dec_ms = e0.elapsed_time(e1) / n_dec
+    model.forward(input_ids=ids, use_cache=True, last_logits_only=True)
+    e1.record()
+    model.generate(input_ids=ids, **gen)
+    e2.record(); torch.cuda.synchronize()
+    prefill_ms = e0.elapsed_time(e1)
+    dec_ms = (e1.elapsed_time(e2) - prefill_ms) / (NEW - 1)
     peaks = measured_peaks()
     weight_bytes = 2.0 * (nl * (4 * h * h + 3 * h * ffn) + h * V)      # every weight once per token (+ one embedding row)
-    kv_bytes = 2.0 * 2 * nl * nh * 128 * (P + n_dec / 2)
+    kv_bytes = 2.0 * 2 * nl * nh * 128 * (P + NEW / 2)
     ach = (weight_bytes + kv_bytes) / (dec_ms * 1e-3) / 1e9
     total_tok = NEW * world * args.steps
-    return {
+    res = {
         "metric": "tokens/sec LLaMA-13B prefill+decode", "value": round(total_tok / (ms * 1e-3), 1), "unit": "tokens/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"llama13b_decode: random-init h5120/L40/H40/FFN13824/V40194, B=1, {P}-token prompt with 4 "
-                               f"image spans, {NEW} greedy tokens (1 prefill + {NEW - 1} cached decode forwards)",
-                   "global_batch": world, "seq_len": P + NEW,
-                   "parallelism": f"dp{world} (independent replicas, no collective)",
-                   "l2": "26 GB of weights stream from HBM every token (207x the L2)", "gemm_cta_group": args.ctas or 1},
+        "config": workload_config(args, world),
+        "kernel_options": {"gemm_cta_group": args.ctas or 1, "decode_step": "CUDA graph replay" if used_graph == 1 else "eager launches"},
         "clocks": clocks,
         "e2e": {"value": round(total_tok / (ms_e2e * 1e-3), 1), "unit": "tokens/s", "h2d_bytes_per_step": P * 8,
                 "d2h_bytes_per_step": (P + NEW) * 8,
                 "api": "models.llama_xformer.LlamaForCausalLM.generate(pinned ids.to(cuda), max_new_tokens) -> seq.cpu()"},
         "gpu_launches": int(launches) * args.steps,
-        "roofline": {"kernel": "sb::gemv_kernel (whole cached decode forward)", "bound": "hbm", "achieved": round(ach, 1),
+        "roofline": {"kernel": "sb::gemv_kernel (whole cached decode step incl. sampler)", "bound": "hbm", "achieved": round(ach, 1),
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None,
                      "peak_source": peaks["source"], "decode_ms_per_token": round(dec_ms, 4),
+                     "prefill_ms": round(prefill_ms, 3),
                      "algorithmic_bytes_per_token": int(weight_bytes + kv_bytes)},
         "cpu_baseline": None,
     }
+    if rank_ms is not None:
+        res["per_rank_ms_per_step"] = rank_ms
+    del model
+    torch.cuda.empty_cache()
+    return res
 
 
 def preprocess_arm(args, world, rank, local):
@@ -541,9 +603,7 @@ def preprocess_arm(args, world, rank, local):
         "metric": "images/sec preprocess (resize+normalise)", "value": round(total / (ms * 1e-3), 1), "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"preprocess_b{B}: uint8 {H}x{W}x3 -> Pillow-exact bicubic 224x224 -> CLIP normalise -> fp16",
-                   "global_batch": B * world, "parallelism": f"dp{world}",
-                   "l2": f"inputs {B * H * W * 3 / 1e6:.0f} MB per step (> L2 at B=256)"},
+        "config": workload_config(args, world),
         "clocks": clocks,
         "e2e": {"value": round(total / (ms_e2e * 1e-3), 1), "unit": "images/s", "h2d_bytes_per_step": B * world * H * W * 3,
                 "d2h_bytes_per_step": 4 * world, "api": "seed_b200.lib.Preprocess(pinned uint8.to(cuda)) -> checksum.cpu()"},
@@ -555,15 +615,14 @@ def preprocess_arm(args, world, rank, local):
     }
 
 
-def llama_arm(args, world, rank, local):
-    from transformers.models.llama.configuration_llama import LlamaConfig
-
-    from models.llama_xformer import LlamaForCausalLM
+def llama_arm(args, world, rank, local, keep=None):
     from seed_b200 import lib as L, synth
 
     dev = torch.device("cuda", local)
     h, nl, nh, ffn, V, S = 4096, 32, 32, 11008, 40194, args.seq
     model = random_llama(dev, rank, h, nl, nh, ffn, V, S, args.ctas)
+    if keep is not None:
+        keep["llama7b"] = model
     ids_host = synth.prompt_ids(1, S, 1, seed=77 + rank).pin_memory()
     ids = ids_host.to(dev)
     out = {}
@@ -579,6 +638,7 @@ def llama_arm(args, world, rank, local):
     L.reset_launch_count()
     with ClockSampler(local) as cs:
         ms = timed(step_device, args.steps, args.warmup, world)
+    rank_ms = per_rank_stats(LAST_LOCAL_MS[0] / args.steps, world)
     launches = L.launch_count() // (args.steps + args.warmup)
     clocks = cs.summary()
     ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup), world)
@@ -592,17 +652,14 @@ def llama_arm(args, world, rank, local):
     if rank == 0 and world == 1 and not args.no_cpu:
         import copy
 
-        a2 = copy.copy(args); a2.steps, a2.warmup = 1, 1
+        a2 = copy.copy(args); a2.steps, a2.warmup, a2.workload = 1, 1, "llama_prefill"
         r = reference_arm(a2, 1, 0)
         cpu = {"value": round(r["value"], 2), "unit": r["unit"], "cores": r["cores"], "kind": "port", "sample": r["sample"]}
-    return {
+    res = {
         "metric": "tokens/sec LLaMA-7B prefill", "value": round(total_tok / (ms * 1e-3), 1), "unit": "tokens/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"llama7b_prefill: random-init h4096/L32/H32/FFN11008/V40194, B=1, S={S} incl. one "
-                               f"34-token image span, logits for all positions", "global_batch": world, "seq_len": S,
-                   "parallelism": f"dp{world} (independent replicas, no collective)",
-                   "l2": "13.5 GB of weights stream through L2 every step", "gemm_cta_group": args.ctas or 1},
+        "config": workload_config(args, world), "kernel_options": {"gemm_cta_group": args.ctas or 1},
         "clocks": clocks,
         "e2e": {"value": round(total_tok / (ms_e2e * 1e-3), 1), "unit": "tokens/s", "h2d_bytes_per_step": S * 8,
                 "d2h_bytes_per_step": V * 4,
@@ -617,6 +674,89 @@ def llama_arm(args, world, rank, local):
                      "whole_step_tflops": round((lin_flops + attn_flops) / (ms / args.steps * 1e-3) / 1e12, 1)},
         "cpu_baseline": cpu,
     }
+    if rank_ms is not None:
+        res["per_rank_ms_per_step"] = rank_ms
+    return res
+
+
+def pipeline_arm(args, world, rank, local, tok=None, model=None):
+    """BASELINE.json config #4 as one device-resident chain: every rank encodes its 256 images, ONE NCCL all-gather
+    hands all ids to every rank, the id -> token arithmetic writes 60 `<img>`+32 ids+`</img>` spans (of the gathered
+    images, rank r takes images [60 r, 60 r + 60)) between text tokens of an S=2048 prompt, and the rank's LLaMA-7B
+    replica prefills it.  No id touches the host (scripts/seed_llama_inference_8B.py:94-103 does a string round trip)."""
+    from models.seed_llama_tokenizer import ImageTokenizer, SeedImageTokenMixin, all_gather_ids
+    from seed_b200 import lib as L, synth
+
+    B, S = args.batch, args.seq
+    dev = torch.device("cuda", local)
+    if tok is None:
+        tok = ImageTokenizer(model_path=synth.encoder_state_dict(VIT_DEPTH, QF_LAYERS, 0), device=dev, fp16=True,
+                             max_batch=B, gemm_ctas=args.ctas)
+    if model is None:
+        model = random_llama(dev, rank, 4096, 32, 32, 11008, 40194, S, args.ctas)
+    n_span = min(60, (S - 8) // 34, B * world)
+    host = synth.images(B, seed=1000 + rank).half().pin_memory()
+    text_host = torch.randint(0, 32000, (1, S), generator=torch.Generator().manual_seed(5 + rank)).pin_memory()
+    x, text = host.to(dev), text_host.to(dev)
+    out = {}
+
+    def chain(images, prompt):
+        ids = tok.encode(images)                                   # [B,32] int64 on the device
+        if world > 1:
+            ids = all_gather_ids(ids)                              # [world*B,32] on every rank
+        first = (rank * n_span) % max(1, ids.shape[0] - n_span + 1)
+        spans = prompt[0, 8:8 + n_span * 34].view(n_span, 34)
+        SeedImageTokenMixin.image_ids_to_tokens(ids[first:first + n_span], 32000, out=spans)
+        return model.forward(input_ids=prompt, use_cache=False, last_logits_only=True)
+
+    def step_device():
+        out["o"] = chain(x, text)
+
+    def step_e2e():
+        o = chain(host.to(dev, non_blocking=True), text_host.to(dev, non_blocking=True))
+        out["last"] = o.logits[:, -1].float().cpu()
+
+    step_device(); torch.cuda.synchronize()
+    L.reset_launch_count()
+    with ClockSampler(local) as cs:
+        ms = timed(step_device, args.steps, args.warmup, world)
+    rank_ms = per_rank_stats(LAST_LOCAL_MS[0] / args.steps, world)
+    launches = L.launch_count() // (args.steps + args.warmup)
+    clocks = cs.summary()
+    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup), world)
+    step_s, e2e_s = ms / args.steps * 1e-3, ms_e2e / args.steps * 1e-3
+    flops = ENCODE_FLOPS_PER_IMAGE * B + 2.0 * S * 32 * (4 * 4096 * 4096 + 3 * 4096 * 11008) + 2.0 * 4096 * 40194 \
+        + 32 * 4.0 * 32 * S * S * 128 * 0.5
+    peaks = measured_peaks()
+    res = {
+        "metric": "images/sec SEED encode+VQ feeding one LLaMA-7B prefill per rank", "value": round(B * world / step_s, 2),
+        "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic", "config": workload_config(args, world),
+        "prefill_tokens_per_s": round(S * world / step_s, 1), "image_spans_per_prompt": n_span,
+        "clocks": clocks,
+        "e2e": {"value": round(B * world / e2e_s, 2), "unit": "images/s",
+                "h2d_bytes_per_step": world * (B * 3 * 224 * 224 * 2 + S * 8), "d2h_bytes_per_step": world * 40194 * 4,
+                "api": "ImageTokenizer.encode(pinned.to(cuda)) -> all_gather_ids -> image_ids_to_tokens(out=prompt span) "
+                       "-> LlamaForCausalLM.forward(last_logits_only) -> logits.cpu()"},
+        "gpu_launches": int(launches) * args.steps,
+        "roofline": {"kernel": "whole chain (tcgen05 GEMMs dominate)", "bound": "tensor",
+                     "achieved": round(flops / step_s / 1e12, 1), "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": round(flops / step_s / 1e12 / peaks["tflops_sustained"], 4), "traffic": None,
+                     "peak_source": peaks["source"]},
+        "cpu_baseline": None,
+    }
+    if rank_ms is not None:
+        res["per_rank_ms_per_step"] = rank_ms
+    return res
+
+
+def compact(r):
+    """a secondary record: the same fields as a full line minus the boilerplate"""
+    keep = ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "config", "kernel_options", "clocks", "e2e",
+            "gpu_launches", "roofline", "cpu_baseline", "per_rank_ms_per_step", "prefill_tokens_per_s",
+            "image_spans_per_prompt")
+    return {k: r[k] for k in keep if k in r and r[k] is not None}
 
 
 def main():
@@ -625,7 +765,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="seedb200", choices=["seedb200", "reference"])
-    ap.add_argument("--workload", default="encode", choices=["encode", "llama_prefill", "llama_decode", "preprocess"])
+    ap.add_argument("--workload", default="encode",
+                    choices=["encode", "llama_prefill", "llama_decode", "pipeline", "preprocess"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (encode)")
     ap.add_argument("--seq", type=int, default=2048, help="prompt length (llama_prefill)")
     ap.add_argument("--prompt", type=int, default=256, help="prompt length (llama_decode)")
@@ -634,6 +775,8 @@ def main():
     ap.add_argument("--vq", default="fp16", choices=["fp16", "fp32"], help="VQ distance arithmetic")
     ap.add_argument("--cpu-images", type=int, default=0, help="images timed by the cpu_baseline leg (0 = ~20 s worth)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="encode workload only: skip the LLaMA half of BASELINE.json's metric (secondary records)")
     ap.add_argument("--ref-seconds", type=float, default=150.0, help="wall-clock budget of the --impl reference run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "seedb200" else args.warmup
@@ -648,8 +791,9 @@ def main():
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(r["ms_per_step"], 2), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": r["workload"], "note": "reference algorithm on the host CPU (oracle port of "
-                           "/root/reference, pinned by tests/golden); no GPU involved"},
+                "config": workload_config(args, max(world, args.gpus)),
+                "note": "reference algorithm on the host CPU (oracle port of /root/reference, pinned by tests/golden); "
+                        "no GPU involved; every step is a BOUNDED SAMPLE of the workload: " + r["sample"],
                 "cpu_baseline": {"value": round(r["value"], 3), "unit": r["unit"], "cores": r["cores"], "kind": "port",
                                  "sample": r["sample"]},
                 "e2e": {"value": round(r["value"], 3), "unit": r["unit"], "h2d_bytes_per_step": 0,
@@ -660,8 +804,35 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the seedb200 arm has no CPU fallback; use --impl reference)")
     world, rank, local = dist_setup(args.gpus)
-    arm = {"encode": encode_arm, "llama_prefill": llama_arm, "llama_decode": llama_decode_arm, "preprocess": preprocess_arm}[args.workload]
-    res = arm(args, world, rank, local)
+    if args.workload == "encode":
+        # headline: images/s through encode -> VQ.  BASELINE.json's metric has a second half (tokens/s through
+        # llama_xformer: 7B prefill, config #3; 13B prefill + 128-step decode, config #5) and a chained config (#4):
+        # they ride in the same line as `secondary` records, measured by the same rules at the same N.
+        import copy
+
+        keep = {}
+        res = encode_arm(args, world, rank, local, keep=keep)
+        if not args.no_secondary:
+            sec = {}
+            a2 = copy.copy(args)
+            a2.workload, a2.steps = "llama_prefill", min(args.steps, 10)
+            sec["llama_prefill"] = compact(llama_arm(a2, world, rank, local, keep=keep))
+            a3 = copy.copy(args)
+            a3.workload, a3.steps = "pipeline", min(args.steps, 5)
+            sec["pipeline"] = compact(pipeline_arm(a3, world, rank, local, tok=keep["tok"], model=keep["llama7b"]))
+            keep.clear()
+            import gc
+
+            gc.collect()
+            torch.cuda.empty_cache()
+            a4 = copy.copy(args)
+            a4.workload, a4.steps = "llama_decode", min(args.steps, 3)
+            sec["llama_decode"] = compact(llama_decode_arm(a4, world, rank, local))
+            res["secondary"] = sec
+    else:
+        arm = {"llama_prefill": llama_arm, "llama_decode": llama_decode_arm, "pipeline": pipeline_arm,
+               "preprocess": preprocess_arm}[args.workload]
+        res = arm(args, world, rank, local)
     if world > 1:
         import torch.distributed as dist
 

@@ -230,6 +230,7 @@ class LlamaForCausalLM(nn.Module):
                 raise ValueError(f"prompt of {S} tokens leaves no room in max_seq={self.max_seq}")
         eos = eos_token_id if eos_token_id is not None else getattr(self.config, "eos_token_id", None)
         eos_list = list(eos) if isinstance(eos, (list, tuple)) else ([eos] if eos is not None else [])
+        eos_list = [int(e) for e in eos_list if int(e) >= 0]      # a negative id disables the stop (fixed-length runs)
         pad = pad_token_id if pad_token_id is not None else (eos_list[0] if eos_list else 0)
         rng_seed = self._next_seed(generator, seed)
         offset = self._draws
@@ -270,13 +271,13 @@ class LlamaForCausalLM(nn.Module):
 
 
 def get_pretrained_llama_causal_model(pretrained_model_name_or_path=None, torch_dtype="fp16", **kwargs):
-    """models/model_tools.py:5-18."""
+    """models/model_tools.py:5-18.  Like the reference, anything that is not one of the four dtype strings passes
+    through unchanged (its `else: torch_dtype == torch.float32` is a no-op comparison), which is what lets
+    scripts/seed_llama_inference_8B.py:77 call it with `torch_dtype=torch.float16`."""
     if torch_dtype in ("fp16", "float16"):
         torch_dtype = torch.float16
     elif torch_dtype in ("bf16", "bfloat16"):
         torch_dtype = torch.bfloat16
-    else:
-        torch_dtype = torch.float32
     kwargs.pop("low_cpu_mem_usage", None)
     return LlamaForCausalLM.from_pretrained(pretrained_model_name_or_path=pretrained_model_name_or_path,
                                             torch_dtype=torch_dtype, **kwargs)

@@ -36,3 +36,20 @@ def test_seedb200_arm_has_no_cpu_fallback():
     p = run(["--steps", "1", "--warmup", "1", "--no-cpu"], timeout=300)
     assert p.returncode != 0
     assert "no CUDA device" in (p.stderr + p.stdout)
+
+
+def test_both_arms_name_the_same_workload():
+    """the driver compares the two arms' `config`: it must be the same object key for key at every N"""
+    import argparse
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(REPO, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for wl in ("encode", "llama_prefill", "llama_decode", "pipeline", "preprocess"):
+        a = argparse.Namespace(workload=wl, batch=256, vq="fp16", seq=2048, prompt=256, new_tokens=128)
+        for world in (1, 8):
+            c1, c2 = bench.workload_config(a, world), bench.workload_config(a, world)
+            assert c1 == c2 and c1["workload"] and c1["global_batch"] >= world
+    src = open(os.path.join(REPO, "bench.py")).read()
+    assert src.count('"config": workload_config(') >= 6      # every arm, product and reference, goes through it

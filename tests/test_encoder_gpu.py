@@ -159,3 +159,24 @@ def test_image_tokenizer_mirror_api_and_errors():
         t.encode_image()
     assert torch.equal(t.encode_image(image_torch=img.cuda()), ids)
     assert t.num_image_tokens == 8192
+
+
+def test_encode_is_cuda_graph_capturable():
+    """seedb200.h: "no hidden synchronisation and no allocation after *_create (so an encode / forward call is
+    CUDA-graph capturable)" -- capture one encode() with torch's CUDA-graph machinery, replay it on new pixels, and
+    compare with eager launches bit for bit (ids and z)."""
+    sd = synth.encoder_state_dict(2, 2, 1)
+    model = make_model(sd, max_batch=4, vq_mode=1)
+    x_static = synth.images(4, seed=81).half().cuda()
+    model.encode_ids(x_static)                                   # warm-up: lazily-set function attributes
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ids_g, z_g = model.encode_ids(x_static, return_z=True)
+    for seed in (82, 83):
+        x_new = synth.images(4, seed=seed).half().cuda()
+        ids_e, z_e = model.encode_ids(x_new, return_z=True)
+        x_static.copy_(x_new)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(ids_g, ids_e) and torch.equal(z_g, z_e)

@@ -112,3 +112,150 @@ def test_generate_greedy_matches_oracle_rollout():
     s2 = model.generate(input_ids=ids.cuda(), max_new_tokens=4, do_sample=True, top_p=0.5, temperature=1.0,
                         generator=torch.Generator(device="cuda").manual_seed(0))
     assert tuple(s2.shape) == (1, 44) and int(s2.max()) < vocab
+
+
+# --------------------------------------------------------------------------------------------------
+# parity at the BENCH dimensions (BASELINE.json configs #3 / #5), layer-truncated so the CPU oracle stays cheap:
+# every GEMM / GEMV / attention shape of the 7B and 13B steps is exercised inside the model, against
+# oracle/restatement.py (fp32) on the same seeded weights
+# --------------------------------------------------------------------------------------------------
+def _greedy_agree(gpu_logits, ref_logits, gap=5e-2):
+    """greedy ids equal wherever the oracle's top-2 logit gap exceeds `gap`; returns (#compared, #positions)."""
+    top2 = ref_logits.float().topk(2, dim=-1).values
+    sure = (top2[..., 0] - top2[..., 1]) > gap
+    same = gpu_logits.float().cpu().argmax(-1) == ref_logits.argmax(-1)
+    assert bool((same | ~sure).all()), f"{int((~same & sure).sum())} greedy ids differ above the {gap} gap"
+    return int(sure.sum()), sure.numel()
+
+
+def test_llama7b_dims_prefill_s2048_matches_oracle():
+    """config #3 shapes: h=4096, 32 heads, ffn=11008, V=40194 (rows 4-byte aligned -> padded stride), S=2048 with an
+    image span; 2 of the 32 layers.  K = 4096 and 11008 GEMMs, BN=256 SiLU-gate tiles, causal tcgen05 attention at
+    2048 x 2048, lm_head over all positions (llama_xformer.py:661-743)."""
+    hidden, layers, heads, ffn, vocab, S = 4096, 2, 32, 11008, 40194, 2048
+    model, sd = make(hidden, layers, heads, ffn, vocab, seed=31, max_batch=1, max_seq=S, ctas=2)
+    ids = synth.prompt_ids(1, S, n_image_spans=1, seed=32)
+    with torch.no_grad():
+        ref_logits, ref_hidden, _ = R.llama_forward(sd, ids, heads, layers)
+    out = model(input_ids=ids.cuda(), use_cache=True)
+    torch.cuda.synchronize()
+    assert tuple(out.logits.shape) == (1, S, vocab) and out.logits.dtype == torch.float16
+    assert out.logits.stride(1) % 8 == 0                      # padded row stride, [..., :V] view
+    assert rel(out.logits, ref_logits) <= LOGIT_TOL, rel(out.logits, ref_logits)
+    assert rel(model._llm.tap_hidden(S), ref_hidden[0]) <= 5e-3
+    n_sure, n = _greedy_agree(out.logits, ref_logits)
+    assert n_sure > n // 2
+    # worst single position, not just the Frobenius average
+    per_pos = (out.logits.float().cpu() - ref_logits).norm(dim=-1) / ref_logits.norm(dim=-1)
+    assert per_pos.max().item() <= 3 * LOGIT_TOL, per_pos.max().item()
+
+
+def test_llama13b_dims_prefill_and_cached_decode_match_oracle():
+    """config #5 shapes: h=5120, 40 heads, ffn=13824, V=40194; a 256-token prompt with 4 image spans, then 8 cached
+    decode steps fed the oracle's greedy tokens (so both sides see the same inputs): GEMV at (15360,5120),
+    (27648,5120), (5120,13824), (5120,5120), (40194,5120), decode attention over 257..264 keys, RMSNorm fused into
+    the GEMV staging, RoPE at positions 256..263 (llama_xformer.py:212-263,745-776)."""
+    hidden, layers, heads, ffn, vocab, P, steps = 5120, 2, 40, 13824, 40194, 256, 8
+    model, sd = make(hidden, layers, heads, ffn, vocab, seed=41, max_batch=1, max_seq=P + steps + 8, ctas=2)
+    ids = synth.prompt_ids(1, P, n_image_spans=4, seed=42)
+    with torch.no_grad():
+        ref_logits, _, ref_past = R.llama_forward(sd, ids, heads, layers)
+    out = model(input_ids=ids.cuda(), use_cache=True)
+    assert rel(out.logits, ref_logits) <= LOGIT_TOL, rel(out.logits, ref_logits)
+    _greedy_agree(out.logits[:, -1:], ref_logits[:, -1:])
+    past = out.past_key_values
+    worst = 0.0
+    for t in range(steps):
+        nxt = ref_logits[:, -1].argmax(-1, keepdim=True)
+        with torch.no_grad():
+            ref_logits, _, ref_past = R.llama_forward(sd, nxt, heads, layers, past=ref_past)
+        o = model(input_ids=nxt.cuda(), past_key_values=past, use_cache=True)
+        past = o.past_key_values
+        assert tuple(o.logits.shape) == (1, 1, vocab)
+        e = rel(o.logits, ref_logits)
+        worst = max(worst, e)
+        assert e <= LOGIT_TOL, (t, e)
+        _greedy_agree(o.logits, ref_logits)
+    # the cache holds what the oracle holds (K post-RoPE), all P + steps rows
+    k_gpu, v_gpu = past[1]
+    assert k_gpu.shape[2] == P + steps
+    assert rel(k_gpu, ref_past[1][0]) <= 5e-3 and rel(v_gpu, ref_past[1][1]) <= 5e-3
+
+
+# --------------------------------------------------------------------------------------------------
+# device-resident generation loop (seedb200_llama_generate): sampler + graph-replayed decode steps
+# --------------------------------------------------------------------------------------------------
+def test_generate_device_loop_graph_equals_eager_equals_python_loop():
+    hidden, layers, heads, ffn, vocab = 512, 2, 4, 1408, 1056
+    model, sd = make(hidden, layers, heads, ffn, vocab, seed=9, max_batch=2, max_seq=160)
+    ids = synth.prompt_ids(2, 40, n_image_spans=1, text_vocab=vocab - 66, n_codes=64, seed=10).cuda()
+    new = 24
+    for kw in (dict(do_sample=False), dict(do_sample=True, top_p=0.5, temperature=1.0, seed=77)):
+        model._draws = 0
+        kw["eos_token_id"] = -1                            # fixed length (LlamaConfig's default eos id is 2)
+        a = model.generate(input_ids=ids, max_new_tokens=new, use_graph=True, **kw)
+        assert model._llm.used_graph == 1                  # the decode step really was a replayed CUDA graph
+        model._draws = 0
+        b = model.generate(input_ids=ids, max_new_tokens=new, use_graph=False, **kw)
+        assert model._llm.used_graph == 0
+        model._draws = 0
+        c = model.generate(input_ids=ids, max_new_tokens=new, device_loop=False, **kw)   # forward() per token from Python
+        assert tuple(a.shape) == (2, 40 + new) and torch.equal(a[:, :40], ids)
+        assert torch.equal(a, b), "graph replay differs from eager launches"
+        assert torch.equal(a, c), "device loop differs from the per-token Python loop"
+        assert int(a.max()) < vocab and int(a.min()) >= 0
+    # a second call replays the cached graph with new parameters (prompt length, seed): still equals eager
+    ids2 = synth.prompt_ids(2, 57, n_image_spans=1, text_vocab=vocab - 66, n_codes=64, seed=11).cuda()
+    model._draws = 5
+    a = model.generate(input_ids=ids2, max_new_tokens=16, do_sample=True, top_p=0.9, seed=3, use_graph=True, eos_token_id=-1)
+    model._draws = 5
+    b = model.generate(input_ids=ids2, max_new_tokens=16, do_sample=True, top_p=0.9, seed=3, use_graph=False, eos_token_id=-1)
+    assert torch.equal(a, b)
+    # successive calls draw from different Philox counters
+    n1 = model.generate(input_ids=ids2, max_new_tokens=16, do_sample=True, top_p=0.95, temperature=1.5, seed=3, eos_token_id=-1)
+    n2 = model.generate(input_ids=ids2, max_new_tokens=16, do_sample=True, top_p=0.95, temperature=1.5, seed=3, eos_token_id=-1)
+    assert not torch.equal(n1, n2)
+
+
+def test_generate_device_loop_eos_and_padding_semantics():
+    """HF semantics: a sequence that emitted eos keeps emitting pad; generation stops once every sequence has
+    finished, and the step that produced the last eos is kept."""
+    hidden, layers, heads, ffn, vocab = 512, 2, 4, 1408, 1056
+    model, sd = make(hidden, layers, heads, ffn, vocab, seed=9, max_batch=2, max_seq=200)
+    ids = synth.prompt_ids(2, 40, n_image_spans=1, text_vocab=vocab - 66, n_codes=64, seed=10).cuda()
+    free = model.generate(input_ids=ids, max_new_tokens=80, do_sample=False, eos_token_id=-1)[:, 40:]
+    # choose as "eos" the token sequence 0 emits at step 5 (and make sure sequence 1 emits it later or never)
+    eos = int(free[0, 5])
+    first = [int((free[b] == eos).nonzero()[0]) if bool((free[b] == eos).any()) else None for b in range(2)]
+    pad = 1055
+    got = model.generate(input_ids=ids, max_new_tokens=80, do_sample=False, eos_token_id=eos, pad_token_id=pad)[:, 40:]
+    ref = model.generate(input_ids=ids, max_new_tokens=80, do_sample=False, eos_token_id=eos, pad_token_id=pad,
+                         device_loop=False)[:, 40:]
+    assert torch.equal(got, ref), (got.shape, ref.shape)
+    for b in range(2):
+        if first[b] is not None and first[b] + 1 < got.shape[1]:
+            assert int(got[b, first[b]]) == eos and bool((got[b, first[b] + 1:] == pad).all())
+    if all(f is not None for f in first):
+        assert got.shape[1] == max(first) + 1
+
+
+def test_cached_decode_forward_is_cuda_graph_capturable():
+    """the C ABI promises "no allocation, no hidden sync after *_create": capture a cached q_len-1 forward with
+    torch's CUDA graph machinery and replay it bit-identically (fresh logits buffer each replay)."""
+    hidden, layers, heads, ffn, vocab = 512, 2, 4, 1408, 1056
+    model, sd = make(hidden, layers, heads, ffn, vocab, seed=9, max_batch=1, max_seq=128)
+    ids = synth.prompt_ids(1, 40, n_image_spans=1, text_vocab=vocab - 66, n_codes=64, seed=10).cuda()
+    out = model(input_ids=ids, use_cache=True)
+    nxt = out.logits[:, -1].float().argmax(-1, keepdim=True)
+    eager = model._llm.forward(input_ids=nxt, past_len=40, last_only=True).clone()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        captured = model._llm.forward(input_ids=nxt, past_len=40, last_only=True)
+    captured.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured, eager)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured, eager)

@@ -374,3 +374,138 @@ def test_rope_kv_append(lib, B, S, H, past):
     kc2 = torch.zeros_like(kc); vc2 = torch.zeros_like(vc)
     q2 = lib.rope_kv_append(qkv, None, B, S, H, D, past, kc2, vc2)
     assert torch.equal(q2, q_out) and torch.equal(kc2, kc)
+
+
+# ----------------------------------------------------------------------------------------------
+# decode-step kernels at the LLaMA-13B / 7B bench shapes (seedb200_gemv, seedb200_decode_attention)
+# ----------------------------------------------------------------------------------------------
+GEMV_SHAPES = [
+    # M, N, K, what
+    (1, 15360, 5120, "13B fused qkv"),
+    (1, 5120, 5120, "13B o_proj"),
+    (1, 5120, 13824, "13B down_proj"),
+    (1, 40194, 5120, "13B lm_head (odd N: last row pair is a single row)"),
+    (1, 12288, 4096, "7B fused qkv"),
+    (1, 4096, 11008, "7B down_proj"),
+    (4, 5120, 13824, "4 activation rows"),
+    (3, 1000, 264, "tails: N not a multiple of the CTA's 8 row pairs, K < one warp pass"),
+]
+
+
+@pytest.mark.parametrize("M,N,K,what", GEMV_SHAPES)
+@pytest.mark.parametrize("variant", ["plain", "residual", "rmsnorm"])
+def test_gemv_decode_shapes(lib, M, N, K, what, variant):
+    """y = x W^T (+ residual) with the fp16 rounding points of nn.Linear on fp16 tensors (llama_xformer.py:223-225,
+    258,718); `rmsnorm`: LlamaRMSNorm fused into the activation staging (llama_xformer.py:105-113)."""
+    x = rand16(M, K, seed=11)
+    w = rand16(N, K, scale=K ** -0.5, seed=12)
+    res = rand16(M, N, seed=13) if variant == "residual" else None
+    nw = (1.0 + 0.1 * torch.randn(K, generator=torch.Generator().manual_seed(14))).half().to(DEV) if variant == "rmsnorm" else None
+    out = lib.gemv(x, w, residual=res, norm_w=nw, eps=1e-6)
+    xin = R.rmsnorm_ref(x, nw, 1e-6) if nw is not None else x
+    ref = R.linear_ref(xin, w, residual=res)
+    mags = [R.linear_ref(xin, w)] if res is not None else []
+    assert_close16(out, ref, mags=mags, ulps=2.0, what=f"gemv {what} {variant}")
+
+
+@pytest.mark.parametrize("M,ffn,K", [(1, 13824, 5120), (1, 11008, 4096), (2, 256, 512)])
+def test_gemv_silu_gate(lib, M, ffn, K):
+    """LlamaMLP.forward (llama_xformer.py:186): silu(gate_proj(x)) * up_proj(x) over the interleaved [128 gate | 128 up]
+    weight, RMSNorm fused (the decode form of post_attention_layernorm + MLP input)."""
+    x = rand16(M, K, seed=21)
+    wg = rand16(ffn, K, scale=K ** -0.5, seed=22)
+    wu = rand16(ffn, K, scale=K ** -0.5, seed=23)
+    nw = (1.0 + 0.1 * torch.randn(K, generator=torch.Generator().manual_seed(24))).half().to(DEV)
+    out = lib.gemv(x, R.interleave_gate_up(wg, wu), norm_w=nw, eps=1e-6, mode=1)
+    xin = R.rmsnorm_ref(x, nw, 1e-6)
+    ref = R.silu_gate_ref(xin, wg, wu)
+    g = R.linear_ref(xin, wg).float()
+    u = R.linear_ref(xin, wu).float()
+    # a 1-ulp flip of fp16(gate) or fp16(up) moves the product by ~ulp(g)*|u| or ulp(u)*|s|
+    assert_close16(out, ref, mags=[g.abs() * u.abs(), u], ulps=3.0, what="gemv silu-gate")
+
+
+@pytest.mark.parametrize("B,H,kv_len,max_seq", [(1, 40, 257, 392), (1, 40, 300, 392), (1, 32, 1024, 1024),
+                                                (2, 8, 1, 64), (1, 4, 128, 128), (1, 4, 129, 8300), (1, 2, 8200, 8300)])
+def test_decode_attention_cache_lengths(lib, B, H, kv_len, max_seq):
+    """one query token against the first kv_len rows of a [B,H,max_seq,128] cache, no mask
+    (llama_xformer.py:240-256 with attn_bias=None); fp32 softmax, fp16 output."""
+    D = 128
+    q = rand16(B, H, D, seed=31)
+    kc = rand16(B, H, max_seq, D, seed=32)
+    vc = rand16(B, H, max_seq, D, seed=33)
+    scale = D ** -0.5
+    out = lib.decode_attention(q, kc, vc, kv_len, scale)
+    ref = R.attention_ref(q[:, :, None, :], kc[:, :, :kv_len], vc[:, :, :kv_len], scale)     # [B,1,H,D]
+    assert_close16(out.view(B, H, D), ref.view(B, H, D), ulps=2.0, atol=2e-4, what=f"decode attention kv={kv_len}")
+
+
+# ----------------------------------------------------------------------------------------------
+# token side of the generation loop: sampler and id -> token arithmetic
+# ----------------------------------------------------------------------------------------------
+def test_sampler_greedy_is_torch_argmax(lib):
+    g = torch.Generator().manual_seed(5)
+    logits = (torch.randn(4, 40194, generator=g) * 2).half()
+    logits[1, 777] = logits[1].max() + 1
+    logits[1, 30000] = logits[1, 777]                 # tie: the lowest index wins (torch.argmax)
+    logits[2, :] = 0.0                                # all equal -> 0
+    logits[3, 40193] = 100.0                          # last column
+    pad = torch.zeros(4, 40200, dtype=torch.float16)  # padded row stride, as the generate loop uses
+    pad[:, :40194] = logits
+    got = lib.sample(pad.to(DEV)[:, :40194])
+    assert got.dtype == torch.int64
+    assert got.cpu().tolist() == [int(logits[0].float().argmax()), 777, 0, 40193]
+
+
+@pytest.mark.parametrize("V,T,P", [(40194, 1.0, 0.5), (40194, 0.7, 0.9), (1000, 1.3, 0.05), (50, 1.0, 1.0), (5120, 1.0, 0.999)])
+def test_sampler_matches_oracle_draw_by_draw(lib, V, T, P):
+    """temperature / top-p / inverse-CDF draw vs oracle/sampler_oracle.py (HF TemperatureLogitsWarper +
+    TopPLogitsWarper semantics, pinned to transformers on the CPU side); same Philox uniforms.  A draw whose uniform
+    lands within 1e-5 of a CDF edge, or a nucleus whose boundary token is within 1e-6 of the threshold, may differ
+    by fp32 summation order and is excluded (counted)."""
+    from oracle import sampler_oracle as S
+
+    g = torch.Generator().manual_seed(V + int(P * 1000))
+    B = 64
+    logits = (torch.randn(B, V, generator=g) * 3.0).half()
+    seed, offset, step = 0x1234ABCD5678, 1000, 7
+    got = lib.sample(logits.to(DEV), do_sample=True, temperature=T, top_p=P, seed=seed, offset=offset, step=step).cpu()
+    checked = 0
+    for b in range(B):
+        tok, dmargin, nmargin = S.sample_ref(logits[b].float().numpy(), True, T, P, seed, offset, step, b)
+        if dmargin < 1e-5 or nmargin < 1e-6:
+            continue
+        checked += 1
+        assert int(got[b]) == tok, (b, int(got[b]), tok, dmargin, nmargin)
+    assert checked >= B - 4
+
+
+def test_sampler_distribution_and_nucleus(lib):
+    """4096 sequences with identical logits draw independently (Philox counter = row): sampled tokens stay inside
+    HF's nucleus and their frequencies match the warped distribution."""
+    from oracle import sampler_oracle as S
+
+    V, T, P, B = 40, 0.9, 0.8, 4096
+    base = (torch.randn(V, generator=torch.Generator().manual_seed(9)) * 2.0).half()
+    logits = base[None].expand(B, V).contiguous()
+    got = lib.sample(logits.to(DEV), do_sample=True, temperature=T, top_p=P, seed=42, offset=0, step=0).cpu()
+    q, keep, _ = S.warp(base.float().numpy(), T, P)
+    assert keep[got.numpy()].all()
+    freq = np.bincount(got.numpy(), minlength=V) / B
+    assert np.abs(freq - q).max() < 4.0 * np.sqrt(q.max() * (1 - q.max()) / B) + 1e-3, np.abs(freq - q).max()
+    # another step -> another draw; same (seed, offset, step) -> the same draw
+    again = lib.sample(logits.to(DEV), do_sample=True, temperature=T, top_p=P, seed=42, offset=0, step=0).cpu()
+    other = lib.sample(logits.to(DEV), do_sample=True, temperature=T, top_p=P, seed=42, offset=0, step=1).cpu()
+    assert torch.equal(again, got) and not torch.equal(other, got)
+
+
+def test_image_ids_to_tokens_kernel(lib):
+    """scripts/seed_llama_inference_8B.py:16-23,60,98-100: '<img>' + '<img_%05d>' x 32 + '</img>' as id arithmetic."""
+    ids = torch.randint(0, 8192, (5, 32), generator=torch.Generator().manual_seed(1))
+    toks = lib.image_ids_to_tokens(ids.to(DEV), 32000, 40192, 40193).cpu()
+    assert tuple(toks.shape) == (5, 34)
+    assert (toks[:, 0] == 40192).all() and (toks[:, 33] == 40193).all() and torch.equal(toks[:, 1:33], ids + 32000)
+    # spans written straight into a prompt buffer (row stride 40)
+    buf = torch.full((5, 40), -1, dtype=torch.int64, device=DEV)
+    lib.image_ids_to_tokens(ids.to(DEV), 32000, 40192, 40193, out=buf)
+    assert torch.equal(buf[:, :34].cpu(), toks) and (buf[:, 34:] == -1).all()

@@ -181,3 +181,45 @@ def test_resize_oracle_matches_pillow(h, w, filt):
     rc = lib.resize_oracle_u8(img.ctypes.data_as(C.c_void_p), h, w, 224, 224, filt, out.ctypes.data_as(C.c_void_p))
     assert rc == 0
     assert np.array_equal(out, ref)
+
+
+# --------------------------------------------------------------------------------------------------
+# sampler oracle (oracle/sampler_oracle.py): pinned against the published Philox vectors and against the
+# `transformers` warpers the reference's generate() call runs (scripts/seed_llama_inference_8B.py:26-38)
+# --------------------------------------------------------------------------------------------------
+def test_philox_known_answers_and_c_host_function():
+    from oracle import sampler_oracle as S
+
+    # Random123 kat_vectors, philox4x32 with 10 rounds
+    assert S.philox4x32_10((0, 0, 0, 0), (0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert S.philox4x32_10((0xffffffff,) * 4, (0xffffffff,) * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert S.philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    from seed_b200 import lib as L
+
+    for seed, off, row in [(0, 0, 0), (1234, 5, 2), (2 ** 40 + 7, 2 ** 33 + 1, 3), (2 ** 63, 99, 0)]:
+        u = S.philox_uniform(seed, off, row)
+        assert 0.0 < float(u) <= 1.0
+        assert float(u) == L.philox_uniform(seed, off, row)       # the library's host-side Philox (no GPU needed)
+
+
+def test_sampler_oracle_matches_transformers_warpers():
+    from transformers.generation.logits_process import TemperatureLogitsWarper, TopPLogitsWarper
+
+    from oracle import sampler_oracle as S
+
+    g = torch.Generator().manual_seed(3)
+    for V, T, P in [(50, 1.0, 0.5), (1000, 0.7, 0.9), (40194, 1.0, 0.5), (333, 1.3, 0.05), (64, 1.0, 1.0)]:
+        logits = (torch.randn(1, V, generator=g) * 3.0).half().float()
+        ids = torch.zeros((1, 1), dtype=torch.long)
+        warped = TemperatureLogitsWarper(T)(ids, logits.clone())
+        if P < 1.0:
+            warped = TopPLogitsWarper(P)(ids, warped)
+        ref_probs = torch.softmax(warped, dim=-1)[0].double().numpy()
+        q, keep, margin = S.warp(logits[0].numpy(), T, P)
+        assert margin > 1e-7                                           # the comparison below is not a coin flip
+        assert (keep == (ref_probs > 0)).all()
+        assert np.abs(q - ref_probs).max() < 1e-6
+    # greedy = torch.argmax (first maximal index)
+    x = np.array([0.5, 2.0, 2.0, -1.0], dtype=np.float32)
+    assert S.sample_ref(x, False)[0] == int(torch.from_numpy(x).argmax()) == 1
