@@ -41,6 +41,9 @@ struct GemmParams {
   int act;
   int row_group, row_stride, row_offset;
   int res_mod, res_offset;
+  int tail_w;                // > 0: the last n-tile is only tail_w (< BN) columns wide -- loaded through the tail tensor
+                             // map, multiplied with a narrower UMMA and read out chunk-limited, so a ragged N (1408 =
+                             // 5.5 x 256, 40194 = 157 x 256 + 2) costs its columns, not a whole tile
 };
 
 // KSUB: 64-wide K sub-blocks per pipeline stage.  KSUB = 2 halves the per-stage fixed cost in the MMA issuer
@@ -188,7 +191,7 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
 template <int BN, int CTAS, int MODE, int KSUB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_bt, const GemmParams p) {
   using Cfg = GemmCfg<BN, CTAS, KSUB>;
   constexpr int STAGE_K = GEMM_BLOCK_K * KSUB;
   constexpr int STAGES = Cfg::STAGES;
@@ -218,6 +221,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.tail_w > 0) tma_prefetch_desc(&tmap_bt);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -249,25 +253,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
         const int m_idx = (mt * CTAS + (int)cta_rank) * GEMM_BLOCK_M;
-        const int n_idx = nt * BN + (int)cta_rank * Cfg::LOAD_N;
+        const bool tail_tile = p.tail_w > 0 && nt == p.n_tiles - 1;
+        const int load_n = tail_tile ? p.tail_w / CTAS : Cfg::LOAD_N;       // W rows this CTA loads per k sub-block
+        const CUtensorMap* tb = tail_tile ? &tmap_bt : &tmap_b;
+        const uint32_t stage_tx = (uint32_t)(Cfg::A_BYTES + KSUB * load_n * GEMM_BLOCK_K * 2);
+        const int n_idx = nt * BN + (int)cta_rank * load_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_a + stage * Cfg::A_BYTES;
           const uint32_t sb_ = smem_b + stage * Cfg::B_BYTES;
           if constexpr (CTAS == 1) {
-            mbar_arrive_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
+            mbar_arrive_expect_tx(full_bar + 8 * stage, stage_tx);
 #pragma unroll
             for (int ks = 0; ks < KSUB; ++ks) {
               tma_load_2d(sa + ks * Cfg::A_SUB, &tmap_a, full_bar + 8 * stage, kb * STAGE_K + ks * GEMM_BLOCK_K, m_idx);
-              tma_load_2d(sb_ + ks * Cfg::B_SUB, &tmap_b, full_bar + 8 * stage, kb * STAGE_K + ks * GEMM_BLOCK_K, n_idx);
+              tma_load_2d(sb_ + ks * Cfg::B_SUB, tb, full_bar + 8 * stage, kb * STAGE_K + ks * GEMM_BLOCK_K, n_idx);
             }
           } else {
             const uint32_t lead_bar = mapa_shared(full_bar + 8 * stage, 0);
-            if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * Cfg::STAGE_BYTES);
+            if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * stage_tx);
 #pragma unroll
             for (int ks = 0; ks < KSUB; ++ks) {
               tma_load_2d_2cta(sa + ks * Cfg::A_SUB, &tmap_a, lead_bar, kb * STAGE_K + ks * GEMM_BLOCK_K, m_idx);
-              tma_load_2d_2cta(sb_ + ks * Cfg::B_SUB, &tmap_b, lead_bar, kb * STAGE_K + ks * GEMM_BLOCK_K, n_idx);
+              tma_load_2d_2cta(sb_ + ks * Cfg::B_SUB, tb, lead_bar, kb * STAGE_K + ks * GEMM_BLOCK_K, n_idx);
             }
             if (!leader) mbar_arrive_cluster(lead_bar);
           }
@@ -278,10 +286,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA, one thread) =====================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(GEMM_BLOCK_M * CTAS, BN);
+      constexpr uint32_t idesc_full = make_idesc_f16(GEMM_BLOCK_M * CTAS, BN);
+      const uint32_t idesc_tail = make_idesc_f16(GEMM_BLOCK_M * CTAS, p.tail_w > 0 ? p.tail_w : BN);
       int stage = 0; uint32_t phase = 0; int iter = 0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step, ++iter) {
         const int as = iter & 1;
+        const uint32_t idesc = (p.tail_w > 0 && (tile % p.n_tiles) == p.n_tiles - 1) ? idesc_tail : idesc_full;
         const uint32_t aphase = (iter >> 1) & 1;
         mbar_wait(tempty_bar + 8 * as, aphase ^ 1);
         tc_fence_after();
@@ -322,9 +332,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t lead_tempty0 = (CTAS == 2) ? mapa_shared(tempty_bar, 0) : tempty_bar;
     __half* bias_smem = reinterpret_cast<__half*>(smem_gen + (bias_off - smem_base));
     constexpr int NCHUNK = (MODE == 1) ? (BN / 32) : (BN / 16);   // 16-column output chunks per tile
-    constexpr int CH0 = (NCHUNK + 1) / 2;
-    const int c_begin = half_id == 0 ? 0 : CH0;
-    const int c_end = half_id == 0 ? CH0 : NCHUNK;
     const int n_limit = (MODE == 1) ? p.N / 2 : p.N;
     const bool has_bias = (MODE == 0) && (p.bias != nullptr);
     if (has_bias && etid < BN && tile0 < total_tiles) {
@@ -336,6 +343,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
+      // the two warps of a TMEM lane quarter split the tile's 16-column chunks; the ragged last tile has fewer
+      const int nchunk = (p.tail_w > 0 && nt == p.n_tiles - 1) ? p.tail_w / 16 : NCHUNK;
+      const int ch0 = (nchunk + 1) / 2;
+      const int c_begin = half_id == 0 ? 0 : ch0;
+      const int c_end = half_id == 0 ? ch0 : nchunk;
       const int n_tile0 = (MODE == 1) ? nt * (BN / 2) : nt * BN;
       const int m = (mt * CTAS + (int)cta_rank) * GEMM_BLOCK_M + quarter * 32 + lane;
       const bool row_ok = m < p.M;
@@ -374,6 +386,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait(tfull_bar + 8 * as, aphase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + as * Cfg::ACC_STRIDE + lane_addr;
+      if (c_begin >= c_end) {       // (one-chunk tail tile: this warp has nothing to read, but still releases the stage)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CTAS == 2) mbar_arrive_cluster(lead_tempty0 + 8 * as);
+          else mbar_arrive(tempty_bar + 8 * as);
+        }
+      }
       for (int c = c_begin; c < c_end; ++c) {
         uint32_t r0[16], r1[16];
         tmem_ld16(t_acc + c * 16, r0);
@@ -416,6 +436,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // ----------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------
+int get_option(const char* key);
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -466,9 +488,19 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_REQUEST));
     attr_set = true;
   }
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tbt;
   SB_PROPAGATE(make_tmap(&ta, d.A, d.M, d.K, d.lda, GEMM_BLOCK_M));
   SB_PROPAGATE(make_tmap(&tb, d.W, d.N, d.K, d.ldw, Cfg::LOAD_N));
+  // ragged N: the last n-tile is loaded / multiplied / read out at its own width (rounded up to what UMMA and the
+  // 8-row core-matrix groups allow: 16 columns per CTA of the pair)
+  int tail_w = 0;
+  if (MODE == 0 && d.N % BN != 0 && get_option("gemm_tail") != 0) {
+    const int q = 16 * CTAS;
+    tail_w = (d.N % BN + q - 1) / q * q;
+    if (tail_w >= BN) tail_w = 0;
+  }
+  if (tail_w > 0) SB_PROPAGATE(make_tmap(&tbt, d.W, d.N, d.K, d.ldw, tail_w / CTAS));
+  else tbt = tb;
 
   GemmParams p;
   p.M = d.M; p.N = d.N; p.K = d.K;
@@ -482,6 +514,7 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   p.act = d.act;
   p.row_group = d.row_group; p.row_stride = d.row_stride; p.row_offset = d.row_offset;
   p.res_mod = d.res_mod; p.res_offset = d.res_offset;
+  p.tail_w = tail_w;
 
   const int sms = num_sms();
   const int tiles = p.m_tiles * p.n_tiles;
@@ -499,7 +532,7 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   profile_mark_begin(0, stream);
-  SB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  SB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tbt, p));
   profile_mark_end(0, stream, 2.0 * (double)d.M * (double)d.N * (double)d.K);
   count_launch();
   return 0;

@@ -70,6 +70,11 @@ GEMM_SHAPES = [
     (1028, 1408, 1408, 176, 2),
     (1000, 768, 768, 128, 2),
     (4096, 1024, 256, 64, 2),
+    (1028, 1408, 1408, 256, 2),   # ragged N on a CTA pair: 5 full tiles + a 128-wide tail tile (proj / fc2 tiling)
+    (513, 1408, 6144, 256, 2),    # same with the 128-deep pipeline stages (fc2)
+    (300, 40194, 512, 256, 2),    # tail of 2 columns -> 32-wide UMMA on the pair (lm_head)
+    (300, 1000, 768, 256, 1),     # single CTA, tail 232 -> 240
+    (200, 272, 256, 256, 1),      # tail of one 16-column chunk: the second epilogue warp of each quarter has no chunk
 ]
 
 
