@@ -8,7 +8,10 @@ algorithm is restated here and pinned against the `transformers` installed in th
 
   TemperatureLogitsWarper   scores / temperature
   TopPLogitsWarper          sort ascending, cumulative softmax, remove tokens with cumsum <= 1 - top_p,
-                            always keep the last (most probable) one
+                            always keep the last (most probable) one.  Tokens whose score EQUALS the least kept score
+                            straddle the boundary in HF by sort order (implementation-defined: torch.sort is not stable
+                            on CUDA); here -- and in the kernel -- all of them are kept (`ties="all"`), which is the
+                            threshold form of the same rule and is identical to HF on tie-free scores
   sample                    softmax over the kept scores, one multinomial draw
 
 The multinomial draw itself is RNG specific; seedb200's kernel (seed_b200/csrc/sampler.cu) defines it as the inverse
@@ -43,7 +46,7 @@ def philox_uniform(seed: int, offset: int, row: int) -> np.float32:
     return np.float32(np.float32(c[0]) * np.float32(2.3283064365386963e-10) + np.float32(1.1641532182693481e-10))
 
 
-def warp(logits: np.ndarray, temperature: float, top_p: float):
+def warp(logits: np.ndarray, temperature: float, top_p: float, ties: str = "all"):
     """-> (probs over the full vocabulary after both warpers (0 outside the nucleus), kept mask, boundary margin).
     The margin is |cumsum - (1 - top_p)| of the token closest to the nucleus boundary: a kernel that sums in another
     order may legitimately differ on a token whose margin is ~1e-6."""
@@ -58,6 +61,8 @@ def warp(logits: np.ndarray, temperature: float, top_p: float):
         remove_sorted = cs <= (1.0 - top_p)
         remove_sorted[-1:] = False                           # min_tokens_to_keep = 1
         keep[order] = ~remove_sorted
+        if ties == "all":                                    # every token tied with the least kept score stays
+            keep = x >= x[keep].min()
         margin = float(np.min(np.abs(cs - (1.0 - top_p))))
     q = np.where(keep, p, 0.0)
     return q / q.sum(), keep, margin

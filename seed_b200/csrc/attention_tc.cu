@@ -28,7 +28,9 @@ constexpr int VA_Q0_BYTES = 16 * VA_G;             // query rows 0..127
 constexpr int VA_Q1_BYTES = 17 * VA_G;             // query rows 128..255 and the group holding row 256
 constexpr int VA_V_BYTES = 33 * VA_G;              // keys 0..263, x2 buffers (P.V walks 16 steps of 16 keys)
 constexpr int VA_DATA_BYTES = VA_K_BYTES + VA_Q0_BYTES + VA_Q1_BYTES + 2 * VA_V_BYTES;
-constexpr int VA_MISC_BYTES = 4 * 128 * 4 + 1088 + 256;   // max/sum exchange, row-256 probabilities, barriers, tmem slot
+constexpr int VA_CLS_LD = 288;                     // floats per row-256 probability buffer: 272 keys + the row's sum
+constexpr int VA_PART_LD = 96;                     // floats per warp of row-256 P.V partials (88 dims, padded)
+constexpr int VA_MISC_BYTES = 2 * VA_CLS_LD * 4 + 8 * VA_PART_LD * 4 + 256;   // row-256 buffers, partials, barriers
 constexpr int VA_SMEM = VA_DATA_BYTES + VA_MISC_BYTES + 128;
 constexpr int VA_THREADS = 448;                       // 8 softmax warps, 4 loader warps, MMA warp, row-256 warp
 // (warp ids matter: the SM's arbiter favours high warp ids, so the two latency-critical single warps come last)
@@ -77,6 +79,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+// tcgen05.wait::ld that also names the 32 destination registers of the chunk it completes: uses of r[] cannot be
+// scheduled above the wait, which matters once the NEXT chunk's load is in flight while this one is consumed
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (P, fp16 packed two per 32-bit column) stays in tensor memory
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
@@ -132,15 +145,14 @@ vit_attention_tc_kernel(const VitAttnParams p) {
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sK0 = base, sQ0 = sK0 + VA_K_BYTES, sQ1 = sQ0 + VA_Q0_BYTES, sV0 = sQ1 + VA_Q1_BYTES;
   const uint32_t misc = sV0 + 2 * VA_V_BYTES;
-  float* s_max = reinterpret_cast<float*>(gen + (misc - base));     // [2][128]
-  float* s_sum = s_max + 256;                                       // [2][128]
-  float* s_cls = s_sum + 256;                                       // [272] probabilities of query row 256
-  const uint32_t bars = misc + 2048 + 1088;
+  float* s_clsb = reinterpret_cast<float*>(gen + (misc - base));    // [2][VA_CLS_LD]: scores, then probabilities of query row 256
+  float* s_part = s_clsb + 2 * VA_CLS_LD;                           // [8][VA_PART_LD]: per-warp partial P.V of row 256
+  const uint32_t bars = misc + 2 * VA_CLS_LD * 4 + 8 * VA_PART_LD * 4;
   const uint32_t bar_s = bars, bar_p = bars + 16, bar_o = bars + 32, bar_free = bars + 48;      // [2] each: per tile pipeline
   const uint32_t q_full = bars + 64 /*[2]*/, q_empty = bars + 80 /*[2]*/;
   const uint32_t k_full = bars + 96, k_empty = bars + 104, v_full = bars + 112 /*[2]*/, v_empty = bars + 128 /*[2]*/;
   const uint32_t cls_bar = bars + 144;           // 8 softmax warps -> row-256 warp: scores of query 256 are in s_cls
-  const uint32_t cls_done = bars + 152;          // row-256 warp -> softmax warps: s_cls may be overwritten
+  const uint32_t cls_p = bars + 152;             // row-256 warp -> softmax warps: probabilities of row 256 are in s_cls
   const uint32_t tmem_slot = bars + 160;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
   uint8_t* gQ0 = gen + (sQ0 - base);
@@ -155,12 +167,12 @@ vit_attention_tc_kernel(const VitAttnParams p) {
       mbar_init(bar_s + 8 * u, 1); mbar_init(bar_p + 8 * u, 4); mbar_init(bar_o + 8 * u, 1); mbar_init(bar_free + 8 * u, 4);
       mbar_init(q_full + 8 * u, 1);
       mbar_init(v_full + 8 * u, 1);
-      mbar_init(v_empty + 8 * u, 10);      // P.V(1) retired + 8 softmax warps (value row 256) + row-256 warp
+      mbar_init(v_empty + 8 * u, 9);       // P.V(1) retired + 8 softmax warps (row-256 partial P.V, value row 256)
     }
     mbar_init(q_empty, 5);                 // S(0) retired + 4 softmax warps of tile 0 (their q rows, for key 256)
     mbar_init(q_empty + 8, 10);            // S(1) retired + all 8 softmax warps (tile-1 rows, query row 256) + row-256 warp
     mbar_init(cls_bar, 8);
-    mbar_init(cls_done, 1);
+    mbar_init(cls_p, 1);
     mbar_init(k_full, 1);
     mbar_init(k_empty, 10);                // S(1) retired + 8 softmax warps + row-256 warp (key row 256)
     fence_mbar_init();
@@ -266,14 +278,14 @@ vit_attention_tc_kernel(const VitAttnParams p) {
     }
     __syncwarp();
   } else if (warp == 13) {
-    // ======================= query row 256 (the 257th token) on the CUDA cores =======================
+    // ======================= query row 256 (the 257th token): its softmax =======================
     // 1 row x 257 keys x 88 dims: a third 128-row MMA tile would be 99% padding.  The 256 softmax threads each
-    // contribute the score of "their" key (thread <-> key), this warp adds key 256, runs the softmax over the 257
-    // scores and the P.V product with the head dims spread over the lanes (no cross-lane reduction).
+    // contribute the score of "their" key (thread <-> key), this warp adds key 256 and runs the softmax over the 257
+    // scores; the P.V product of the row is spread over the 256 softmax threads again (it was 12 k cycles per item on
+    // this one warp -- the whole kernel's period).  s_cls is double buffered by item parity.
     uint32_t n = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
-      const int b = item / p.heads, h = item - b * p.heads;
-      const uint32_t vb = n & 1;
+      float* cls = s_clsb + (n & 1) * VA_CLS_LD;
       VA_STAMP(9, 0);
       mbar_wait(q_full + 8, n & 1);
       mbar_wait(k_full, n & 1);
@@ -296,7 +308,7 @@ vit_attention_tc_kernel(const VitAttnParams p) {
       __syncwarp();
       if (lane == 0) { mbar_arrive(k_empty); mbar_arrive(q_empty + 8); }
       VA_STAMP(9, 2);
-      mbar_wait(cls_bar, n & 1);                          // the 256 distributed scores are in s_cls[0..255]
+      mbar_wait(cls_bar, n & 1);                          // the 256 distributed scores are in cls[0..255]
       VA_STAMP(9, 3);
       float sc[9];
       float mx = -INFINITY;
@@ -304,7 +316,7 @@ vit_attention_tc_kernel(const VitAttnParams p) {
       for (int i = 0; i < 9; ++i) {
         const int key = lane + 32 * i;
         float v = -INFINITY;
-        if (key < VA_N - 1) v = s_cls[key] * p.scale_log2;
+        if (key < VA_N - 1) v = cls[key] * p.scale_log2;
         else if (key == VA_N - 1) v = part * p.scale_log2;
         sc[i] = v;
         mx = fmaxf(mx, v);
@@ -317,46 +329,13 @@ vit_attention_tc_kernel(const VitAttnParams p) {
         const int key = lane + 32 * i;
         const float pr = __half2float(__float2half_rn(ex2f(sc[i] - mx)));   // P rounded to fp16 like the tile path
         sum += pr;
-        if (key < VA_KP) s_cls[key] = pr;                  // 0 for keys 257..271
+        if (key < VA_KP) cls[key] = pr;                    // 0 for keys 257..271
       }
       sum = warp_sum(sum);
+      if (lane == 0) cls[VA_KP] = sum;
       __syncwarp();
+      if (lane == 0) mbar_arrive(cls_p);                  // release: the probabilities are visible to the waiters
       VA_STAMP(9, 4);
-      mbar_wait(v_full + 8 * vb, (n >> 1) & 1);
-      VA_STAMP(9, 5);
-      // out[d] = sum_k p_k V[k][d]: lane l owns the dim pairs l and l + 32 (44 pairs); keys walk in groups of 8
-      const uint8_t* gV = gV0 + vb * VA_V_BYTES;
-      const int pr0 = lane, pr1 = lane + 32;               // pair index -> dims 2*pr, 2*pr+1
-      const bool has1 = pr1 < VA_D / 2;
-      const uint32_t off0 = (uint32_t)(pr0 >> 2) * 128 + (pr0 & 3) * 4;
-      const uint32_t off1 = (uint32_t)((has1 ? pr1 : 0) >> 2) * 128 + ((has1 ? pr1 : 0) & 3) * 4;
-      // the 8 lane groups (4 lanes = one 16-byte chunk of dims) walk the 8 rows of a key group in rotated order, so
-      // that one LDS touches 8 different 16-byte bank groups instead of the same one 8 times
-      const int rot = lane >> 2;
-      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-#pragma unroll 3
-      for (int kg = 0; kg < 33; ++kg) {                    // 33 groups of 8 keys (rows 257..263 are zero, p = 0)
-        const uint8_t* vg = gV + (uint32_t)kg * VA_G;
-        const float* pg = s_cls + kg * 8;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int rr = (r + rot) & 7;
-          const float pk = pg[rr];
-          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(vg + rr * 16 + off0));
-          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(vg + rr * 16 + off1));
-          a0 = fmaf(pk, f0.x, a0); a1 = fmaf(pk, f0.y, a1);
-          b0 = fmaf(pk, f1.x, b0); b1 = fmaf(pk, f1.y, b1);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(v_empty + 8 * vb); mbar_arrive(cls_done); }
-      VA_STAMP(9, 6);
-      const float inv = 1.0f / sum;
-      __half* og = p.o + b * p.o_bs + h * p.o_hs + (long long)(VA_N - 1) * p.o_ts;
-      float unused = 0.0f;
-      *reinterpret_cast<uint32_t*>(og + 2 * pr0) = pack2(a0 * inv, a1 * inv, unused);
-      if (has1) *reinterpret_cast<uint32_t*>(og + 2 * pr1) = pack2(b0 * inv, b1 * inv, unused);
-      VA_STAMP(9, 7);
     }
   } else {
     // ======================= softmax + epilogue: warps 0-3 own tile 0 (rows 0..127), warps 4-7 tile 1 =======================
@@ -375,7 +354,6 @@ vit_attention_tc_kernel(const VitAttnParams p) {
       mbar_wait_relaxed(q_full + 8 * u, pn);
       if (u == 0) mbar_wait_relaxed(q_full + 8, pn);                // query row 256 lives in the second Q buffer
       mbar_wait_relaxed(k_full, pn);
-      if (n > 0) mbar_wait_relaxed(cls_done, pn ^ 1);               // row-256 warp is done with last item's s_cls
       VA_STAMP(warp, 1);
       float s256 = 0.0f, t256 = 0.0f;
       {
@@ -403,7 +381,7 @@ vit_attention_tc_kernel(const VitAttnParams p) {
           }
         }
       }
-      s_cls[row] = t256;
+      s_clsb[(n & 1) * VA_CLS_LD + row] = t256;
       __syncwarp();
       if (lane == 0) { mbar_arrive(q_empty + 8 * u); if (u == 0) mbar_arrive(q_empty + 8); mbar_arrive(k_empty); mbar_arrive(cls_bar); }
 
@@ -411,33 +389,56 @@ vit_attention_tc_kernel(const VitAttnParams p) {
       mbar_wait_relaxed(bar_s + 8 * u, pn);
       tc_fence_after();
       VA_STAMP(warp, 3);
+      // Both passes walk the row in 32-column chunks with the NEXT chunk's tcgen05.ld already in flight while the
+      // current one is consumed (two register buffers, loops fully unrolled): a thread only ever has one round trip to
+      // tensor memory exposed, not one per chunk (14 serialized ld+wait round trips per item were most of the period).
+      uint32_t r0[32], r1[32];
       // pass 1: row maximum
       float mx = s256;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t ra[32], rb[32];
-        tmem_ld32(trow + c * 64, ra);
-        tmem_ld32(trow + c * 64 + 32, rb);
-        tmem_ld_wait();
+      auto chunk_max = [&](const uint32_t(&cur)[32]) {
+        float m0 = __uint_as_float(cur[0]), m1 = __uint_as_float(cur[1]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[j]), __uint_as_float(rb[j])));
+        for (int j = 2; j < 32; j += 2) {
+          m0 = fmaxf(m0, __uint_as_float(cur[j]));
+          m1 = fmaxf(m1, __uint_as_float(cur[j + 1]));
+        }
+        mx = fmaxf(mx, fmaxf(m0, m1));
+      };
+      tmem_ld32(trow, r0);
+#pragma unroll 1
+      for (int c = 0; c < 8; c += 2) {                     // chunk pairs: buffer roles are compile-time inside the body
+        tmem_ld_wait32(r0);
+        tmem_ld32(trow + (c + 1) * 32, r1);
+        chunk_max(r0);
+        tmem_ld_wait32(r1);
+        tmem_ld32(trow + ((c + 2) & 7) * 32, r0);          // after chunk 7 this is chunk 0 again: pass 2's first load
+        chunk_max(r1);
       }
       VA_STAMP(warp, 4);
       const float m = mx * p.scale_log2;                 // scale > 0
       // pass 2: P = exp2(s*scale*log2e - m), rounded to fp16 (as the reference does under autocast), written in
-      // place: chunk c of S (32 columns) becomes 16 packed columns that lie inside chunks already consumed
+      // place: chunk c of S (32 columns) becomes 16 packed columns that lie inside chunks already loaded
       float sum = 0.0f;
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        uint32_t r[32];
-        tmem_ld32(trow + c * 32, r);
-        tmem_ld_wait();
-        uint32_t pk[16];
+      auto chunk_exp = [&](const uint32_t(&cur)[32], uint32_t dst) {
 #pragma unroll
-        for (int g = 0; g < 16; ++g)
-          pk[g] = pack2(ex2f(fmaf(__uint_as_float(r[2 * g]), p.scale_log2, -m)),
-                        ex2f(fmaf(__uint_as_float(r[2 * g + 1]), p.scale_log2, -m)), sum);
-        tmem_st16(trow + (c < 4 ? c * 16 : 128 + (c - 4) * 16), pk);
+        for (int hf = 0; hf < 2; ++hf) {                   // two halves of 16 columns: bounds the live temporaries
+          uint32_t pk[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            pk[g] = pack2(ex2f(fmaf(__uint_as_float(cur[hf * 16 + 2 * g]), p.scale_log2, -m)),
+                          ex2f(fmaf(__uint_as_float(cur[hf * 16 + 2 * g + 1]), p.scale_log2, -m)), sum);
+          tmem_st8(dst + hf * 8, pk);
+        }
+      };
+#pragma unroll 1
+      for (int c = 0; c < 8; c += 2) {
+        const uint32_t dst = trow + (c < 4 ? c * 16 : 128 + (c - 4) * 16);
+        tmem_ld_wait32(r0);
+        tmem_ld32(trow + (c + 1) * 32, r1);
+        chunk_exp(r0, dst);
+        tmem_ld_wait32(r1);
+        if (c + 2 < 8) tmem_ld32(trow + (c + 2) * 32, r0);
+        chunk_exp(r1, dst + 16);
       }
       const float p256 = __half2float(__float2half_rn(ex2f(fmaf(s256, p.scale_log2, -m))));
       sum += p256;
@@ -447,6 +448,62 @@ vit_attention_tc_kernel(const VitAttnParams p) {
       if (lane == 0) mbar_arrive(bar_p + 8 * u);
       VA_STAMP(warp, 5);
 
+      // ---- query row 256: this warp's share of its P.V product, in the shadow of the tile's P.V MMA ----
+      // lane = (chunk quad c4, key k8): one LDS.128 per (8 keys x 4 dim chunks) is a contiguous 512 bytes of the
+      // canonical V image; warp w takes key groups w, w + 8, ... of the 33.
+      {
+        mbar_wait_relaxed(cls_p, pn);
+        mbar_wait_relaxed(v_full + 8 * vb, (n >> 1) & 1);
+        const float* pc = s_clsb + (n & 1) * VA_CLS_LD;
+        const uint8_t* gV = gV0 + vb * VA_V_BYTES;
+        const int k8 = lane & 7, c4 = lane >> 3;
+        float a[3][8];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[q][j] = 0.0f;
+#pragma unroll 1
+        for (int kg = warp; kg < 33; kg += 8) {            // keys 257..263 of the last group are zero rows, p = 0
+          const float pk = pc[kg * 8 + k8];
+          const uint8_t* vrow = gV + (uint32_t)kg * VA_G + k8 * 16 + c4 * 128;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {                    // chunk q*4 + c4 (chunk 11 is the zero padding)
+            const uint4 vv = *reinterpret_cast<const uint4*>(vrow + q * 512);
+            const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 vf = __half22float2(v2[j]);
+              a[q][2 * j] = fmaf(pk, vf.x, a[q][2 * j]);
+              a[q][2 * j + 1] = fmaf(pk, vf.y, a[q][2 * j + 1]);
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v = a[q][j];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            a[q][j] = v;
+          }
+        if (k8 == 0) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            float* dst = s_part + warp * VA_PART_LD + (q * 4 + c4) * 8;
+            *reinterpret_cast<float4*>(dst) = make_float4(a[q][0], a[q][1], a[q][2], a[q][3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(a[q][4], a[q][5], a[q][6], a[q][7]);
+          }
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");     // the 8 softmax warps
+        if (tid < VA_D) {
+          float acc = 0.0f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) acc += s_part[w * VA_PART_LD + tid];
+          p.o[b * p.o_bs + h * p.o_hs + (long long)(VA_N - 1) * p.o_ts + tid] = __float2half_rn(acc / pc[VA_KP]);
+        }
+      }
       const float inv = 1.0f / sum;
       const float w256 = p256 * inv;
       mbar_wait_relaxed(bar_o + 8 * u, pn);

@@ -27,6 +27,7 @@ void count_launch(int n = 1);
     if (_e != cudaSuccess) {                                                             \
       sb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,    \
                     __LINE__);                                                           \
+      (void)cudaGetLastError(); /* reported: do not leave it for an unrelated later launch check */ \
       return SEEDB200_ERR_CUDA;                                                          \
     }                                                                                    \
   } while (0)

@@ -49,6 +49,8 @@ struct seedb200_llama {
   __half* glogits;                // [max_batch, vpad]
   sb::GenParams* gparams;         // sampling parameters + eos/pad, read by the sampler at run time
   int* gstate_host;               // pinned mirror of gstate (early-stop polling)
+  cudaStream_t gstream;           // private stream the decode step is captured on (the caller's may be the legacy
+                                  // default stream, which cannot be captured); replays go to the caller's stream
   cudaGraphExec_t gexec[5];       // decode-step graph per batch size (1..4)
   int gunit_launches[5];          // kernels inside one captured unit (launch accounting of graph replays)
   int used_graph;
@@ -143,6 +145,7 @@ static int llama_build(seedb200_llama* m) {
   SB_PROPAGATE(llama_alloc(m, &m->glogits, (size_t)c.max_batch * m->vpad));
   SB_PROPAGATE(llama_alloc(m, &m->gparams, 1));
   SB_CHECK_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->gstate_host), 8 * sizeof(int)));
+  SB_CHECK_CUDA(cudaStreamCreateWithFlags(&m->gstream, cudaStreamNonBlocking));
   SB_CHECK_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
@@ -248,8 +251,9 @@ static int gen_unit(seedb200_llama* m, int B, cudaStream_t st) {
   return 0;
 }
 
-static int gen_capture(seedb200_llama* m, int B, cudaStream_t st) {
+static int gen_capture(seedb200_llama* m, int B) {
   cudaGraph_t graph = nullptr;
+  cudaStream_t st = m->gstream;
   SB_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
   const int64_t before = seedb200_launch_count();
   const int s = gen_unit(m, B, st);
@@ -306,10 +310,10 @@ static int llama_generate(seedb200_llama* m, const int64_t* prompt_ids, int B, i
   }
   if (units > done && use_graph) {
     if (m->gexec[B] == nullptr) {
-      int s = gen_capture(m, B, st);
+      int s = gen_capture(m, B);
       if (s != 0 && get_option("decode_pdl") != 0) {   // retry without programmatic launches inside the graph
         seedb200_set_option("decode_pdl", 0);
-        s = gen_capture(m, B, st);
+        s = gen_capture(m, B);
         seedb200_set_option("decode_pdl", 1);
       }
       if (s != 0) return s;
@@ -366,6 +370,7 @@ int seedb200_llama_create(const seedb200_llama_config* cfg, const seedb200_tenso
   m->last_T = 0;
   m->device = sb::cur_device();
   m->gstate_host = nullptr;
+  m->gstream = nullptr;
   m->used_graph = -1;
   m->gen_cache_len = 0;
   for (int i = 0; i < 5; ++i) { m->gexec[i] = nullptr; m->gunit_launches[i] = 0; }
@@ -385,6 +390,7 @@ void seedb200_llama_destroy(seedb200_llama* llm) {
   for (int i = 0; i < 5; ++i)
     if (llm->gexec[i]) cudaGraphExecDestroy(llm->gexec[i]);
   if (llm->gstate_host) cudaFreeHost(llm->gstate_host);
+  if (llm->gstream) cudaStreamDestroy(llm->gstream);
   for (void* p : llm->owned) cudaFree(p);
   delete llm;
 }

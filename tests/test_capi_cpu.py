@@ -84,7 +84,7 @@ def test_missing_library_fails_loudly(tmp_path):
 def test_no_oracle_imports_in_product_code():
     """only tests/, __graft_entry__.smoke() and bench.py may touch oracle/ (tier rule 3)."""
     bad = []
-    for root in ("seed_b200", "models"):
+    for root in ("seed_b200", "models", "tools", "include"):
         for dp, _, files in os.walk(os.path.join(REPO, root)):
             for f in files:
                 if f.endswith((".py", ".cu", ".cuh", ".h")):

@@ -210,16 +210,25 @@ def test_sampler_oracle_matches_transformers_warpers():
 
     g = torch.Generator().manual_seed(3)
     for V, T, P in [(50, 1.0, 0.5), (1000, 0.7, 0.9), (40194, 1.0, 0.5), (333, 1.3, 0.05), (64, 1.0, 1.0)]:
-        logits = (torch.randn(1, V, generator=g) * 3.0).half().float()
+        logits = (torch.randn(1, V, generator=g) * 3.0).half().float()     # fp16 logits: tied scores do occur
         ids = torch.zeros((1, 1), dtype=torch.long)
         warped = TemperatureLogitsWarper(T)(ids, logits.clone())
         if P < 1.0:
             warped = TopPLogitsWarper(P)(ids, warped)
         ref_probs = torch.softmax(warped, dim=-1)[0].double().numpy()
-        q, keep, margin = S.warp(logits[0].numpy(), T, P)
+        x = logits[0].numpy()
+        q, keep, margin = S.warp(x, T, P, ties="sort")                 # HF's rule incl. its (stable-sort) tie split
         assert margin > 1e-7                                           # the comparison below is not a coin flip
         assert (keep == (ref_probs > 0)).all()
         assert np.abs(q - ref_probs).max() < 1e-6
+        # the threshold form used by the kernel: a superset that differs only by tokens tied with the least kept score
+        _, keep_all, _ = S.warp(x, T, P)
+        assert (keep_all | ~keep).all() and (x[keep_all & ~keep] == x[keep].min()).all()
+    # tied scores at the nucleus boundary: HF's stable CPU sort keeps a suffix of the tie group, the threshold form all
+    x = np.array([1.0, 3.0, 1.0, 1.0, 0.0], dtype=np.float32)
+    _, keep_hf, _ = S.warp(x, 1.0, 0.9, ties="sort")
+    _, keep_all, _ = S.warp(x, 1.0, 0.9, ties="all")
+    assert keep_all.tolist() == [True, True, True, True, False] and keep_hf.sum() <= keep_all.sum() and keep_hf[1]
     # greedy = torch.argmax (first maximal index)
     x = np.array([0.5, 2.0, 2.0, -1.0], dtype=np.float32)
     assert S.sample_ref(x, False)[0] == int(torch.from_numpy(x).argmax()) == 1

@@ -23,7 +23,7 @@ names = {0: "softmax w0", 4: "softmax w4", 8: "mma", 9: "row256", 10: "ld Q0", 1
 ev = {8: ["start", "S0 issue", "S1 issue", "wait v", "v ok", "PV0 issue", "PV1 issue", "end"],
       0: ["start", "q,k ok", "s256 done", "S ok", "max done", "P done", "O ok", "end"],
       10: ["start", "empty ok", "issued", "full"]}
-ev[9] = ["start", "q ok", "k ok", "scores", "softmax", "v ok", "pv", "end"]; ev[4] = ev[0]; ev[11] = ev[12] = ev[13] = ev[10]
+ev[9] = ["start", "q,k ok", "key256", "scores ok", "p written"]; ev[4] = ev[0]; ev[11] = ev[12] = ev[13] = ev[10]
 for item in range(0, 6):
     print(f"--- item {item}")
     for slot in (8, 9, 0, 4, 10, 11, 12, 13):
