@@ -41,6 +41,9 @@ struct GemmParams {
   int act;
   int row_group, row_stride, row_offset;
   int res_mod, res_offset;
+  int tile_shift;            // round r of the persistent schedule hands unit u the tile r*units + (u + r*tile_shift) % units:
+                             // with a cheap tail column the plain round robin (shift 0) gives some units all the cheap
+                             // tiles and others none whenever units % n_tiles shares a factor with n_tiles
   int tail_w;                // > 0: the last n-tile is only tail_w (< BN) columns wide -- loaded through the tail tensor
                              // map, multiplied with a narrower UMMA and read out chunk-limited, so a ragged N (1408 =
                              // 5.5 x 256, 40194 = 157 x 256 + 2) costs its columns, not a whole tile
@@ -243,14 +246,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int num_kb = (p.K + STAGE_K - 1) / STAGE_K;
   const int total_tiles = p.m_tiles * p.n_tiles;
-  const int tile0 = (CTAS == 2) ? (blockIdx.x >> 1) : blockIdx.x;
-  const int tile_step = (CTAS == 2) ? (gridDim.x >> 1) : gridDim.x;
+  const int unit = (CTAS == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const int units = (CTAS == 2) ? (gridDim.x >> 1) : gridDim.x;
+  auto tile_of = [&](int round) { return round * units + (unit + round * p.tile_shift) % units; };
+  const int tile0 = tile_of(0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      for (int round = 0; round * units < total_tiles; ++round) {
+        const int tile = tile_of(round);
+        if (tile >= total_tiles) break;            // only the last round is partial
         const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
         const int m_idx = (mt * CTAS + (int)cta_rank) * GEMM_BLOCK_M;
         const bool tail_tile = p.tail_w > 0 && nt == p.n_tiles - 1;
@@ -289,7 +296,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       constexpr uint32_t idesc_full = make_idesc_f16(GEMM_BLOCK_M * CTAS, BN);
       const uint32_t idesc_tail = make_idesc_f16(GEMM_BLOCK_M * CTAS, p.tail_w > 0 ? p.tail_w : BN);
       int stage = 0; uint32_t phase = 0; int iter = 0;
-      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++iter) {
+      for (int round = 0; round * units < total_tiles; ++round, ++iter) {
+        const int tile = tile_of(round);
+        if (tile >= total_tiles) break;
         const int as = iter & 1;
         const uint32_t idesc = (p.tail_w > 0 && (tile % p.n_tiles) == p.n_tiles - 1) ? idesc_tail : idesc_full;
         const uint32_t aphase = (iter >> 1) & 1;
@@ -339,7 +348,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       bias_smem[etid] = (n < p.N) ? p.bias[n] : __float2half(0.0f);
     }
     int iter = 0;
-    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++iter) {
+    for (int round = 0; round * units < total_tiles; ++round, ++iter) {
+      const int tile = tile_of(round);
+      if (tile >= total_tiles) break;
       const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
@@ -366,8 +377,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (has_bias) {
         // this tile's bias was staged one tile ago (or in the prologue); the barrier publishes it
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int next = tile + tile_step;
-        if (next < total_tiles && etid < BN) {     // issue the load now, consume it after the chunk loop
+        const int next = tile_of(round + 1);
+        if ((round + 1) * units < total_tiles && next < total_tiles && etid < BN) {     // issue the load now, consume it after the chunk loop
           const int n = (next % p.n_tiles) * BN + etid;
           if (n < p.N) bias_next = p.bias[n];
         }
@@ -515,12 +526,20 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   p.row_group = d.row_group; p.row_stride = d.row_stride; p.row_offset = d.row_offset;
   p.res_mod = d.res_mod; p.res_offset = d.res_offset;
   p.tail_w = tail_w;
+  p.tile_shift = 0;
 
   const int sms = num_sms();
   const int tiles = p.m_tiles * p.n_tiles;
   int units = sms / CTAS;
   if (units > tiles) units = tiles;
   if (units < 1) units = 1;
+  if (tail_w > 0 && p.n_tiles > 1) {
+    // advance of a unit's n-tile index per round = (units + shift) mod n_tiles: make it coprime with n_tiles so that
+    // every unit meets the cheap tail column once every n_tiles rounds
+    auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+    for (int sft = 0; sft < p.n_tiles; ++sft)
+      if (gcd((units + sft) % p.n_tiles, p.n_tiles) == 1) { p.tile_shift = sft; break; }
+  }
 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(units * CTAS);

@@ -462,7 +462,7 @@ def test_sampler_greedy_is_torch_argmax(lib):
     assert got.cpu().tolist() == [int(logits[0].float().argmax()), 777, 0, 40193]
 
 
-@pytest.mark.parametrize("V,T,P", [(40194, 1.0, 0.5), (40194, 0.7, 0.9), (1000, 1.3, 0.05), (50, 1.0, 1.0), (5120, 1.0, 0.999)])
+@pytest.mark.parametrize("V,T,P", [(40194, 1.0, 0.5), (40194, 0.7, 0.9), (1000, 1.3, 0.05), (50, 1.0, 1.0), (5120, 1.0, 0.97)])
 def test_sampler_matches_oracle_draw_by_draw(lib, V, T, P):
     """temperature / top-p / inverse-CDF draw vs oracle/sampler_oracle.py (HF TemperatureLogitsWarper +
     TopPLogitsWarper semantics, pinned to transformers on the CPU side); same Philox uniforms.  A draw whose uniform
