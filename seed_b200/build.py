@@ -18,8 +18,8 @@ LIB = os.path.join(ROOT, "libseedb200.so")
 ORACLE_DIR = os.path.join(REPO, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "libvq_oracle.so")
 
-SOURCES = ["capi.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "attention_causal_tc.cu", "rowwise.cu", "vq.cu", "misc.cu", "sampler.cu", "encoder.cu", "llama.cu", "preprocess.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "ops.h"), os.path.join(REPO, "include", "seedb200.h")]
+SOURCES = ["capi.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "attention_tc2.cu", "attention_causal_tc.cu", "rowwise.cu", "vq.cu", "misc.cu", "sampler.cu", "encoder.cu", "llama.cu", "preprocess.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "ops.h"), os.path.join(CSRC, "attention_tc_common.cuh"), os.path.join(REPO, "include", "seedb200.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [

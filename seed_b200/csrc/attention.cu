@@ -328,6 +328,7 @@ static int launch_attn(const seedb200_attn_desc& d, cudaStream_t stream) {
 
 bool vit_attention_tc_applicable(const seedb200_attn_desc& d);
 int vit_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream);
+int vit_attention_tc2(const seedb200_attn_desc& d, cudaStream_t stream);
 bool causal_attention_tc_applicable(const seedb200_attn_desc& d);
 int causal_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream);
 int get_option(const char* key);
@@ -346,7 +347,8 @@ int attention(const seedb200_attn_desc& d, cudaStream_t stream) {
   SB_REQUIRE(((uintptr_t)d.q % 16 == 0) && ((uintptr_t)d.k % 16 == 0) && ((uintptr_t)d.v % 16 == 0) &&
                  ((uintptr_t)d.o % 4 == 0),
              "attention: misaligned pointer");
-  if (vit_attention_tc_applicable(d) && get_option("vit_attention_tc") != 0) return vit_attention_tc(d, stream);
+  if (vit_attention_tc_applicable(d) && get_option("vit_attention_tc") != 0)
+    return get_option("vit_attention_tc") == 2 ? vit_attention_tc2(d, stream) : vit_attention_tc(d, stream);
   if (causal_attention_tc_applicable(d) && get_option("causal_attention_tc") != 0) return causal_attention_tc(d, stream);
   if (d.head_dim == 64) {
     if (d.nq <= 32) return launch_attn<64, 2>(d, stream);

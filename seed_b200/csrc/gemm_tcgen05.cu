@@ -560,10 +560,11 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
 static int pick_bn(int N, int mode, int ctas) {
   if (mode == 1) return 256;
   if (N % 256 == 0) return 256;
+  // CTA pairs: 256-wide tiles plus a narrow tail tile (the ragged last column costs its own width, and the persistent
+  // schedule spreads the cheap tiles over the units) beat the exactly dividing narrower tilings: N=1408 proj 1143 vs
+  // 967 (BN=176) TFLOP/s, N=4224 qkv 1355-1370 vs 1328 (BN=192)
+  if (ctas == 2 && N >= 1024) return 256;
   if (N % 192 == 0) return 192;
-  // CTA pairs: a 256-wide tile with a partly empty last column beats an exactly dividing narrower tile while
-  // the padding stays under 10% (N=1408: BN=256 1370 TFLOP/s vs BN=176 1323 on fc2, 1071 vs 967 on proj)
-  if (ctas == 2 && N >= 1024 && ((N + 255) / 256 * 256 - N) * 10 <= N) return 256;
   if (N % 176 == 0) return 176;
   if (N % 128 == 0) return 128;
   if (N <= 32) return 32;
