@@ -64,7 +64,10 @@ void seedb200_reset_launch_count(void);
  * tcgen05 kernel (attention_causal_tc.cu), 0 to the mma.sync kernel.
  * "decode_pdl": 1 (default) launches the kernels of the cached decode step (q_len 1) with programmatic stream
  * serialization (each starts while its predecessor drains and waits on griddepcontrol before reading activations).
- * "gemm_ksub": 0 (default) = heuristic, 1 = 64-deep GEMM pipeline stages, 2 = 128-deep.                      */
+ * "gemm_ksub": 0 (default) = heuristic, 1 = 64-deep GEMM pipeline stages, 2 = 128-deep.
+ * "gemm_tail": 1 (default) = a ragged last column of tiles runs at its own width, 0 = as a full tile.
+ * "encoder_ln_fold" (read by seedb200_encoder_create): 1 (default) = norm1 / norm2 of the ViT blocks are folded
+ * into the qkv / fc1 GEMMs (seedb200_gemm_desc.ln_stats), 0 = standalone LayerNorm kernels.                    */
 int seedb200_set_option(const char* key, int value);
 int seedb200_profile_begin(void);
 int seedb200_profile_end(double* out6);
@@ -108,8 +111,26 @@ typedef struct seedb200_gemm_desc {
   int32_t res_mod, res_offset;
   int32_t bn;                         /* tile-N hint, 0 = auto                   */
   int32_t ctas;                       /* 1 or 2 (cta_group::2 pair), 0 = auto    */
+  /* LayerNorm folded into the GEMM (eva_vit.py:201-202: x + attn(norm1(x)), x + mlp(norm2(x))): with
+   * W' = W diag(gamma) as the W operand and A = the UN-normalised rows x,
+   *   linear(LayerNorm(x), W, bias) = rstd_m * (acc_mn - mean_m * c_n) + b'_n,
+   *   c_n = sum_k W'[n,k],  b'_n = sum_k W[n,k] beta_k + bias_n        (seedb200_ln_fold_weights)
+   * ln_stats: float2 (mean, rstd) per row of A (seedb200_row_stats); ln_c, ln_b: fp32 [N].  All NULL = plain GEMM.
+   * The normalised activations are never materialised (no LN kernel, no fp16 LN tensor in HBM); the reference's
+   * rounding of LN(x) to fp16 is replaced by the rounding of W gamma to fp16 -- same order, bounded in the tests. */
+  const void* ln_stats; const void* ln_c; const void* ln_b;
 } seedb200_gemm_desc;
 int seedb200_gemm(const seedb200_gemm_desc* d, void* stream);
+
+/* The two helpers of the LayerNorm-folded GEMM (seedb200_gemm_desc.ln_stats):
+ * row_stats: (mean, rstd = 1/sqrt(var + eps)) of every row of x [rows, cols] fp16, two-pass in fp32 exactly like
+ * seedb200_layernorm (torch.nn.LayerNorm's statistics); stats_out: float2 [rows].
+ * ln_fold_weights: W [N,K], gamma/beta [K], bias [N] or NULL (fp16) -> W' [N,K] fp16 = W diag(gamma) rounded once,
+ * c [N] fp32 = row sums of the ROUNDED W' (so that acc - mean*c is exact for the operand the MMA really reads),
+ * b' [N] fp32 = W beta + bias.                                                                                   */
+int seedb200_row_stats(const void* x, int64_t ldx, int rows, int cols, float eps, void* stats_out, void* stream);
+int seedb200_ln_fold_weights(const void* W, int64_t ldw, const void* gamma, const void* beta, const void* bias, int N,
+                             int K, void* W_out, void* c_out, void* b_out, void* stream);
 
 /* y = LayerNorm(x) * w + b, statistics in fp32 (eva_vit.py:201-202 norm1/norm2,
  * blip2.py:179-184 ln_vision, qformer_causual.py:96/:254/:336).               */

@@ -46,7 +46,7 @@ void profile_mark_end(int kind, cudaStream_t stream, double flops) {
 }
 
 static std::map<std::string, int>& options() {
-  static std::map<std::string, int> o = {{"vit_attention_tc", 2}, {"causal_attention_tc", 1}, {"decode_pdl", 1}, {"gemv_ksplit", 0}, {"gemm_ksub", 0}, {"gemm_tail", 1}};
+  static std::map<std::string, int> o = {{"vit_attention_tc", 2}, {"causal_attention_tc", 1}, {"decode_pdl", 1}, {"gemv_ksplit", 0}, {"gemm_ksub", 0}, {"gemm_tail", 1}, {"encoder_ln_fold", 1}};
   return o;
 }
 static long long g_dbg_ptr = 0;

@@ -30,6 +30,10 @@ constexpr int DT_OUT = 1024;
 
 struct VitBlockW {
   const __half *n1w, *n1b, *qkv_w, *qkv_b, *proj_w, *proj_b, *n2w, *n2b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+  // LayerNorm folded into the consuming GEMM (option "encoder_ln_fold"): W diag(gamma) in fp16, and the fp32
+  // per-column vectors of seedb200_gemm_desc.ln_c / ln_b
+  const __half *qkv_wf, *fc1_wf;
+  const float *qkv_c, *qkv_bf, *fc1_c, *fc1_bf;
 };
 struct QfLayerW {
   const __half *qkv_w, *qkv_b, *ao_w, *ao_b, *aln_w, *aln_b;
@@ -64,6 +68,8 @@ struct seedb200_encoder {
   __half *cols, *x, *ln, *att, *big;   // big = [qkv | mlp hidden] region, reused for the fused cross K|V
   __half *hq, *hq_t, *q_qkv, *q_ctx, *q_inter, *z, *quant, *dtmp;
   int64_t* ids_buf;
+  float* row_stats;                // [T] (mean, rstd) pairs of the LayerNorm-folded GEMMs
+  int ln_fold;
   __half* img_in;                  // staging for the host entry point
   int last_B;
   int device;                      // the device that was current at create (weights + workspace live there)
@@ -130,6 +136,20 @@ static int linear(cudaStream_t st, int ctas, int M, int N, int K, const void* A,
   return gemm(d, st);
 }
 
+// linear(LayerNorm(x), W, bias) with the LayerNorm folded into the GEMM (seedb200_gemm_desc.ln_stats)
+static int linear_ln(cudaStream_t st, int ctas, int M, int N, int K, const void* x, const void* Wf, const void* stats,
+                     const void* c, const void* bf, void* out, int64_t ldo, int act) {
+  seedb200_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.M = M; d.N = N; d.K = K;
+  d.A = x; d.lda = K; d.W = Wf; d.ldw = K;
+  d.out = out; d.ldo = ldo; d.act = act; d.ctas = ctas;
+  d.ln_stats = stats; d.ln_c = c; d.ln_b = bf;
+  return gemm(d, st);
+}
+
+int get_option(const char* key);
+
 static int build(seedb200_encoder* e) {
   const seedb200_encoder_config& c = e->cfg;
   cudaStream_t st = 0;
@@ -171,6 +191,22 @@ static int build(seedb200_encoder* e) {
     SB_CHECK_CUDA(cudaMemcpyAsync(qkvb, qb, VIT_D * 2, cudaMemcpyDeviceToDevice, st));
     SB_CHECK_CUDA(cudaMemcpyAsync(qkvb + 2 * VIT_D, vb, VIT_D * 2, cudaMemcpyDeviceToDevice, st));
     b.qkv_b = qkvb;
+    b.qkv_wf = b.fc1_wf = nullptr;
+    if (e->ln_fold) {
+      // norm1 -> qkv and norm2 -> fc1 (eva_vit.py:201-202): the GEMM reads x itself, see seedb200_gemm_desc.ln_stats
+      __half *wq, *wf;
+      float *cq, *bq, *cf, *bf;
+      SB_PROPAGATE(dev_alloc_t(e, &wq, (size_t)3 * VIT_D * VIT_D));
+      SB_PROPAGATE(dev_alloc_t(e, &cq, 3 * VIT_D));
+      SB_PROPAGATE(dev_alloc_t(e, &bq, 3 * VIT_D));
+      SB_PROPAGATE(ln_fold_weights(b.qkv_w, VIT_D, b.n1w, b.n1b, b.qkv_b, 3 * VIT_D, VIT_D, wq, cq, bq, st));
+      SB_PROPAGATE(dev_alloc_t(e, &wf, (size_t)VIT_FF * VIT_D));
+      SB_PROPAGATE(dev_alloc_t(e, &cf, VIT_FF));
+      SB_PROPAGATE(dev_alloc_t(e, &bf, VIT_FF));
+      SB_PROPAGATE(ln_fold_weights(b.fc1_w, VIT_D, b.n2w, b.n2b, b.fc1_b, VIT_FF, VIT_D, wf, cf, bf, st));
+      b.qkv_wf = wq; b.qkv_c = cq; b.qkv_bf = bq;
+      b.fc1_wf = wf; b.fc1_c = cf; b.fc1_bf = bf;
+    }
   }
   // ---------------- Q-Former ----------------
   const __half *qtok, *eln_w, *eln_b;
@@ -278,6 +314,7 @@ static int build(seedb200_encoder* e) {
   SB_PROPAGATE(dev_alloc_t(e, &e->quant, Q * CB_DIM));
   SB_PROPAGATE(dev_alloc_t(e, &e->dtmp, Q * 256 + B * DT_OUT));
   SB_PROPAGATE(dev_alloc_t(e, &e->ids_buf, Q));
+  SB_PROPAGATE(dev_alloc_t(e, &e->row_stats, 2 * T));
   SB_PROPAGATE(dev_alloc_t(e, &e->img_in, B * 3 * 224 * 224));
   SB_CHECK_CUDA(cudaStreamSynchronize(st));
   return 0;
@@ -322,14 +359,25 @@ static int run_vit(seedb200_encoder* e, const void* images, int B, cudaStream_t 
   const float scale = 0.10660035817780521f;   // 88^-0.5 (eva_vit.py:93)
   for (size_t i = 0; i < e->vit.size(); ++i) {
     const VitBlockW& b = e->vit[i];
-    SB_PROPAGATE(layernorm(e->x, VIT_D, b.n1w, b.n1b, e->ln, VIT_D, T, VIT_D, 1e-6f, st));
-    SB_PROPAGATE(linear(st, ct, T, 3 * VIT_D, VIT_D, e->ln, VIT_D, b.qkv_w, b.qkv_b, qkv, 3 * VIT_D));
+    if (e->ln_fold) {
+      SB_PROPAGATE(row_stats(e->x, VIT_D, T, VIT_D, 1e-6f, e->row_stats, st));
+      SB_PROPAGATE(linear_ln(st, ct, T, 3 * VIT_D, VIT_D, e->x, b.qkv_wf, e->row_stats, b.qkv_c, b.qkv_bf, qkv, 3 * VIT_D, 0));
+    } else {
+      SB_PROPAGATE(layernorm(e->x, VIT_D, b.n1w, b.n1b, e->ln, VIT_D, T, VIT_D, 1e-6f, st));
+      SB_PROPAGATE(linear(st, ct, T, 3 * VIT_D, VIT_D, e->ln, VIT_D, b.qkv_w, b.qkv_b, qkv, 3 * VIT_D));
+    }
     SB_PROPAGATE(attn_call(st, qkv, (int64_t)VIT_TOK * 3 * VIT_D, VIT_HD, 3 * VIT_D, qkv + VIT_D, qkv + 2 * VIT_D,
                            (int64_t)VIT_TOK * 3 * VIT_D, VIT_HD, 3 * VIT_D, e->att, (int64_t)VIT_TOK * VIT_D, VIT_HD,
                            VIT_D, B, VIT_H, VIT_TOK, VIT_TOK, VIT_HD, 0, scale));
     SB_PROPAGATE(linear(st, ct, T, VIT_D, VIT_D, e->att, VIT_D, b.proj_w, b.proj_b, e->x, VIT_D, 0, e->x, VIT_D));
-    SB_PROPAGATE(layernorm(e->x, VIT_D, b.n2w, b.n2b, e->ln, VIT_D, T, VIT_D, 1e-6f, st));
-    SB_PROPAGATE(linear(st, ct, T, VIT_FF, VIT_D, e->ln, VIT_D, b.fc1_w, b.fc1_b, hid, VIT_FF, SEEDB200_ACT_GELU));
+    if (e->ln_fold) {
+      SB_PROPAGATE(row_stats(e->x, VIT_D, T, VIT_D, 1e-6f, e->row_stats, st));
+      SB_PROPAGATE(linear_ln(st, ct, T, VIT_FF, VIT_D, e->x, b.fc1_wf, e->row_stats, b.fc1_c, b.fc1_bf, hid, VIT_FF,
+                             SEEDB200_ACT_GELU));
+    } else {
+      SB_PROPAGATE(layernorm(e->x, VIT_D, b.n2w, b.n2b, e->ln, VIT_D, T, VIT_D, 1e-6f, st));
+      SB_PROPAGATE(linear(st, ct, T, VIT_FF, VIT_D, e->ln, VIT_D, b.fc1_w, b.fc1_b, hid, VIT_FF, SEEDB200_ACT_GELU));
+    }
     SB_PROPAGATE(linear(st, ct, T, VIT_D, VIT_FF, hid, VIT_FF, b.fc2_w, b.fc2_b, e->x, VIT_D, 0, e->x, VIT_D));
   }
   SB_PROPAGATE(layernorm(e->x, VIT_D, e->lnv_w, e->lnv_b, e->ln, VIT_D, T, VIT_D, 1e-5f, st));
@@ -449,6 +497,7 @@ int seedb200_encoder_create(const seedb200_encoder_config* cfg, const seedb200_t
   e->cfg = *cfg;
   e->last_B = 0;
   e->device = sb::cur_device();
+  e->ln_fold = sb::get_option("encoder_ln_fold") != 0;
   for (int i = 0; i < n_weights; ++i) e->w[std::string(weights[i].name)] = weights[i];
   int s = sb::build(e);
   if (s != 0) {

@@ -41,6 +41,9 @@ struct GemmParams {
   int act;
   int row_group, row_stride, row_offset;
   int res_mod, res_offset;
+  const float2* ln_stats;    // LayerNorm folded into this GEMM (see seedb200_gemm_desc.ln_stats): per-row (mean, rstd),
+  const float* ln_c;         // per-column c[n] = sum_k W'[n,k] and b'[n] = sum_k W[n,k] beta[k] + bias[n]:
+  const float* ln_b;         //   out = rstd * (acc - mean * c) + b'
   int tile_shift;            // round r of the persistent schedule hands unit u the tile r*units + (u + r*tile_shift) % units:
                              // with a cheap tail column the plain round robin (shift 0) gives some units all the cheap
                              // tiles and others none whenever units % n_tiles shares a factor with n_tiles
@@ -64,7 +67,7 @@ struct GemmCfg {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16 + 2 * 256 * 2;   // barriers, tmem slot, bias stage
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16 + 2 * 256 * 2 + 2 * 2 * 256 * 4;   // barriers, tmem slot, bias stage, LN-fold c / b' stages
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + BAR_BYTES;
   // keep one CTA per SM (TMEM is allocated per CTA): request more than half of the SM's smem
   static constexpr int SMEM_REQUEST = SMEM_BYTES < 120 * 1024 ? 120 * 1024 : SMEM_BYTES;
@@ -115,7 +118,9 @@ template <int MODE>
 __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint32_t (&acc)[16],
                                                  const uint32_t (&acc2)[16], const __half* bias_s,
                                                  const __half* res_row, __half* out_row, bool res_loaded,
-                                                 const uint4& res0, const uint4& res1, int n0, int n_limit) {
+                                                 const uint4& res0, const uint4& res1, int n0, int n_limit,
+                                                 const float* lnc_s = nullptr, const float* lnb_s = nullptr,
+                                                 float ln_mean = 0.0f, float ln_rstd = 1.0f) {
   if (n0 >= n_limit) return;
   __half h[16];
   if constexpr (MODE == 1) {
@@ -131,6 +136,19 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
     float v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+    if (lnc_s != nullptr) {
+      // LayerNorm folded into the GEMM: acc = sum_k W'[n,k] x[m,k] with W' = W diag(gamma), so
+      // W LN(x) + bias = rstd * (acc - mean * c[n]) + b'[n]   (fp32, one rounding to fp16 below)
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(lnc_s + j);
+        const float4 b4 = *reinterpret_cast<const float4*>(lnb_s + j);
+        v[j + 0] = fmaf(ln_rstd, fmaf(-ln_mean, c4.x, v[j + 0]), b4.x);
+        v[j + 1] = fmaf(ln_rstd, fmaf(-ln_mean, c4.y, v[j + 1]), b4.y);
+        v[j + 2] = fmaf(ln_rstd, fmaf(-ln_mean, c4.z, v[j + 2]), b4.z);
+        v[j + 3] = fmaf(ln_rstd, fmaf(-ln_mean, c4.w, v[j + 3]), b4.w);
+      }
+    }
     if (bias_s != nullptr) {
       const uint4 b0 = *reinterpret_cast<const uint4*>(bias_s);
       const uint4 b1 = *reinterpret_cast<const uint4*>(bias_s + 8);
@@ -211,6 +229,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t tempty_bar = tfull_bar + 16;           // [2]
   const uint32_t tmem_slot = tempty_bar + 16;           // uint32
   const uint32_t bias_off = tmem_slot + 16;             // [2][256] halves
+  const uint32_t lnc_off = bias_off + 2 * 256 * 2;      // [2][256] floats
+  const uint32_t lnb_off = lnc_off + 2 * 256 * 4;       // [2][256] floats
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -342,10 +362,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __half* bias_smem = reinterpret_cast<__half*>(smem_gen + (bias_off - smem_base));
     constexpr int NCHUNK = (MODE == 1) ? (BN / 32) : (BN / 16);   // 16-column output chunks per tile
     const int n_limit = (MODE == 1) ? p.N / 2 : p.N;
-    const bool has_bias = (MODE == 0) && (p.bias != nullptr);
-    if (has_bias && etid < BN && tile0 < total_tiles) {
+    float* lnc_smem = reinterpret_cast<float*>(smem_gen + (lnc_off - smem_base));
+    float* lnb_smem = reinterpret_cast<float*>(smem_gen + (lnb_off - smem_base));
+    const bool has_ln = (MODE == 0) && (p.ln_stats != nullptr);
+    const bool has_bias = (MODE == 0) && (p.bias != nullptr) && !has_ln;
+    const bool has_cols = has_bias || has_ln;          // some per-column vector is staged one tile ahead
+    if (has_cols && etid < BN && tile0 < total_tiles) {
       const int n = (tile0 % p.n_tiles) * BN + etid;
-      bias_smem[etid] = (n < p.N) ? p.bias[n] : __float2half(0.0f);
+      if (has_ln) {
+        lnc_smem[etid] = (n < p.N) ? p.ln_c[n] : 0.0f;
+        lnb_smem[etid] = (n < p.N) ? p.ln_b[n] : 0.0f;
+      } else {
+        bias_smem[etid] = (n < p.N) ? p.bias[n] : __float2half(0.0f);
+      }
     }
     int iter = 0;
     for (int round = 0; round * units < total_tiles; ++round, ++iter) {
@@ -374,13 +403,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // stage this tile's bias in shared memory and prefetch the first residual chunk while the MMAs of
       // the tile are still running (both are global-memory latencies that used to sit in the chunk loop)
       __half bias_next = __float2half(0.0f);
-      if (has_bias) {
-        // this tile's bias was staged one tile ago (or in the prologue); the barrier publishes it
+      float lnc_next = 0.0f, lnb_next = 0.0f;
+      float2 ln_st = make_float2(0.0f, 1.0f);
+      if (has_ln && row_ok) ln_st = p.ln_stats[m];       // (mean, rstd) of this thread's row
+      if (has_cols) {
+        // this tile's vectors were staged one tile ago (or in the prologue); the barrier publishes them
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int next = tile_of(round + 1);
         if ((round + 1) * units < total_tiles && next < total_tiles && etid < BN) {     // issue the load now, consume it after the chunk loop
           const int n = (next % p.n_tiles) * BN + etid;
-          if (n < p.N) bias_next = p.bias[n];
+          if (n < p.N) {
+            if (has_ln) { lnc_next = p.ln_c[n]; lnb_next = p.ln_b[n]; }
+            else bias_next = p.bias[n];
+          }
         }
       }
       uint4 rn0 = make_uint4(0, 0, 0, 0), rn1 = rn0;
@@ -432,10 +467,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         if (row_ok)
           epilogue_store16<MODE>(p, r0, r1, has_bias ? bias_smem + as * 256 + c * 16 : nullptr, res_row, out_row,
-                                 rc_ok, rc0, rc1, n_tile0 + c * 16, n_limit);
+                                 rc_ok, rc0, rc1, n_tile0 + c * 16, n_limit,
+                                 has_ln ? lnc_smem + as * 256 + c * 16 : nullptr, lnb_smem + as * 256 + c * 16, ln_st.x,
+                                 ln_st.y);
       }
-      // stage the next tile's bias (other accumulator stage: nobody reads it until the next barrier)
-      if (has_bias && etid < BN) bias_smem[(as ^ 1) * 256 + etid] = bias_next;
+      // stage the next tile's vectors (other accumulator stage: nobody reads it until the next barrier)
+      if (has_cols && etid < BN) {
+        if (has_ln) { lnc_smem[(as ^ 1) * 256 + etid] = lnc_next; lnb_smem[(as ^ 1) * 256 + etid] = lnb_next; }
+        else bias_smem[(as ^ 1) * 256 + etid] = bias_next;
+      }
     }
   }
 
@@ -527,6 +567,9 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   p.res_mod = d.res_mod; p.res_offset = d.res_offset;
   p.tail_w = tail_w;
   p.tile_shift = 0;
+  p.ln_stats = static_cast<const float2*>(d.ln_stats);
+  p.ln_c = static_cast<const float*>(d.ln_c);
+  p.ln_b = static_cast<const float*>(d.ln_b);
 
   const int sms = num_sms();
   const int tiles = p.m_tiles * p.n_tiles;
@@ -580,6 +623,10 @@ int gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   SB_REQUIRE(d.A && d.W && d.out, "gemm: null operand");
   SB_REQUIRE(d.mode == 0 || d.mode == 1, "gemm: unknown mode %d", d.mode);
   SB_REQUIRE(d.K % 8 == 0, "gemm: K=%d must be a multiple of 8 (16-byte TMA rows)", d.K);
+  if (d.ln_stats != nullptr) {
+    SB_REQUIRE(d.mode == 0 && d.ln_c != nullptr && d.ln_b != nullptr && d.bias == nullptr && d.row_group == 0,
+               "gemm: LayerNorm-folded mode takes ln_stats + ln_c + ln_b, no bias (it is inside ln_b), mode 0, no row remap");
+  }
   if (d.mode == 1) {
     SB_REQUIRE(d.N % 256 == 0, "gemm: SiLU-gate mode needs N %% 256 == 0 (got %d)", d.N);
     SB_REQUIRE(d.bias == nullptr && d.act == 0, "gemm: SiLU-gate mode takes no bias/activation");

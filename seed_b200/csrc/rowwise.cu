@@ -12,7 +12,9 @@ namespace sb {
 //   RMSNorm: llama_xformer.py:105-113 -- variance and x*rsqrt in fp32, ROUND to fp16, then * weight.
 // TPR threads cooperate on one row; each holds VPT 8-half vectors.
 // ----------------------------------------------------------------------------
-template <int TPR, int VPT, bool RMS>
+// STATS: only the per-row (mean, rstd) pair is written (float2 per row, through `y`): the LayerNorm-folded GEMM
+// (seedb200_gemm_desc.ln_stats) applies the normalisation in its epilogue and the normalised tensor never exists.
+template <int TPR, int VPT, bool RMS, bool STATS = false>
 __global__ void __launch_bounds__(256)
 norm_kernel(const __half* __restrict__ x, long long ldx, const __half* __restrict__ w,
             const __half* __restrict__ bvec, __half* __restrict__ y, long long ldy, int rows, int cols,
@@ -79,6 +81,10 @@ norm_kernel(const __half* __restrict__ x, long long ldx, const __half* __restric
     const float var = row_reduce(sq, 1) * inv_n;
     rstd = rsqrtf(var + eps);
   }
+  if constexpr (STATS) {
+    if (active && sub == 0) reinterpret_cast<float2*>(y)[row] = make_float2(mean, rstd);
+    return;
+  }
 
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
@@ -135,6 +141,66 @@ static int launch_norm(const void* x, int64_t ldx, const void* w, const void* b,
 #undef SB_NORM_LAUNCH
   set_error("norm: cols=%d too large", cols);
   return SEEDB200_ERR_UNSUPPORTED;
+}
+
+int row_stats(const void* x, int64_t ldx, int rows, int cols, float eps, void* stats, cudaStream_t stream) {
+  SB_REQUIRE(x && stats && rows > 0 && cols > 0, "row_stats: bad arguments");
+  SB_REQUIRE(cols % 8 == 0 && ldx % 8 == 0, "row_stats: cols/ld must be multiples of 8 (cols=%d)", cols);
+  const __half* xp = static_cast<const __half*>(x);
+  __half* yp = static_cast<__half*>(stats);
+  const int nvec = cols / 8;
+#define SB_STATS_LAUNCH(TPR_, VPT_)                                                              \
+  {                                                                                              \
+    const int rpb = 256 / TPR_;                                                                  \
+    norm_kernel<TPR_, VPT_, false, true><<<(rows + rpb - 1) / rpb, 256, 0, stream>>>(xp, ldx, nullptr, nullptr, yp, 0, \
+                                                                                      rows, cols, eps);              \
+    SB_LAUNCH_CHECK();                                                                           \
+    return 0;                                                                                    \
+  }
+  if (nvec <= 32 * 1) SB_STATS_LAUNCH(32, 1)
+  if (nvec <= 32 * 2) SB_STATS_LAUNCH(32, 2)
+  if (nvec <= 32 * 3) SB_STATS_LAUNCH(32, 3)
+  if (nvec <= 32 * 6) SB_STATS_LAUNCH(32, 6)      // 1408
+  if (nvec <= 256 * 2) SB_STATS_LAUNCH(256, 2)
+  if (nvec <= 256 * 8) SB_STATS_LAUNCH(256, 8)
+#undef SB_STATS_LAUNCH
+  set_error("row_stats: cols=%d too large", cols);
+  return SEEDB200_ERR_UNSUPPORTED;
+}
+
+// W' = fp16(W * gamma), c[n] = sum_k W'[n,k] (of the ROUNDED values), b'[n] = sum_k W[n,k] beta[k] + bias[n].
+// One warp per output row; run once per weight at handle creation.
+__global__ void __launch_bounds__(256)
+ln_fold_weights_kernel(const __half* __restrict__ W, long long ldw, const __half* __restrict__ gamma,
+                       const __half* __restrict__ beta, const __half* __restrict__ bias, int N, int K,
+                       __half* __restrict__ Wo, float* __restrict__ c, float* __restrict__ b) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float cs = 0.0f, bs = 0.0f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = __half2float(W[(long long)n * ldw + k]);
+    const __half wf = __float2half_rn(w * __half2float(gamma[k]));
+    Wo[(long long)n * K + k] = wf;
+    cs += __half2float(wf);
+    bs = fmaf(w, __half2float(beta[k]), bs);
+  }
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  if (lane == 0) {
+    c[n] = cs;
+    b[n] = bs + (bias != nullptr ? __half2float(bias[n]) : 0.0f);
+  }
+}
+
+int ln_fold_weights(const void* W, int64_t ldw, const void* gamma, const void* beta, const void* bias, int N, int K,
+                    void* W_out, void* c_out, void* b_out, cudaStream_t stream) {
+  SB_REQUIRE(W && gamma && beta && W_out && c_out && b_out && N > 0 && K > 0, "ln_fold_weights: bad arguments");
+  ln_fold_weights_kernel<<<(N + 7) / 8, 256, 0, stream>>>(
+      static_cast<const __half*>(W), ldw, static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
+      static_cast<const __half*>(bias), N, K, static_cast<__half*>(W_out), static_cast<float*>(c_out),
+      static_cast<float*>(b_out));
+  SB_LAUNCH_CHECK();
+  return 0;
 }
 
 int layernorm(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy, int rows, int cols,
@@ -370,6 +436,13 @@ extern "C" {
 int seedb200_layernorm(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy, int rows,
                        int cols, float eps, void* stream) {
   return sb::layernorm(x, ldx, w, b, y, ldy, rows, cols, eps, static_cast<cudaStream_t>(stream));
+}
+int seedb200_row_stats(const void* x, int64_t ldx, int rows, int cols, float eps, void* stats_out, void* stream) {
+  return sb::row_stats(x, ldx, rows, cols, eps, stats_out, static_cast<cudaStream_t>(stream));
+}
+int seedb200_ln_fold_weights(const void* W, int64_t ldw, const void* gamma, const void* beta, const void* bias, int N,
+                             int K, void* W_out, void* c_out, void* b_out, void* stream) {
+  return sb::ln_fold_weights(W, ldw, gamma, beta, bias, N, K, W_out, c_out, b_out, static_cast<cudaStream_t>(stream));
 }
 int seedb200_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int cols, float eps,
                      void* stream) {

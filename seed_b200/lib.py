@@ -33,6 +33,7 @@ EXPORTS = [
     "seedb200_gemv", "seedb200_decode_attention", "seedb200_decode_attention_workspace_bytes",
     "seedb200_sample", "seedb200_philox_uniform", "seedb200_image_ids_to_tokens", "seedb200_encoder_encode_tokens",
     "seedb200_llama_forward_ld", "seedb200_llama_generate", "seedb200_llama_generate_used_graph",
+    "seedb200_row_stats", "seedb200_ln_fold_weights",
 ]
 
 
@@ -51,7 +52,8 @@ class GemmDesc(C.Structure):
                 ("act", C.c_int32), ("mode", C.c_int32),
                 ("row_group", C.c_int32), ("row_stride", C.c_int32), ("row_offset", C.c_int32),
                 ("res_mod", C.c_int32), ("res_offset", C.c_int32),
-                ("bn", C.c_int32), ("ctas", C.c_int32)]
+                ("bn", C.c_int32), ("ctas", C.c_int32),
+                ("ln_stats", C.c_void_p), ("ln_c", C.c_void_p), ("ln_b", C.c_void_p)]
 
 
 class AttnDesc(C.Structure):
@@ -137,6 +139,9 @@ def load() -> C.CDLL:
                                            C.c_void_p]
     lib.seedb200_llama_tap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     lib.seedb200_llama_tap.restype = C.c_int64
+    lib.seedb200_row_stats.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    lib.seedb200_ln_fold_weights.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.seedb200_preprocess_create_ex.argtypes = [C.c_int] * 9 + [C.POINTER(C.c_void_p)]
     lib.seedb200_gemv.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -222,8 +227,9 @@ def profile_end() -> dict:
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, mode: int = 0,
          bn: int = 0, ctas: int = 0, row_group: int = 0, row_stride: int = 0, row_offset: int = 0,
-         res_mod: int = 0, res_offset: int = 0) -> torch.Tensor:
-    """out = epilogue(a @ w.T); a [M,K], w [N,K] fp16 (nn.Linear layout)."""
+         res_mod: int = 0, res_offset: int = 0, ln=None) -> torch.Tensor:
+    """out = epilogue(a @ w.T); a [M,K], w [N,K] fp16 (nn.Linear layout).  ln = (stats [M,2] fp32, c [N] fp32,
+    b [N] fp32) selects the LayerNorm-folded epilogue (w must then be the folded weight of ln_fold_weights)."""
     _need_cuda_f16(a, "gemm.a"); _need_cuda_f16(w, "gemm.w")
     M, K = a.shape
     N = w.shape[0]
@@ -242,6 +248,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     d.row_group, d.row_stride, d.row_offset = row_group, row_stride, row_offset
     d.res_mod, d.res_offset = res_mod, res_offset
     d.bn, d.ctas = bn, ctas
+    if ln is not None:
+        stats, cvec, bvec = ln
+        for t in (stats, cvec, bvec):
+            if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+                raise RuntimeError("gemm: ln tensors must be contiguous CUDA float32")
+        d.ln_stats, d.ln_c, d.ln_b = stats.data_ptr(), cvec.data_ptr(), bvec.data_ptr()
     with on(a.device):
         check(load().seedb200_gemm(C.byref(d), stream_ptr(a.device)), "seedb200_gemm")
     return out
@@ -255,6 +267,31 @@ def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float) -> 
         check(load().seedb200_layernorm(x.data_ptr(), x.stride(0), w.data_ptr(), b.data_ptr(), y.data_ptr(),
                                         y.stride(0), rows, cols, eps, stream_ptr(x.device)), "seedb200_layernorm")
     return y
+
+
+def row_stats(x: torch.Tensor, eps: float) -> torch.Tensor:
+    """(mean, rstd) per row of x [rows, cols] fp16 -> float32 [rows, 2] (LayerNorm statistics, two-pass fp32)."""
+    _need_cuda_f16(x, "row_stats.x")
+    rows, cols = x.shape
+    out = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
+    with on(x.device):
+        check(load().seedb200_row_stats(x.data_ptr(), x.stride(0), rows, cols, eps, out.data_ptr(), stream_ptr(x.device)),
+              "seedb200_row_stats")
+    return out
+
+
+def ln_fold_weights(w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: Optional[torch.Tensor] = None):
+    """-> (W' = fp16(W diag(gamma)) [N,K], c [N] fp32 = row sums of W', b' [N] fp32 = W beta + bias)."""
+    _need_cuda_f16(w, "ln_fold_weights.w")
+    N, K = w.shape
+    wf = torch.empty((N, K), dtype=torch.float16, device=w.device)
+    c = torch.empty((N,), dtype=torch.float32, device=w.device)
+    b = torch.empty((N,), dtype=torch.float32, device=w.device)
+    with on(w.device):
+        check(load().seedb200_ln_fold_weights(w.data_ptr(), w.stride(0), gamma.data_ptr(), beta.data_ptr(), _p(bias), N, K,
+                                              wf.data_ptr(), c.data_ptr(), b.data_ptr(), stream_ptr(w.device)),
+              "seedb200_ln_fold_weights")
+    return wf, c, b
 
 
 def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:

@@ -180,3 +180,28 @@ def test_encode_is_cuda_graph_capturable():
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(ids_g, ids_e) and torch.equal(z_g, z_e)
+
+
+def test_layernorm_fold_option_agrees_with_standalone_layernorm():
+    """option "encoder_ln_fold": norm1 / norm2 folded into the qkv / fc1 GEMMs vs standalone LayerNorm kernels --
+    same ids above the margin, activations within the stated tolerance of each other and of the oracle"""
+    from seed_b200 import lib as L
+
+    sd = synth.encoder_state_dict(4, 2, 0)
+    x = synth.images(3, seed=91)
+    with torch.no_grad():
+        ref = R.encode(x, sd, 4, 2)
+    outs = {}
+    for fold in (1, 0):
+        L.set_option("encoder_ln_fold", fold)
+        try:
+            model = make_model(sd, max_batch=4, vq_mode=1)
+        finally:
+            L.set_option("encoder_ln_fold", 1)
+        ids, z = model.encode_ids(x.cuda(), return_z=True)
+        taps = model.taps(3)
+        torch.cuda.synchronize()
+        check_ids(ids, ref["ids"], ref["margin"], f"ln_fold={fold}")
+        assert (z.float().cpu() - ref["z"].reshape(-1, 32)).abs().max().item() <= 1e-2
+        outs[fold] = (ids.cpu(), taps["vit"].float().cpu())
+    assert rel(outs[1][1], outs[0][1]) <= 3e-3

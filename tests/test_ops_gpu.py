@@ -537,3 +537,46 @@ def test_image_ids_to_tokens_kernel(lib):
     buf = torch.full((5, 40), -1, dtype=torch.int64, device=DEV)
     lib.image_ids_to_tokens(ids.to(DEV), 32000, 40192, 40193, out=buf)
     assert torch.equal(buf[:, :34].cpu(), toks) and (buf[:, 34:] == -1).all()
+
+
+# ----------------------------------------------------------------------------------------------
+# LayerNorm folded into the consuming GEMM (seedb200_gemm_desc.ln_stats): norm1 -> qkv, norm2 -> fc1
+# ----------------------------------------------------------------------------------------------
+def test_row_stats_match_torch_layernorm_statistics(lib):
+    x = rand16(1000, 1408, scale=2.0, seed=81) + 0.5
+    st = lib.row_stats(x, 1e-6)
+    xf = x.float()
+    mean = xf.mean(-1)
+    rstd = torch.rsqrt(xf.var(-1, unbiased=False) + 1e-6)
+    assert torch.allclose(st[:, 0], mean, rtol=0, atol=2e-6 * xf.abs().max().item())
+    assert torch.allclose(st[:, 1], rstd, rtol=2e-6, atol=0)
+
+
+@pytest.mark.parametrize("M,N,K,act,ctas", [(1028, 4224, 1408, 0, 2), (1028, 6144, 1408, 1, 2), (300, 512, 768, 0, 1),
+                                            (2056, 1408, 1408, 1, 2)])
+def test_gemm_layernorm_folded(lib, M, N, K, act, ctas):
+    """linear(LayerNorm(x), W, bias) [+ GELU] without materialising LayerNorm(x): W' = fp16(W gamma) as the operand,
+    rstd * (acc - mean * c) + b' in the epilogue (eva_vit.py:201-202 with :133-135 / :60-65).  The reference rounds
+    LN(x) to fp16 before the GEMM; here W gamma is rounded instead -- the two differ by a few fp16 ulps of the
+    output (both are one rounding of one operand), and both sit equally close to the fp32 value."""
+    g = torch.Generator().manual_seed(82)
+    x = (torch.randn(M, K, generator=g) * 1.5 + 0.3 * torch.randn(M, 1, generator=g)).half().to(DEV)
+    x[:, 7] += 20.0                                            # an outlier channel, as real ViT activations have
+    w = rand16(N, K, scale=K ** -0.5, seed=83)
+    gamma = (1.0 + 0.2 * torch.randn(K, generator=g)).half().to(DEV)
+    beta = (0.1 * torch.randn(K, generator=g)).half().to(DEV)
+    bias = rand16(N, scale=0.1, seed=84)
+    wf, c, bf = lib.ln_fold_weights(w, gamma, beta, bias)
+    # the folded vectors are what they claim to be
+    assert torch.equal(wf, (w.float() * gamma.float()).half())
+    assert torch.allclose(c, wf.float().sum(-1), rtol=1e-5, atol=1e-4)
+    assert torch.allclose(bf, w.float() @ beta.float() + bias.float(), rtol=1e-5, atol=1e-4)
+    out = lib.gemm(x, wf, act=act, ctas=ctas, ln=(lib.row_stats(x, 1e-6), c, bf))
+    ref16 = R.linear_ref(R.layernorm_ref(x, gamma, beta, 1e-6), w, bias, act)          # the reference's rounding points
+    ref32 = torch.nn.functional.layer_norm(x.float(), (K,), gamma.float(), beta.float(), 1e-6) @ w.float().t() + bias.float()
+    if act == 1:
+        ref32 = torch.nn.functional.gelu(ref32)
+    e_ours, e_ref = rel_err(out, ref32), rel_err(ref16, ref32)
+    assert e_ours <= 1.5 * e_ref + 1e-4, (e_ours, e_ref)      # as close to exact arithmetic as the reference's own rounding
+    assert rel_err(out, ref16) < 1.5e-3
+    assert_close16(out, ref16, ulps=6.0, atol=2e-3, what="LN-folded GEMM vs rounding-point reference")

@@ -76,3 +76,65 @@ def test_encode_image_pil_equals_reference_processor_path():
     ids_gpu_pre = tok.encode(tok.gpu_processor(pil))
     ids_cpu_pre = tok.encode(tok.processor(pil).to("cuda"))
     assert torch.equal(ids_gpu_pre, ids_cpu_pre)
+
+
+# keep_ratio=True: Resize(224) -> CenterCrop(224), the DEFAULT of models/transforms.py:4-12
+KEEP_SIZES = [(224, 224), (480, 640), (640, 480), (1000, 800), (225, 223), (333, 500), (500, 333), (224, 1000), (1000, 224),
+              (100, 224), (449, 448), (448, 449), (64, 48), (3, 500), (1536, 2048), (301, 299), (227, 226)]
+
+
+@pytest.mark.parametrize("h,w", KEEP_SIZES)
+def test_preprocess_keep_ratio_bit_exact_vs_torchvision(h, w):
+    """windowed resample (seedb200_preprocess_create_ex) == torchvision Resize(224) + CenterCrop(224) + ToTensor +
+    Normalize on the same bytes, including torchvision's int(size * long / short) and round-half-even crop origin"""
+    from models.transforms import get_gpu_transform, get_transform
+
+    img = Image.fromarray(rand_image(h, w, seed=h * 13 + w), "RGB")
+    ref = get_transform("clip", keep_ratio=True, image_size=224)(img).half()
+    out = get_gpu_transform("clip", keep_ratio=True, image_size=224)(img)
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (3, 224, 224)
+    assert torch.equal(out.cpu().view(torch.int16), ref.view(torch.int16)), \
+        f"{(out.cpu().float() - ref.float()).abs().max().item()} max abs diff"
+
+
+def test_keep_ratio_geometry_matches_torchvision_functional():
+    import torchvision.transforms.functional as TF
+
+    from seed_b200.preprocess import keep_ratio_geometry
+
+    for h, w in KEEP_SIZES + [(225, 224), (226, 224), (224, 227), (1001, 333)]:
+        img = Image.new("RGB", (w, h))
+        r = TF.resize(img, 224)
+        (rh, rw), (top, left) = keep_ratio_geometry(h, w, 224)
+        assert (r.size[1], r.size[0]) == (rh, rw), (h, w)
+        # crop origin: feed a coordinate ramp through center_crop and read where it starts
+        ramp = torch.arange(rh * rw).reshape(1, rh, rw)
+        c = TF.center_crop(ramp, 224)
+        assert int(c[0, 0, 0]) == top * rw + left, (h, w, top, left)
+
+
+def test_plan_cache_is_bounded_lru():
+    """a stream of heterogeneous image sizes must not accumulate one plan (with its device buffers) per size"""
+    from seed_b200.preprocess import GpuClipTransform
+
+    t = GpuClipTransform(224, "bicubic", max_batch=2, max_plans=3)
+    sizes = [(100 + 7 * i, 90 + 5 * i) for i in range(8)]
+    torch.cuda.synchronize()
+    base = torch.cuda.memory_allocated()
+    free0 = torch.cuda.mem_get_info()[0]
+    for rep in range(3):
+        for (h, w) in sizes:
+            img = Image.fromarray(rand_image(h, w, seed=h), "RGB")
+            out = t(img)
+            assert len(t._plans) <= 3
+    ref = reference_pipeline("bicubic")(Image.fromarray(rand_image(*sizes[-1], seed=sizes[-1][0]), "RGB")).half()
+    assert torch.equal(out.cpu().view(torch.int16), ref.view(torch.int16))
+    assert list(t._plans)[-1] == sizes[-1]                      # most recently used last
+    # a re-used size moves to the back instead of being rebuilt
+    p = t._plans[sizes[-2]]
+    t(Image.fromarray(rand_image(*sizes[-2], seed=1), "RGB"))
+    assert t._plans[sizes[-2]] is p and list(t._plans)[-1] == sizes[-2]
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 64 * 2 ** 20                          # plans are cudaMalloc'ed outside torch: bounded growth
