@@ -57,9 +57,10 @@ void seedb200_reset_launch_count(void);
  * the calling thread is bracketed by CUDA events on its stream.  end() synchronises, then reports for
  * kind 0 (tcgen05 GEMM) and kind 1 (attention): launches, summed device milliseconds and, for the GEMM, the
  * summed algorithmic FLOPs (2*M*N*K per launch).  out[kind*3 + {0,1,2}] = {launches, ms, flops}. */
-/* Process-wide switches (tests / A-B measurements).  "vit_attention_tc": 2 (default) routes the 257x257x88
- * ViT attention to the staggered tcgen05 kernel (attention_tc2.cu), 1 to the lock-step tcgen05 kernel
- * (attention_tc.cu), 0 to the mma.sync kernel (attention.cu).
+/* Process-wide switches (tests / A-B measurements).  "vit_attention_tc": 1 (default) routes the 257x257x88
+ * ViT attention to the tcgen05 kernel attention_tc.cu, 2 to its staggered-pipeline variant attention_tc2.cu (same
+ * results; measured slower while both are bound by the per-SM load/store unit, profiles/r02_attention.md), 0 to the
+ * mma.sync kernel (attention.cu).
  * "causal_attention_tc": 1 (default) routes causal head_dim-128 attention with nq >= 128 (LLaMA prefill) to the
  * tcgen05 kernel (attention_causal_tc.cu), 0 to the mma.sync kernel.
  * "decode_pdl": 1 (default) launches the kernels of the cached decode step (q_len 1) with programmatic stream

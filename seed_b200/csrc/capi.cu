@@ -1,7 +1,9 @@
 // capi.cu -- C-ABI plumbing shared by every entry point: thread-local error text, launch counter,
 // device query, and the stand-alone RoPE entry (which owns a small cache of cos/sin tables).
 #include <stdarg.h>
+#include <ctype.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -46,7 +48,17 @@ void profile_mark_end(int kind, cudaStream_t stream, double flops) {
 }
 
 static std::map<std::string, int>& options() {
-  static std::map<std::string, int> o = {{"vit_attention_tc", 2}, {"causal_attention_tc", 1}, {"decode_pdl", 1}, {"gemv_ksplit", 0}, {"gemm_ksub", 0}, {"gemm_tail", 1}, {"encoder_ln_fold", 1}};
+  static std::map<std::string, int> o = [] {
+    std::map<std::string, int> m = {{"vit_attention_tc", 1}, {"causal_attention_tc", 1}, {"decode_pdl", 1}, {"gemv_ksplit", 0},
+                                    {"gemm_ksub", 0}, {"gemm_tail", 1}, {"encoder_ln_fold", 1}};
+    // A/B runs of unmodified commands (bench.py): SEEDB200_OPT_<KEY>=<int> overrides a default at load time
+    for (auto& kv : m) {
+      std::string env = "SEEDB200_OPT_";
+      for (char ch : kv.first) env += (char)toupper((unsigned char)ch);
+      if (const char* v = getenv(env.c_str())) kv.second = atoi(v);
+    }
+    return m;
+  }();
   return o;
 }
 static long long g_dbg_ptr = 0;

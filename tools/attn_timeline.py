@@ -1,13 +1,13 @@
 """Per-role clock64 timeline of block 0 of a tcgen05 ViT attention kernel, plus the kernel time at the bench shape.
 
-    python tools/attn_timeline.py [variant]        variant 2 (default): attention_tc2.cu, 1: attention_tc.cu
+    python tools/attn_timeline.py [variant]        variant 1 (default): attention_tc.cu, 2: attention_tc2.cu
 """
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from seed_b200 import lib as L
 
-variant = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+variant = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 H, N, D = 16, 257, 88
 lib = L.load()
 
@@ -44,7 +44,7 @@ lib.seedb200_debug_set_attn_timeline(dbg.data_ptr())
 L.attention(q, k, v, D ** -0.5, False)
 torch.cuda.synchronize()
 lib.seedb200_debug_set_attn_timeline(None)
-L.set_option("vit_attention_tc", 2)
+L.set_option("vit_attention_tc", 1)
 t = dbg.cpu().view(16, 64, 8)
 if variant == 2:
     names = {0: "softmax w0", 4: "softmax w4", 8: "mma", 9: "row256", 10: "loader 0", 13: "loader 3"}
