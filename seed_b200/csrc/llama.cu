@@ -38,6 +38,7 @@ struct seedb200_llama {
   int max_pos;
   __half *x, *nb, *qkv, *q, *att, *gu, *hn, *last;
   float* da_ws;
+  int* da_tickets;
   int last_T;
   int device;
   // ---- device-resident generation loop (seedb200_llama_generate) ----
@@ -136,7 +137,9 @@ static int llama_build(seedb200_llama* m) {
   SB_PROPAGATE(llama_alloc(m, &m->gu, T * ffn));
   SB_PROPAGATE(llama_alloc(m, &m->hn, T * h));
   SB_PROPAGATE(llama_alloc(m, &m->last, (size_t)c.max_batch * h));
-  SB_PROPAGATE(llama_alloc(m, &m->da_ws, (size_t)c.max_batch * c.heads * 64 * (128 + 2)));
+  SB_PROPAGATE(llama_alloc(m, &m->da_ws, (size_t)c.max_batch * c.heads * decode_attention_max_splits(c.max_seq) * (128 + 2)));
+  SB_PROPAGATE(llama_alloc(m, &m->da_tickets, (size_t)c.max_batch * c.heads));   // zero now, left zero by every launch
+  SB_CHECK_CUDA(cudaMemsetAsync(m->da_tickets, 0, (size_t)c.max_batch * c.heads * sizeof(int), st));
   m->vpad = (c.vocab + 7) / 8 * 8;
   SB_PROPAGATE(llama_alloc(m, &m->gstate, 8));
   SB_PROPAGATE(llama_alloc(m, &m->gfinished, (size_t)c.max_batch));
@@ -191,7 +194,8 @@ static int llama_forward(seedb200_llama* m, const int64_t* input_ids, const void
     SB_PROPAGATE(rope_kv_append_tables(m->qkv, position_ids, B, S, H, D, past_len, c.max_seq, m->max_pos, m->cos_t,
                                        m->sin_t, m->q, L.k_cache, L.v_cache, st, dyn));
     if (S == 1) {
-      SB_PROPAGATE(decode_attention(m->q, L.k_cache, L.v_cache, m->att, B, H, D, kv_len, c.max_seq, scale, m->da_ws, st, dyn));
+      SB_PROPAGATE(decode_attention(m->q, L.k_cache, L.v_cache, m->att, B, H, D, kv_len, c.max_seq, scale, m->da_ws, st, dyn,
+                                    m->da_tickets));
     } else {
       seedb200_attn_desc a;
       memset(&a, 0, sizeof(a));

@@ -58,7 +58,7 @@ template <int M, int MODE, bool NORM>
 __global__ void __launch_bounds__(256)
 gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long long ldw, __half* __restrict__ out,
             const __half* __restrict__ residual, const __half* __restrict__ norm_w, float eps, int N, int K,
-            int ksplit, int iters, long long ldo) {
+            int ksplit, int iters, long long ldo, int pf_lines) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint4* xs = reinterpret_cast<uint4*>(smem_raw);     // [M][K/8]
   __shared__ float red[8];
@@ -90,6 +90,13 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
     for (int u = 0; u < 4; ++u) {
       const int vi = v0 + lane + u * 32;
       if (vi < v1) { wa[u] = __ldg(w0 + vi); wb[u] = __ldg(w1 + vi); }
+    }
+    // ... and the next pf_lines 128-byte lines of both rows go to L2: with programmatic dependent launch this CTA is
+    // resident long before its predecessor has finished, and the dependency wait + activation staging below would
+    // otherwise leave HBM idle (weights never depend on the predecessor).  Sized by the host to ~24 MB per launch.
+    for (int l = lane; l < pf_lines; l += 32) {
+      const int vi = v0 + 128 + l * 8;
+      if (vi < v1) { prefetch_l2(w0 + vi); prefetch_l2(w1 + vi); }
     }
   }
   pdl_trigger();
@@ -252,8 +259,12 @@ int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* resid
     int blocks = (n_tasks + tpi - 1) / tpi;                                                                \
     if (blocks > resident) blocks = resident;                                                              \
     const int iters = (n_tasks + blocks * tpi - 1) / (blocks * tpi);                                       \
+    /* L2 prefetch ahead of the dependency wait: ~24 MB per launch, spread over the tasks' first lines */    \
+    int pf_lines = get_option("gemv_prefetch_mb") > 0                                                       \
+                       ? (int)(((long long)get_option("gemv_prefetch_mb") << 20) / (2LL * n_tasks * 128)) : 0; \
+    if (pf_lines > (K * 2 / ksplit) / 128) pf_lines = (K * 2 / ksplit) / 128;                               \
     SB_CHECK_CUDA(launch_chain(kern, dim3(blocks), dim3(256), smem, stream, xp, wp, (long long)ldw, op, rp, np, eps, N, K, \
-                               ksplit, iters, (long long)ldo));                                            \
+                               ksplit, iters, (long long)ldo, pf_lines));                                  \
     SB_LAUNCH_CHECK();                                                                                     \
     return 0;                                                                                              \
   }
@@ -294,7 +305,7 @@ __host__ __device__ inline void da_split(int kv_len, int& nsplit, int& chunk) {
 __global__ void __launch_bounds__(128)
 decode_attn_partial(const __half* __restrict__ q, const __half* __restrict__ kc, const __half* __restrict__ vc,
                     float* __restrict__ ws, int H, int kv_len, int max_seq, int chunk, float scale_log2,
-                    const int* __restrict__ dyn) {
+                    const int* __restrict__ dyn, int* __restrict__ tickets, __half* __restrict__ out) {
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   int nsplit = gridDim.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -385,6 +396,30 @@ decode_attn_partial(const __half* __restrict__ q, const __half* __restrict__ kc,
   float* dst = ws + (((long long)b * H + h) * nsplit + split) * (DA_D + 2);
   if (tid == 0) { dst[0] = m_run; dst[1] = l_run; }
   dst[2 + tid] = o_run;
+  if (tickets == nullptr) return;              // two-kernel form: decode_attn_merge follows
+  // fused merge: the split that finishes last for this (b, h) combines all of them (one launch less per layer)
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int t = atomicAdd(&tickets[b * H + h], 1);
+    s_last = (t == nsplit - 1);
+    if (s_last) tickets[b * H + h] = 0;        // self-resetting: zero again for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* src = ws + ((long long)b * H + h) * nsplit * (DA_D + 2);
+  float mm = -INFINITY;
+  for (int sidx = 0; sidx < nsplit; ++sidx) mm = fmaxf(mm, __ldcg(src + sidx * (DA_D + 2)));
+  const float mu = (mm == -INFINITY) ? 0.0f : mm;
+  float ll = 0.0f, acc = 0.0f;
+  for (int sidx = 0; sidx < nsplit; ++sidx) {
+    const float c = exp2f(__ldcg(src + sidx * (DA_D + 2)) - mu);
+    ll += __ldcg(src + sidx * (DA_D + 2) + 1) * c;
+    acc += __ldcg(src + sidx * (DA_D + 2) + 2 + tid) * c;
+  }
+  out[((long long)b * H + h) * DA_D + tid] = __float2half_rn(ll > 0.0f ? acc / ll : 0.0f);
 }
 
 __global__ void __launch_bounds__(DA_D)
@@ -413,20 +448,26 @@ int decode_attention_max_splits(int max_seq) {
   return nsplit;
 }
 
+// workspace: [B*H*max_splits*(D+2)] floats of partials (+ [B*H] int tickets when `tickets` is NULL: zeroed here on
+// every call).  tickets != NULL: a caller-owned [>= B*H] int array that is zero on entry -- the kernel leaves it zero,
+// so a handle zeroes it once at create and never again.
 int decode_attention(const void* q, const void* k_cache, const void* v_cache, void* out, int B, int H, int D,
-                     int kv_len, int max_seq, float scale, void* workspace, cudaStream_t stream, const int* dyn) {
+                     int kv_len, int max_seq, float scale, void* workspace, cudaStream_t stream, const int* dyn,
+                     int* tickets) {
   SB_REQUIRE(D == DA_D, "decode_attention: head_dim %d unsupported (LLaMA uses 128)", D);
   SB_REQUIRE(dyn != nullptr || (kv_len >= 1 && kv_len <= max_seq), "decode_attention: kv_len %d outside [1,%d]", kv_len, max_seq);
   int nsplit, chunk;
   da_split(dyn != nullptr ? max_seq : kv_len, nsplit, chunk);    // dyn: grid for the longest cache, trimmed in-kernel
-  // the partial results of (b, h) are laid out with the split count the kernels derive for the ACTUAL length
+  if (tickets == nullptr) {
+    tickets = reinterpret_cast<int*>(static_cast<float*>(workspace) +
+                                     (size_t)B * H * decode_attention_max_splits(max_seq) * (DA_D + 2));
+    SB_CHECK_CUDA(cudaMemsetAsync(tickets, 0, (size_t)B * H * sizeof(int), stream));
+  }
   dim3 grid(nsplit, H, B);
   SB_CHECK_CUDA(launch_chain(decode_attn_partial, grid, dim3(128), 0, stream, static_cast<const __half*>(q),
                              static_cast<const __half*>(k_cache), static_cast<const __half*>(v_cache),
-                             static_cast<float*>(workspace), H, kv_len, max_seq, chunk, scale * 1.4426950408889634f, dyn));
-  SB_LAUNCH_CHECK();
-  SB_CHECK_CUDA(launch_chain(decode_attn_merge, dim3(B * H), dim3(DA_D), 0, stream, static_cast<const float*>(workspace),
-                             static_cast<__half*>(out), nsplit, dyn));
+                             static_cast<float*>(workspace), H, kv_len, max_seq, chunk, scale * 1.4426950408889634f, dyn,
+                             tickets, static_cast<__half*>(out)));
   SB_LAUNCH_CHECK();
   return 0;
 }
@@ -443,7 +484,8 @@ int seedb200_gemv(const void* x, const void* W, int64_t ldw, void* out, const vo
 }
 
 int64_t seedb200_decode_attention_workspace_bytes(int B, int H, int max_seq) {
-  return (int64_t)B * H * sb::decode_attention_max_splits(max_seq) * (sb::DA_D + 2) * (int64_t)sizeof(float);
+  return (int64_t)B * H * sb::decode_attention_max_splits(max_seq) * (sb::DA_D + 2) * (int64_t)sizeof(float) +
+         (int64_t)B * H * (int64_t)sizeof(int);
 }
 
 int seedb200_decode_attention(const void* q, const void* k_cache, const void* v_cache, void* out, int B, int H, int D,

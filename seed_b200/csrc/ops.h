@@ -39,7 +39,7 @@ int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* resid
 // dyn (optional, device): kv_len = dyn[0] + 1 at run time; the grid is then sized for max_seq keys
 int decode_attention(const void* q, const void* k_cache, const void* v_cache, void* out, int B, int H, int D,
                      int kv_len, int max_seq, float scale, void* workspace, cudaStream_t stream,
-                     const int* dyn = nullptr);
+                     const int* dyn = nullptr, int* tickets = nullptr);
 int decode_attention_max_splits(int max_seq);
 // sampler.cu
 struct GenParams { seedb200_sample_params sp; long long eos, pad; };
