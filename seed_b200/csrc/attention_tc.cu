@@ -16,15 +16,26 @@
 //     store O.
 // Synchronisation: tcgen05.commit -> mbarrier for "S ready" / "O ready", mbarrier arrives (one per compute
 // warp) for "P written" / "TMEM free", fence.proxy.async between generic-proxy smem writes and UMMA reads.
+#include <string.h>
+
 #include "common.cuh"
 #include "attention_tc_common.cuh"
 
 namespace sb {
 
+// TMA = true: Q and K arrive by TMA (3-D tensor maps over the packed qkv buffer: 88 elements per head slot with OOB zero
+// fill up to 96, 48 head slots, rows) in the K-major swizzled layouts the GEMM uses -- a 128-byte-swizzled block of head
+// dims 0..63 and a 64-byte-swizzled block of dims 64..95 -- instead of 16-byte cp.async copies into the no-swizzle
+// core-matrix layout: the cp.async path cost ~20 LSU cycles per 512 bytes (tools/attn_timeline.py: 5-8 k cycles per
+// operand), and the SM's one load/store unit was what bounded the kernel's period (profiles/r02_attention.md).
+// V (an MN-major operand) stays on the cp.async / no-swizzle path.
+template <bool TMA>
 __global__ void __launch_bounds__(VA_THREADS, 1)
-vit_attention_tc_kernel(const VitAttnParams p) {
+vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorMap tm_a64,
+                        const __grid_constant__ CUtensorMap tm_a32, const __grid_constant__ CUtensorMap tm_r64,
+                        const __grid_constant__ CUtensorMap tm_r32) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t base = TMA ? ((smem_u32(smem_raw) + 1023u) & ~1023u) : ((smem_u32(smem_raw) + 127u) & ~127u);
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sK0 = base, sQ0 = sK0 + VA_K_BYTES, sQ1 = sQ0 + VA_Q0_BYTES, sV0 = sQ1 + VA_Q1_BYTES;
   const uint32_t misc = sV0 + 2 * VA_V_BYTES;
@@ -42,10 +53,24 @@ vit_attention_tc_kernel(const VitAttnParams p) {
   uint8_t* gQ1 = gen + (sQ1 - base);
   uint8_t* gV0 = gen + (sV0 - base);
   const uint8_t* gK = gen + (sK0 - base);
+  // 16-byte chunk c (8 head dims) of row r of a Q / K buffer with `rows8` 8-row groups: the CUDA-core readers of the
+  // 257th token see either the no-swizzle core-matrix image or the two swizzled blocks (Swizzle<3,4,3> on 128-byte
+  // rows for dims 0..63, Swizzle<2,4,3> on 64-byte rows for dims 64..95)
+  auto qk_chunk = [&](const uint8_t* buf, int rows8, int r, int c) -> const uint4* {
+    if constexpr (TMA) {
+      if (c < 8) return reinterpret_cast<const uint4*>(buf + r * 128 + ((c ^ (r & 7)) << 4));
+      return reinterpret_cast<const uint4*>(buf + rows8 * 1024 + r * 64 + (((c - 8) ^ ((r >> 1) & 3)) << 4));
+    } else {
+      return reinterpret_cast<const uint4*>(buf + (uint32_t)(r >> 3) * VA_G + c * 128 + (r & 7) * 16);
+    }
+  };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
+    if constexpr (TMA) {
+      tma_prefetch_desc(&tm_a64); tma_prefetch_desc(&tm_a32); tma_prefetch_desc(&tm_r64); tma_prefetch_desc(&tm_r32);
+    }
     for (int u = 0; u < 2; ++u) {
       mbar_init(bar_s + 8 * u, 1); mbar_init(bar_p + 8 * u, 4); mbar_init(bar_o + 8 * u, 1); mbar_init(bar_free + 8 * u, 4);
       mbar_init(q_full + 8 * u, 1);
@@ -91,6 +116,31 @@ vit_attention_tc_kernel(const VitAttnParams p) {
       VA_STAMP(10 + which, 0);
       mbar_wait_relaxed(empty, par ^ 1);    // previous contents consumed (passes immediately the first time)
       VA_STAMP(10 + which, 1);
+      if constexpr (TMA) {
+        if (which < 3) {
+          // one thread, a handful of bulk-tensor copies: 128-row boxes of the two swizzled blocks (+ row 256 alone)
+          if (lane == 0) {
+            const int slot = (which == 1 ? 16 : 0) + h;          // q heads 0..15, k heads 16..31 (v: 32..47)
+            const int grow = b * VA_N + row0;
+            const int rows8 = which == 0 ? 16 : (which == 1 ? 33 : 17);
+            const uint32_t b0 = dst, b1 = dst + rows8 * 1024;
+            const int big = which == 1 ? 2 : 1;                  // 128-row boxes
+            const bool last_row = which != 0;                    // K and the second Q buffer also hold token 256
+            mbar_arrive_expect_tx(full, (uint32_t)(big * 128 * 192 + (last_row ? 192 : 0)));
+            for (int i = 0; i < big; ++i) {
+              tma_load_3d(b0 + i * 128 * 128, &tm_a64, full, 0, slot, grow + i * 128);
+              tma_load_3d(b1 + i * 128 * 64, &tm_a32, full, 64, slot, grow + i * 128);
+            }
+            if (last_row) {
+              const int lr = big * 128;                          // local row of token 256 (start of its own 8-row group)
+              tma_load_3d(b0 + lr * 128, &tm_r64, full, 0, slot, grow + lr);
+              tma_load_3d(b1 + lr * 64, &tm_r32, full, 64, slot, grow + lr);
+            }
+          }
+          VA_STAMP(10 + which, 3);
+          continue;
+        }
+      }
       const int groups = (rows + 7) >> 3;
       const __half* rp = src + (long long)(row0 + r8) * ts + cq * 8;
       uint32_t dp = dst + cq * 128 + r8 * 16;
@@ -119,10 +169,22 @@ vit_attention_tc_kernel(const VitAttnParams p) {
         const uint32_t sV = sV0 + vb * VA_V_BYTES;
         auto issue_s = [&](int u) {             // S_u = Q_u K^T (keys 0..255) into the tile's 256 TMEM columns
           const uint32_t qa = u == 0 ? sQ0 : sQ1;
+          if constexpr (TMA) {
+            const uint32_t qa1 = qa + (u == 0 ? 16 : 17) * 1024, ka1 = sK0 + 33 * 1024;    // the 64-byte-swizzled blocks
 #pragma unroll
-          for (int j = 0; j < VA_DP / 16; ++j)
-            umma_f16<1>(tmem + u * VA_TILE_COLS, make_desc_nosw(qa + j * 256, 128, VA_G),
-                        make_desc_nosw(sK0 + j * 256, 128, VA_G), IDESC_S256, j > 0);
+            for (int j = 0; j < 4; ++j)              // head dims 0..63: +32 bytes per 16-element k-step inside the atom
+              umma_f16<1>(tmem + u * VA_TILE_COLS, make_smem_desc_sw128(qa) + 2 * j, make_smem_desc_sw128(sK0) + 2 * j,
+                          IDESC_S256, j > 0);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)              // head dims 64..95 (88..95 are the TMA's zero fill)
+              umma_f16<1>(tmem + u * VA_TILE_COLS, make_smem_desc_sw64(qa1) + 2 * j, make_smem_desc_sw64(ka1) + 2 * j,
+                          IDESC_S256, 1u);
+          } else {
+#pragma unroll
+            for (int j = 0; j < VA_DP / 16; ++j)
+              umma_f16<1>(tmem + u * VA_TILE_COLS, make_desc_nosw(qa + j * 256, 128, VA_G),
+                          make_desc_nosw(sK0 + j * 256, 128, VA_G), IDESC_S256, j > 0);
+          }
           umma_commit<1>(bar_s + 8 * u);
           umma_commit<1>(q_empty + 8 * u);      // the Q rows may be overwritten once S has retired (and the softmax
         };                                      // warps have read their rows for key 256)
@@ -176,8 +238,8 @@ vit_attention_tc_kernel(const VitAttnParams p) {
       // score of key 256: lanes 0..10 take one 8-dim chunk each
       float part = 0.0f;
       if (lane < CH) {
-        const uint4 qa = *reinterpret_cast<const uint4*>(gQ1 + 16 * VA_G + lane * 128);
-        const uint4 ka = *reinterpret_cast<const uint4*>(gK + 32 * VA_G + lane * 128);
+        const uint4 qa = *qk_chunk(gQ1, 17, 128, lane);   // query row 256 = local row 128 of the second Q buffer
+        const uint4 ka = *qk_chunk(gK, 33, 256, lane);    // key row 256
         const __half2* q2 = reinterpret_cast<const __half2*>(&qa);
         const __half2* k2 = reinterpret_cast<const __half2*>(&ka);
 #pragma unroll
@@ -226,7 +288,6 @@ vit_attention_tc_kernel(const VitAttnParams p) {
     const int rl = quarter * 32 + lane;               // row inside the tile: one full row (256 + 1 keys) per thread
     const int row = u * 128 + rl;
     const uint32_t trow = tmem + u * VA_TILE_COLS + ((uint32_t)(quarter * 32) << 16);
-    const uint8_t* qrow = (u == 0 ? gQ0 : gQ1) + (uint32_t)(rl >> 3) * VA_G + (rl & 7) * 16;
     uint32_t n = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
       const int b = item / p.heads, h = item - b * p.heads;
@@ -240,15 +301,12 @@ vit_attention_tc_kernel(const VitAttnParams p) {
       VA_STAMP(warp, 1);
       float s256 = 0.0f, t256 = 0.0f;
       {
-        const uint8_t* k256 = gK + 32 * VA_G;              // row 256 = first row of group 32
-        const uint8_t* q256 = gQ1 + 16 * VA_G;             // local row 128 of the second Q buffer
-        const uint8_t* krow = gK + (uint32_t)(row >> 3) * VA_G + (row & 7) * 16;    // key index == row index
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
-          const uint4 qa = *reinterpret_cast<const uint4*>(qrow + c * 128);
-          const uint4 ka = *reinterpret_cast<const uint4*>(k256 + c * 128);
-          const uint4 qb = *reinterpret_cast<const uint4*>(q256 + c * 128);
-          const uint4 kb_ = *reinterpret_cast<const uint4*>(krow + c * 128);
+          const uint4 qa = *qk_chunk(u == 0 ? gQ0 : gQ1, u == 0 ? 16 : 17, rl, c);    // this thread's query row
+          const uint4 ka = *qk_chunk(gK, 33, 256, c);                                  // key 256
+          const uint4 qb = *qk_chunk(gQ1, 17, 128, c);                                 // query 256
+          const uint4 kb_ = *qk_chunk(gK, 33, row, c);                                 // key index == row index
           const __half2* q2 = reinterpret_cast<const __half2*>(&qa);
           const __half2* k2 = reinterpret_cast<const __half2*>(&ka);
           const __half2* q3 = reinterpret_cast<const __half2*>(&qb);
@@ -446,11 +504,54 @@ bool vit_attention_tc_applicable(const seedb200_attn_desc& d) {
          (reinterpret_cast<uintptr_t>(d.o) & 15) == 0;
 }
 
+typedef CUresult (*EncodeTiledFnA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 3-D map over the packed projection buffer: (88 elements of a head | 48 head slots = q, k, v x 16 | token rows)
+static int make_qkv_tmap(CUtensorMap* tm, const void* base, long long rows, long long pitch_elems, int box_elems,
+                         int box_rows, CUtensorMapSwizzle swz) {
+  static EncodeTiledFnA fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFnA>(ptr);
+  }
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return SEEDB200_ERR_CUDA;
+  }
+  cuuint64_t gdim[3] = {(cuuint64_t)VA_D, 48, (cuuint64_t)rows};
+  cuuint64_t gstr[2] = {(cuuint64_t)VA_D * 2, (cuuint64_t)pitch_elems * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_elems, 1, (cuuint32_t)box_rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("vit_attention: cuTensorMapEncodeTiled failed with CUresult %d (box %d x %d)", (int)r, box_elems, box_rows);
+    return SEEDB200_ERR_CUDA;
+  }
+  return 0;
+}
+
+int get_option(const char* key);
+
 int vit_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream) {
-  static bool attr_set_dev[SB_MAX_DEVICES] = {};   // cudaFuncSetAttribute is per device
-  bool& attr_set = attr_set_dev[cur_device()];
+  // TMA needs q, k, v to be the [B*257, 3, 16, 88] views of ONE projection buffer (what the fused qkv GEMM writes,
+  // eva_vit.py:133-138); any other strided layout takes the cp.async loaders
+  const __half* qp = static_cast<const __half*>(d.q);
+  const bool packed = d.heads == 16 && d.q_hs == VA_D && d.k_hs == VA_D && d.q_ts == d.k_ts && d.q_ts % 8 == 0 &&
+                      d.q_ts >= 48 * VA_D && d.q_bs == (int64_t)VA_N * d.q_ts && d.k_bs == d.q_bs &&
+                      static_cast<const __half*>(d.k) == qp + 16 * VA_D && (reinterpret_cast<uintptr_t>(qp) & 15) == 0;
+  const bool tma = packed && get_option("vit_attention_tma") != 0;
+  auto kern = tma ? vit_attention_tc_kernel<true> : vit_attention_tc_kernel<false>;
+  static bool attr_set_dev[SB_MAX_DEVICES][2] = {};   // cudaFuncSetAttribute is per device
+  bool& attr_set = attr_set_dev[cur_device()][tma ? 1 : 0];
   if (!attr_set) {
-    SB_CHECK_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VA_SMEM));
+    SB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, VA_SMEM));
     attr_set = true;
   }
   VitAttnParams p;
@@ -463,10 +564,19 @@ int vit_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream) {
   p.items = d.batch * d.heads; p.heads = d.heads;
   p.scale_log2 = d.scale * 1.4426950408889634f;
   p.dbg = reinterpret_cast<long long*>(static_cast<uintptr_t>(get_option64("vit_attention_dbg_ptr")));
+  CUtensorMap ta64, ta32, tr64, tr32;
+  memset(&ta64, 0, sizeof(ta64)); ta32 = ta64; tr64 = ta64; tr32 = ta64;
+  if (tma) {
+    const long long rows = (long long)d.batch * VA_N;
+    SB_PROPAGATE(make_qkv_tmap(&ta64, qp, rows, d.q_ts, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B));
+    SB_PROPAGATE(make_qkv_tmap(&ta32, qp, rows, d.q_ts, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B));
+    SB_PROPAGATE(make_qkv_tmap(&tr64, qp, rows, d.q_ts, 64, 1, CU_TENSOR_MAP_SWIZZLE_128B));
+    SB_PROPAGATE(make_qkv_tmap(&tr32, qp, rows, d.q_ts, 32, 1, CU_TENSOR_MAP_SWIZZLE_64B));
+  }
   int grid = num_sms();
   if (grid > p.items) grid = p.items;
   profile_mark_begin(1, stream);
-  vit_attention_tc_kernel<<<grid, VA_THREADS, VA_SMEM, stream>>>(p);
+  kern<<<grid, VA_THREADS, VA_SMEM, stream>>>(p, ta64, ta32, tr64, tr32);
   profile_mark_end(1, stream, 4.0 * (double)d.batch * d.heads * (double)d.nq * d.nk * d.head_dim);
   SB_LAUNCH_CHECK();
   return 0;

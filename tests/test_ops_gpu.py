@@ -238,17 +238,20 @@ def test_vit_attention_tcgen05_vs_mma_paths(lib, B, use_tc):
     qkv = rand16(B * N, 3 * H * D, seed=34)
     v4 = qkv.view(B, N, 3, H, D)
     q, k, v = (v4[:, :, i].permute(0, 2, 1, 3) for i in range(3))
-    lib.set_option("vit_attention_tc", use_tc)
-    try:
-        o = lib.attention(q, k, v, D ** -0.5, False)
-        torch.cuda.synchronize()
-    finally:
-        lib.set_option("vit_attention_tc", VIT_TC_DEFAULT)
     ref = R.attention_ref(q, k, v, D ** -0.5, False)
-    assert rel_err(o, ref) < 2e-3, rel_err(o, ref)
-    assert (o.float() - ref.float()).abs().max().item() < 1e-2
-    # the 257th query row is computed outside the MMA tiles: check it on its own
-    assert rel_err(o[:, 256], ref[:, 256]) < 2e-3
+    for tma in ((1, 0) if use_tc == 1 else (1,)):     # kernel 1: Q/K by TMA (swizzled blocks) and by cp.async (no swizzle)
+        lib.set_option("vit_attention_tc", use_tc)
+        lib.set_option("vit_attention_tma", tma)
+        try:
+            o = lib.attention(q, k, v, D ** -0.5, False)
+            torch.cuda.synchronize()
+        finally:
+            lib.set_option("vit_attention_tc", VIT_TC_DEFAULT)
+            lib.set_option("vit_attention_tma", 1)
+        assert rel_err(o, ref) < 2e-3, (tma, rel_err(o, ref))
+        assert (o.float() - ref.float()).abs().max().item() < 1e-2
+        # the 257th query row is computed outside the MMA tiles: check it on its own
+        assert rel_err(o[:, 256], ref[:, 256]) < 2e-3
 
 
 def test_vit_attention_variants_agree_on_large_scores(lib):

@@ -20,8 +20,9 @@ def make(B):
 
 # kernel time at the bench shape (B = 256: 4096 items over 148 persistent CTAs), both variants
 q, k, v = make(256)
-for var in (1, 2):
+for var, tma in ((1, 1), (1, 0), (2, 0)):
     L.set_option("vit_attention_tc", var)
+    L.set_option("vit_attention_tma", tma)
     for _ in range(3):
         L.attention(q, k, v, D ** -0.5, False)
     torch.cuda.synchronize()
@@ -31,10 +32,11 @@ for var in (1, 2):
         s.record(); L.attention(q, k, v, D ** -0.5, False); e.record(); torch.cuda.synchronize()
         ts.append(s.elapsed_time(e))
     ts.sort()
-    print(f"variant {var}: B=256 kernel time min {ts[0]:.4f} ms  median {ts[len(ts)//2]:.4f} ms "
+    print(f"variant {var} (Q/K by {'TMA' if tma and var == 1 else 'cp.async'}): B=256 kernel time min {ts[0]:.4f} ms  median {ts[len(ts)//2]:.4f} ms "
           f"({4.0 * 256 * H * N * N * D / ts[0] / 1e9:.0f} TFLOP/s)")
 
 L.set_option("vit_attention_tc", variant)
+L.set_option("vit_attention_tma", 1)
 q, k, v = make(64)
 dbg = torch.zeros(16 * 64 * 8, dtype=torch.int64, device="cuda")
 for _ in range(2):
