@@ -288,45 +288,49 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
     const int rl = quarter * 32 + lane;               // row inside the tile: one full row (256 + 1 keys) per thread
     const int row = u * 128 + rl;
     const uint32_t trow = tmem + u * VA_TILE_COLS + ((uint32_t)(quarter * 32) << 16);
+    // ---- the 257th token on the CUDA cores: s256 = q_row . k_256 (key 256 for this thread's row) and
+    //      t = q_256 . k_key (this thread's key for query row 256, left in s_cls for the row-256 warp).  The dot products
+    //      of item n+1 are computed while the P.V MMA of item n runs (its Q and K are already in shared memory: both S
+    //      MMAs of item n retired long ago and the TMA refills the buffers in ~1 k cycles), so they are off the
+    //      S -> softmax -> P.V -> read-out chain; only item 0's are exposed.
+    auto dots = [&](uint32_t nn) -> float {
+      const uint32_t pq = nn & 1;
+      mbar_wait_relaxed(q_full + 8 * u, pq);
+      if (u == 0) mbar_wait_relaxed(q_full + 8, pq);                // query row 256 lives in the second Q buffer
+      mbar_wait_relaxed(k_full, pq);
+      float s256 = 0.0f, t256 = 0.0f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const uint4 qa = *qk_chunk(u == 0 ? gQ0 : gQ1, u == 0 ? 16 : 17, rl, c);    // this thread's query row
+        const uint4 ka = *qk_chunk(gK, 33, 256, c);                                  // key 256
+        const uint4 qb = *qk_chunk(gQ1, 17, 128, c);                                 // query 256
+        const uint4 kb_ = *qk_chunk(gK, 33, row, c);                                 // key index == row index
+        const __half2* q2 = reinterpret_cast<const __half2*>(&qa);
+        const __half2* k2 = reinterpret_cast<const __half2*>(&ka);
+        const __half2* q3 = reinterpret_cast<const __half2*>(&qb);
+        const __half2* k3 = reinterpret_cast<const __half2*>(&kb_);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 qf = __half22float2(q2[j]), kf = __half22float2(k2[j]);
+          const float2 qg = __half22float2(q3[j]), kg = __half22float2(k3[j]);
+          s256 = fmaf(qf.x, kf.x, s256);
+          s256 = fmaf(qf.y, kf.y, s256);
+          t256 = fmaf(qg.x, kg.x, t256);
+          t256 = fmaf(qg.y, kg.y, t256);
+        }
+      }
+      s_clsb[(nn & 1) * VA_CLS_LD + row] = t256;
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(q_empty + 8 * u); if (u == 0) mbar_arrive(q_empty + 8); mbar_arrive(k_empty); mbar_arrive(cls_bar); }
+      return s256;
+    };
     uint32_t n = 0;
+    float s256 = 0.0f;
+    if ((int)blockIdx.x < p.items) s256 = dots(0);
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
       const int b = item / p.heads, h = item - b * p.heads;
       const uint32_t vb = n & 1, pn = n & 1;
-      // ---- the 257th token on the CUDA cores, under the S MMA (which covers keys 0..255 x rows 0..255):
-      //      s256 = q_row . k_256 (key 256 for this thread's row) and t = q_256 . k_key (this thread's key for row 256)
       VA_STAMP(warp, 0);
-      mbar_wait_relaxed(q_full + 8 * u, pn);
-      if (u == 0) mbar_wait_relaxed(q_full + 8, pn);                // query row 256 lives in the second Q buffer
-      mbar_wait_relaxed(k_full, pn);
-      VA_STAMP(warp, 1);
-      float s256 = 0.0f, t256 = 0.0f;
-      {
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const uint4 qa = *qk_chunk(u == 0 ? gQ0 : gQ1, u == 0 ? 16 : 17, rl, c);    // this thread's query row
-          const uint4 ka = *qk_chunk(gK, 33, 256, c);                                  // key 256
-          const uint4 qb = *qk_chunk(gQ1, 17, 128, c);                                 // query 256
-          const uint4 kb_ = *qk_chunk(gK, 33, row, c);                                 // key index == row index
-          const __half2* q2 = reinterpret_cast<const __half2*>(&qa);
-          const __half2* k2 = reinterpret_cast<const __half2*>(&ka);
-          const __half2* q3 = reinterpret_cast<const __half2*>(&qb);
-          const __half2* k3 = reinterpret_cast<const __half2*>(&kb_);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 qf = __half22float2(q2[j]), kf = __half22float2(k2[j]);
-            const float2 qg = __half22float2(q3[j]), kg = __half22float2(k3[j]);
-            s256 = fmaf(qf.x, kf.x, s256);
-            s256 = fmaf(qf.y, kf.y, s256);
-            t256 = fmaf(qg.x, kg.x, t256);
-            t256 = fmaf(qg.y, kg.y, t256);
-          }
-        }
-      }
-      s_clsb[(n & 1) * VA_CLS_LD + row] = t256;
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(q_empty + 8 * u); if (u == 0) mbar_arrive(q_empty + 8); mbar_arrive(k_empty); mbar_arrive(cls_bar); }
-
-      VA_STAMP(warp, 2);
       mbar_wait_relaxed(bar_s + 8 * u, pn);
       tc_fence_after();
       VA_STAMP(warp, 3);
@@ -445,6 +449,11 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
           p.o[b * p.o_bs + h * p.o_hs + (long long)(VA_N - 1) * p.o_ts + tid] = __float2half_rn(acc / pc[VA_KP]);
         }
       }
+      VA_STAMP(warp, 1);
+      // next item's 257th-token dot products, in the same shadow
+      float s256_next = 0.0f;
+      if (item + (int)gridDim.x < p.items) s256_next = dots(n + 1);
+      VA_STAMP(warp, 2);
       const float inv = 1.0f / sum;
       const float w256 = p256 * inv;
       mbar_wait_relaxed(bar_o + 8 * u, pn);
@@ -489,6 +498,7 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
       __syncwarp();
       if (lane == 0) mbar_arrive(v_empty + 8 * vb);         // V row 256 has been read
       VA_STAMP(warp, 7);
+      s256 = s256_next;
     }
   }
 

@@ -71,7 +71,14 @@ def test_encode_matches_reference_golden(name, ctas):
     # second return value of get_codebook_indices and the de-tokenizer head, driven by the REFERENCE ids
     ids2, qup = model.get_codebook_indices(x)
     assert torch.equal(ids2, ids)
-    assert sample_rel(qup, g["query_output_up"]) <= ACT_TOL
+    # query_output_up = decode_task_layer(codebook[id]): compare the tokens whose id is the reference's (a token under
+    # the id margin may legitimately pick the neighbouring code, and then decodes that code)
+    s = g["query_output_up"]
+    flat = qup.float().cpu().reshape(-1)[:: s["step"]]
+    tok = (torch.arange(flat.numel()) * s["step"]) // qup.shape[-1]
+    keep = (ids.cpu().reshape(-1) == g["ids"].reshape(-1))[tok]
+    assert int((~keep).sum()) <= flips * (qup.shape[-1] // s["step"] + 1)
+    assert ((flat - s["values"])[keep].norm() / s["values"][keep].norm()).item() <= ACT_TOL
     emb = model.get_codebook_entry(g["ids"].cuda())
     assert tuple(emb.shape) == (c["batch"], 1024)
     assert rel(emb, g["image_embeds_out"]) <= ACT_TOL, rel(emb, g["image_embeds_out"])

@@ -59,7 +59,7 @@ if variant == 2:
 else:
     names = {0: "softmax w0", 4: "softmax w4", 8: "mma", 9: "row256", 10: "ld Q0", 11: "ld K", 12: "ld Q1", 13: "ld V"}
     ev = {8: ["start", "S0 issue", "S1 issue", "wait v", "v ok", "PV0 issue", "PV1 issue", "end"],
-          0: ["start", "q,k ok", "s256 done", "S ok", "max done", "P done", "O ok", "end"],
+          0: ["start", "row256 share done", "next item's dots done", "S ok", "max done", "P done", "O ok", "end"],
           10: ["start", "empty ok", "issued", "full"], 9: ["start", "q,k ok", "key256", "scores ok", "p written"]}
     ev[4] = ev[0]; ev[11] = ev[12] = ev[13] = ev[10]
     t0 = int(t[8, 0, 0])
