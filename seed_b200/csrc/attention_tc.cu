@@ -232,8 +232,8 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
       float* cls = s_clsb + (n & 1) * VA_CLS_LD;
       VA_STAMP(9, 0);
-      mbar_wait(q_full + 8, n & 1);
-      mbar_wait(k_full, n & 1);
+      mbar_wait_relaxed(q_full + 8, n & 1);
+      mbar_wait_relaxed(k_full, n & 1);
       VA_STAMP(9, 1);
       // score of key 256: lanes 0..10 take one 8-dim chunk each
       float part = 0.0f;
@@ -253,7 +253,7 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
       __syncwarp();
       if (lane == 0) { mbar_arrive(k_empty); mbar_arrive(q_empty + 8); }
       VA_STAMP(9, 2);
-      mbar_wait(cls_bar, n & 1);                          // the 256 distributed scores are in cls[0..255]
+      mbar_wait_relaxed(cls_bar, n & 1);                  // the 256 distributed scores are in cls[0..255]
       VA_STAMP(9, 3);
       float sc[9];
       float mx = -INFINITY;

@@ -160,33 +160,49 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+// Bounded waits: a protocol bug traps (kernel error) instead of hanging the GPU.  The deadline is checked once every
+// 4096 polls only: a clock64() + compare per poll made the wait loops ~half of all instructions the attention kernel
+// issued (profiles/r02_attention.md) -- issue slots and power taken from the warps doing work.
 #ifndef SB_MBAR_TIMEOUT_CYCLES
 #define SB_MBAR_TIMEOUT_CYCLES (8000000000LL)
 #endif
+// try_wait that lets the hardware park the thread for up to `ns` nanoseconds before it reports "not yet"
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
+  printf("seedb200: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
+// latency-critical waits (MMA issuer, TMA producer): plain polling, deadline check amortised
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > SB_MBAR_TIMEOUT_CYCLES) {
-      printf("seedb200: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x,
-             bar, parity);
-      __trap();
-    }
+    if ((++polls & 4095u) == 0 && clock64() - t0 > SB_MBAR_TIMEOUT_CYCLES) mbar_timeout_trap(bar, parity);
   }
 }
 
-// Same, for waits that are expected to be long (loader warps waiting for a free buffer, softmax warps waiting for
-// an MMA): back off with nanosleep so that the polling warp does not steal issue slots from the warps doing work.
+// waits that are expected to be long (epilogue / softmax warps waiting for an MMA, loaders waiting for a free buffer):
+// the thread is parked by the hardware (suspend-time hint) instead of spinning, so it neither steals issue slots from
+// the warps doing work nor burns power polling.
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(40);
-    if (clock64() - t0 > SB_MBAR_TIMEOUT_CYCLES) {
-      printf("seedb200: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
+  uint32_t polls = 0;
+  while (!mbar_try_wait_hint(bar, parity, 2000u)) {
+    if ((++polls & 255u) == 0 && clock64() - t0 > SB_MBAR_TIMEOUT_CYCLES) mbar_timeout_trap(bar, parity);
   }
 }
 

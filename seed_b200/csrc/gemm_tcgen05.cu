@@ -286,7 +286,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t stage_tx = (uint32_t)(Cfg::A_BYTES + KSUB * load_n * GEMM_BLOCK_K * 2);
         const int n_idx = nt * BN + (int)cta_rank * load_n;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          mbar_wait_relaxed(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_a + stage * Cfg::A_BYTES;
           const uint32_t sb_ = smem_b + stage * Cfg::B_BYTES;
           if constexpr (CTAS == 1) {
@@ -429,7 +429,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       }
 
-      mbar_wait(tfull_bar + 8 * as, aphase);
+      mbar_wait_relaxed(tfull_bar + 8 * as, aphase);     // a whole tile of MMAs away: park, do not spin
       tc_fence_after();
       const uint32_t t_acc = tmem_base + as * Cfg::ACC_STRIDE + lane_addr;
       if (c_begin >= c_end) {       // (one-chunk tail tile: this warp has nothing to read, but still releases the stage)
