@@ -1,0 +1,52 @@
+"""The four ViT-g GEMM shapes exactly as the encode step launches them (M = 65 792 = 256 images x 257 tokens):
+qkv and fc1 with the LayerNorm-folded epilogue reading the residual stream itself, proj and fc2 with bias + in-place
+residual, BN = 256 CTA-pair tiles + narrow tail tile.  Warm-up round, then one launch per shape (for `ncu --set full`):
+
+    ncu --set full --clock-control none -k regex:gemm_tcgen05 --launch-skip 4 -c 4 -f -o gpurun_out/r02_gemm python tools/vit_gemm_capture.py
+"""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from seed_b200 import lib as L
+
+M, D, FF = 65792, 1408, 6144
+g = torch.Generator(device="cuda").manual_seed(1)
+def r(*s, std=1.0):
+    return (torch.randn(*s, device="cuda", generator=g) * std).half()
+
+x = r(M, D)
+gamma, beta = (1.0 + 0.1 * torch.randn(D, device="cuda")).half(), r(D, std=0.02)
+w_qkv, b_qkv = r(3 * D, D, std=D ** -0.5), r(3 * D, std=0.02)
+w_fc1, b_fc1 = r(FF, D, std=D ** -0.5), r(FF, std=0.02)
+w_proj, b_proj = r(D, D, std=D ** -0.5), r(D, std=0.02)
+w_fc2, b_fc2 = r(D, FF, std=FF ** -0.5), r(D, std=0.02)
+qkv_f = L.ln_fold_weights(w_qkv, gamma, beta, b_qkv)
+fc1_f = L.ln_fold_weights(w_fc1, gamma, beta, b_fc1)
+stats = L.row_stats(x, 1e-6)
+qkv = torch.empty(M, 3 * D, device="cuda", dtype=torch.float16)
+hid = torch.empty(M, FF, device="cuda", dtype=torch.float16)
+att = r(M, D)
+
+def run():
+    L.gemm(x, qkv_f[0], out=qkv, ctas=2, ln=(stats, qkv_f[1], qkv_f[2]))                       # norm1 + qkv
+    L.gemm(att, w_proj, bias=b_proj, residual=x, out=x, ctas=2)                                # proj + residual
+    L.gemm(x, fc1_f[0], act=L.ACT_GELU, out=hid, ctas=2, ln=(stats, fc1_f[1], fc1_f[2]))       # norm2 + fc1 + GELU
+    L.gemm(hid, w_fc2, bias=b_fc2, residual=x, out=x, ctas=2)                                  # fc2 + residual
+
+run(); torch.cuda.synchronize()
+run(); torch.cuda.synchronize()
+# event timing of the same four launches (not under ncu: compare)
+names = ["qkv_4224x1408_lnfold", "proj_1408x1408", "fc1_6144x1408_lnfold_gelu", "fc2_1408x6144"]
+flops = [2.0 * M * 3 * D * D, 2.0 * M * D * D, 2.0 * M * FF * D, 2.0 * M * D * FF]
+if "--time" in sys.argv:
+    fns = [lambda: L.gemm(x, qkv_f[0], out=qkv, ctas=2, ln=(stats, qkv_f[1], qkv_f[2])),
+           lambda: L.gemm(att, w_proj, bias=b_proj, residual=x, out=x, ctas=2),
+           lambda: L.gemm(x, fc1_f[0], act=L.ACT_GELU, out=hid, ctas=2, ln=(stats, fc1_f[1], fc1_f[2])),
+           lambda: L.gemm(hid, w_fc2, bias=b_fc2, residual=x, out=x, ctas=2)]
+    for nm, fl, fn in zip(names, flops, fns):
+        ts = []
+        for _ in range(6):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
+        print(json.dumps({"shape": nm, "ms": round(min(ts), 4), "tflops": round(fl / min(ts) / 1e9, 1)}))
+print("vit_gemm_capture done")
