@@ -519,7 +519,7 @@ typedef CUresult (*EncodeTiledFnA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 3-D map over the packed projection buffer: (88 elements of a head | 48 head slots = q, k, v x 16 | token rows)
-static int make_qkv_tmap(CUtensorMap* tm, const void* base, long long rows, long long pitch_elems, int box_elems,
+int make_qkv_tmap(CUtensorMap* tm, const void* base, long long rows, long long pitch_elems, int box_elems,
                          int box_rows, CUtensorMapSwizzle swz) {
   static EncodeTiledFnA fn = nullptr;
   if (fn == nullptr) {
@@ -549,14 +549,18 @@ static int make_qkv_tmap(CUtensorMap* tm, const void* base, long long rows, long
 
 int get_option(const char* key);
 
-int vit_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream) {
-  // TMA needs q, k, v to be the [B*257, 3, 16, 88] views of ONE projection buffer (what the fused qkv GEMM writes,
-  // eva_vit.py:133-138); any other strided layout takes the cp.async loaders
+// TMA needs q, k, v to be the [B*257, 3, 16, 88] views of ONE projection buffer (what the fused qkv GEMM writes,
+// eva_vit.py:133-138); any other strided layout takes the cp.async loaders
+bool vit_attention_packed_qkv(const seedb200_attn_desc& d) {
   const __half* qp = static_cast<const __half*>(d.q);
-  const bool packed = d.heads == 16 && d.q_hs == VA_D && d.k_hs == VA_D && d.q_ts == d.k_ts && d.q_ts % 8 == 0 &&
-                      d.q_ts >= 48 * VA_D && d.q_bs == (int64_t)VA_N * d.q_ts && d.k_bs == d.q_bs &&
-                      static_cast<const __half*>(d.k) == qp + 16 * VA_D && (reinterpret_cast<uintptr_t>(qp) & 15) == 0;
-  const bool tma = packed && get_option("vit_attention_tma") != 0;
+  return d.heads == 16 && d.q_hs == VA_D && d.k_hs == VA_D && d.q_ts == d.k_ts && d.q_ts % 8 == 0 &&
+         d.q_ts >= 48 * VA_D && d.q_bs == (int64_t)VA_N * d.q_ts && d.k_bs == d.q_bs &&
+         static_cast<const __half*>(d.k) == qp + 16 * VA_D && (reinterpret_cast<uintptr_t>(qp) & 15) == 0;
+}
+
+int vit_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream) {
+  const __half* qp = static_cast<const __half*>(d.q);
+  const bool tma = vit_attention_packed_qkv(d) && get_option("vit_attention_tma") != 0;
   auto kern = tma ? vit_attention_tc_kernel<true> : vit_attention_tc_kernel<false>;
   static bool attr_set_dev[SB_MAX_DEVICES][2] = {};   // cudaFuncSetAttribute is per device
   bool& attr_set = attr_set_dev[cur_device()][tma ? 1 : 0];

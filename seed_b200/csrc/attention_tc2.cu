@@ -9,8 +9,8 @@
 // P.V share, the O read-out) waited its turn in the same warps.  Here the two tiles are HALF A PERIOD APART:
 //   * the MMA warp is a two-stream state machine; S of tile 1 is issued only after P.V of tile 0 of the same item, so
 //     tile 1 runs its exponentials while tile 0 reads out / prepares the next item, and vice versa;
-//   * the four loader warps cooperate on ONE operand at a time (Q0, V, K, Q1 in the order their buffers come free),
-//     so K -- single buffered, freed only when S of tile 1 has retired -- is back ~1.2 k cycles later instead of ~8 k;
+//   * Q and K arrive by TMA (swizzled K-major blocks, as in attention_tc.cu), so K -- single buffered, freed only when
+//     S of tile 1 has retired -- is back ~1-3 k cycles later instead of ~8 k with cp.async;
 //   * the softmax row sums come out of the P.V MMA itself (V's padding column 88 holds 1.0), which removes the
 //     unpack + add per probability from the MUFU-bound pass;
 //   * the 257th query row: scores by the 256 softmax threads, softmax by warp 13, P.V spread over the softmax threads
@@ -19,13 +19,17 @@
 
 namespace sb {
 
-constexpr int V2_K_BYTES = 33 * VA_G;               // keys 0..263 (group 32: key 256 + zero rows)
-constexpr int V2_Q0_BYTES = 17 * VA_G;              // query rows 0..127, group 16 = query row 256 (+ zero rows)
-constexpr int V2_Q1_BYTES = 16 * VA_G;              // query rows 128..255
-constexpr int V2_V_BYTES = 33 * VA_G;               // keys 0..263, x2 buffers
+// Q and K live in the swizzled K-major blocks the TMA writes (see attention_tc.cu, TMA = true): per buffer a
+// 128-byte-swizzled block of head dims 0..63 (1024 B per 8-row group) followed by a 64-byte-swizzled block of dims
+// 64..95 (512 B per group).  Buffer order K, Q1, Q0, V keeps every swizzled block on its 1024 / 512-byte boundary.
+constexpr int V2_K_G = 33, V2_Q0_G = 17, V2_Q1_G = 16;   // 8-row groups: keys 0..256 | rows 0..127 + row 256 | rows 128..255
+constexpr int V2_K_BYTES = 34 * VA_G;               // 33 groups used; 34 keeps the next buffer 1024-byte aligned
+constexpr int V2_Q1_BYTES = V2_Q1_G * VA_G;
+constexpr int V2_Q0_BYTES = V2_Q0_G * VA_G;
+constexpr int V2_V_BYTES = 33 * VA_G;               // keys 0..263, x2 buffers, no-swizzle core-matrix image (cp.async)
 constexpr int V2_DATA_BYTES = V2_K_BYTES + V2_Q0_BYTES + V2_Q1_BYTES + 2 * V2_V_BYTES;
 constexpr int V2_MISC_BYTES = 2 * VA_CLS_LD * 4 + 2 * 8 * VA_PART_LD * 4 + 256;
-constexpr int V2_SMEM = V2_DATA_BYTES + V2_MISC_BYTES + 128;
+constexpr int V2_SMEM = V2_DATA_BYTES + V2_MISC_BYTES + 1024;
 
 __device__ __forceinline__ void cp_async_commit_tc() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
@@ -37,11 +41,13 @@ __device__ __forceinline__ uint32_t pack2_nosum(float a, float b) {
 }
 
 __global__ void __launch_bounds__(VA_THREADS, 1)
-vit_attention_tc2_kernel(const VitAttnParams p) {
+vit_attention_tc2_kernel(const VitAttnParams p, const __grid_constant__ CUtensorMap tm_a64,
+                         const __grid_constant__ CUtensorMap tm_a32, const __grid_constant__ CUtensorMap tm_r64,
+                         const __grid_constant__ CUtensorMap tm_r32) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sK0 = base, sQ0 = sK0 + V2_K_BYTES, sQ1 = sQ0 + V2_Q0_BYTES, sV0 = sQ1 + V2_Q1_BYTES;
+  const uint32_t sK0 = base, sQ1 = sK0 + V2_K_BYTES, sQ0 = sQ1 + V2_Q1_BYTES, sV0 = sQ0 + V2_Q0_BYTES;
   const uint32_t misc = sV0 + 2 * V2_V_BYTES;
   float* s_clsb = reinterpret_cast<float*>(gen + (misc - base));    // [2][VA_CLS_LD]: scores, then probabilities of row 256
   float* s_part = s_clsb + 2 * VA_CLS_LD;                           // [2][8][VA_PART_LD]: per-warp partial P.V of row 256
@@ -58,19 +64,25 @@ vit_attention_tc2_kernel(const VitAttnParams p) {
   uint8_t* gQ1 = gen + (sQ1 - base);
   uint8_t* gV0 = gen + (sV0 - base);
   const uint8_t* gK = gen + (sK0 - base);
+  // 16-byte chunk c (8 head dims) of row r of a swizzled Q / K buffer with `rows8` 8-row groups
+  auto qk_chunk = [&](const uint8_t* buf, int rows8, int r, int c) -> const uint4* {
+    if (c < 8) return reinterpret_cast<const uint4*>(buf + r * 128 + ((c ^ (r & 7)) << 4));
+    return reinterpret_cast<const uint4*>(buf + rows8 * 1024 + r * 64 + (((c - 8) ^ ((r >> 1) & 3)) << 4));
+  };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
+    tma_prefetch_desc(&tm_a64); tma_prefetch_desc(&tm_a32); tma_prefetch_desc(&tm_r64); tma_prefetch_desc(&tm_r32);
     for (int u = 0; u < 2; ++u) {
       mbar_init(bar_s + 8 * u, 1); mbar_init(bar_p + 8 * u, 4); mbar_init(bar_o + 8 * u, 1); mbar_init(bar_free + 8 * u, 4);
-      mbar_init(q_full + 8 * u, 4);        // one arrive per loader warp
-      mbar_init(v_full + 8 * u, 4);
+      mbar_init(q_full + 8 * u, 1);        // the TMA's expect_tx arrive
+      mbar_init(v_full + 8 * u, 1);
       mbar_init(v_empty + 8 * u, 9);       // P.V(1) retired + 8 softmax warps (row-256 share, value row 256)
     }
     mbar_init(q_empty, 10);                // S(0) retired + 8 softmax warps (tile-0 rows / query row 256) + warp 13
     mbar_init(q_empty + 8, 5);             // S(1) retired + 4 softmax warps of tile 1
-    mbar_init(k_full, 4);
+ mbar_init(k_full, 1);
     mbar_init(k_empty, 10);                // S(1) retired + 8 softmax warps + warp 13 (key row 256)
     mbar_init(cls_bar, 8);
     mbar_init(cls_p, 1);
@@ -100,52 +112,67 @@ vit_attention_tc2_kernel(const VitAttnParams p) {
   constexpr int CH = VA_D / 8;            // 11 16-byte chunks per row
 
   if (warp >= 8 && warp < 12) {
-    // ======================= loaders: the four warps share every operand =======================
-    // unit = (8-row group, chunk quad): one cp.async instruction moves 8 rows x 4 chunks (512 B) into 4 core-matrix
-    // columns; warp lw takes units lw, lw + 4, ...  Operands in the order their buffers come free in steady state.
-    const int lw = warp - 8;
+    // ======================= loaders: warp 8 = Q0 (+ query row 256), 9 = K, 10 = Q1 by TMA; warp 11 = V by cp.async ===========
+    const int which = warp - 8;
     const int r8 = lane & 7, cq = lane >> 3;
-    auto load = [&](const __half* src, long long ts, int row0, int rows, uint32_t dst, int g0) {
-      const int groups = (rows + 7) >> 3;
-      for (int unit = lw; unit < groups * 3; unit += 4) {
-        const int g = unit / 3, j = unit - g * 3;
-        const int chunk = j * 4 + cq;
-        if (g * 8 + r8 < rows && chunk < CH)
-          cp_async16_tc(dst + (uint32_t)(g0 + g) * VA_G + chunk * 128 + r8 * 16,
-                        src + (long long)(row0 + g * 8 + r8) * ts + chunk * 8);
-      }
-    };
-    auto publish = [&](uint32_t full) {
-      cp_async_wait_all_tc();
-      fence_proxy_async_smem();             // generic-proxy writes -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full);
-    };
     uint32_t n = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
       const int b = item / p.heads, h = item - b * p.heads;
-      const __half* qs = p.q + b * p.q_bs + h * p.q_hs;
-      const __half* ks = p.k + b * p.k_bs + h * p.k_hs;
-      const __half* vs = p.v + b * p.v_bs + h * p.v_hs;
       const uint32_t vb = n & 1, par = n & 1;
-      VA_STAMP(10 + lw, 0);
-      mbar_wait_relaxed(q_empty, par ^ 1);
-      load(qs, p.q_ts, 0, 128, sQ0, 0);
-      load(qs, p.q_ts, 256, 1, sQ0, 16);                            // query row 256 -> group 16
-      publish(q_full);
-      VA_STAMP(10 + lw, 1);
+      VA_STAMP(10 + which, 0);
+      if (which < 3) {
+        const uint32_t empty = which == 0 ? q_empty : (which == 1 ? k_empty : q_empty + 8);
+        const uint32_t full = which == 0 ? q_full : (which == 1 ? k_full : q_full + 8);
+        mbar_wait_relaxed(empty, par ^ 1);
+        VA_STAMP(10 + which, 1);
+        if (lane == 0) {
+          const int slot = (which == 1 ? 16 : 0) + h;            // q heads 0..15, k heads 16..31
+          const int grow = b * VA_N;
+          if (which == 0) {                                      // rows 0..127, then token 256 at local row 128
+            const uint32_t b0 = sQ0, b1 = sQ0 + V2_Q0_G * 1024;
+            mbar_arrive_expect_tx(full, 128 * 192 + 192);
+            tma_load_3d(b0, &tm_a64, full, 0, slot, grow);
+            tma_load_3d(b1, &tm_a32, full, 64, slot, grow);
+            tma_load_3d(b0 + 128 * 128, &tm_r64, full, 0, slot, grow + 256);
+            tma_load_3d(b1 + 128 * 64, &tm_r32, full, 64, slot, grow + 256);
+          } else if (which == 1) {                               // keys 0..255 in two boxes, key 256 alone
+            const uint32_t b0 = sK0, b1 = sK0 + V2_K_G * 1024;
+            mbar_arrive_expect_tx(full, 256 * 192 + 192);
+            for (int i = 0; i < 2; ++i) {
+              tma_load_3d(b0 + i * 128 * 128, &tm_a64, full, 0, slot, grow + i * 128);
+              tma_load_3d(b1 + i * 128 * 64, &tm_a32, full, 64, slot, grow + i * 128);
+            }
+            tma_load_3d(b0 + 256 * 128, &tm_r64, full, 0, slot, grow + 256);
+            tma_load_3d(b1 + 256 * 64, &tm_r32, full, 64, slot, grow + 256);
+          } else {                                               // rows 128..255
+            const uint32_t b0 = sQ1, b1 = sQ1 + V2_Q1_G * 1024;
+            mbar_arrive_expect_tx(full, 128 * 192);
+            tma_load_3d(b0, &tm_a64, full, 0, slot, grow + 128);
+            tma_load_3d(b1, &tm_a32, full, 64, slot, grow + 128);
+          }
+        }
+        VA_STAMP(10 + which, 3);
+        continue;
+      }
+      // V: no-swizzle core-matrix image (MN-major B operand of the P.V MMA), 16-byte cp.async copies
       mbar_wait_relaxed(v_empty + 8 * vb, ((n >> 1) & 1) ^ 1);
-      load(vs, p.v_ts, 0, VA_N, sV0 + vb * V2_V_BYTES, 0);
-      publish(v_full + 8 * vb);
-      VA_STAMP(10 + lw, 2);
-      mbar_wait_relaxed(k_empty, par ^ 1);
-      load(ks, p.k_ts, 0, VA_N, sK0, 0);
-      publish(k_full);
-      VA_STAMP(10 + lw, 3);
-      mbar_wait_relaxed(q_empty + 8, par ^ 1);
-      load(qs, p.q_ts, 128, 128, sQ1, 0);
-      publish(q_full + 8);
-      VA_STAMP(10 + lw, 4);
+      VA_STAMP(10 + which, 1);
+      const __half* rp = p.v + b * p.v_bs + h * p.v_hs + (long long)r8 * p.v_ts + cq * 8;
+      uint32_t dp = sV0 + vb * V2_V_BYTES + cq * 128 + r8 * 16;
+      for (int g = 0; g < 33; ++g) {
+        if (g * 8 + r8 < VA_N) {
+          cp_async16_tc(dp, rp);                                  // chunks 0..3
+          cp_async16_tc(dp + 4 * 128, rp + 32);                   // chunks 4..7
+          if (cq < 3) cp_async16_tc(dp + 8 * 128, rp + 64);       // chunks 8..10 (chunk 11: the ones column / padding)
+        }
+        rp += 8 * p.v_ts;
+        dp += VA_G;
+      }
+      cp_async_wait_all_tc();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(v_full + 8 * vb);
+      VA_STAMP(10 + which, 3);
     }
   } else if (warp == 12) {
     // ======================= MMA issuer: two streams (tile 0 / tile 1), whichever is ready goes =======================
@@ -154,10 +181,15 @@ vit_attention_tc2_kernel(const VitAttnParams p) {
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) ++n_items;
       auto issue_s = [&](int u) {             // S_u = Q_u K^T (keys 0..255) into the tile's 256 TMEM columns
         const uint32_t qa = u == 0 ? sQ0 : sQ1;
+        const uint32_t qa1 = qa + (u == 0 ? V2_Q0_G : V2_Q1_G) * 1024, ka1 = sK0 + V2_K_G * 1024;
 #pragma unroll
-        for (int j = 0; j < VA_DP / 16; ++j)
-          umma_f16<1>(tmem + u * VA_TILE_COLS, make_desc_nosw(qa + j * 256, 128, VA_G),
-                      make_desc_nosw(sK0 + j * 256, 128, VA_G), IDESC_S256, j > 0);
+        for (int j = 0; j < 4; ++j)              // head dims 0..63: +32 bytes per 16-element k-step inside the swizzle atom
+          umma_f16<1>(tmem + u * VA_TILE_COLS, make_smem_desc_sw128(qa) + 2 * j, make_smem_desc_sw128(sK0) + 2 * j,
+                      IDESC_S256, j > 0);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)              // head dims 64..95 (88..95: the TMA's zero fill)
+          umma_f16<1>(tmem + u * VA_TILE_COLS, make_smem_desc_sw64(qa1) + 2 * j, make_smem_desc_sw64(ka1) + 2 * j,
+                      IDESC_S256, 1u);
         umma_commit<1>(bar_s + 8 * u);
         umma_commit<1>(q_empty + 8 * u);      // + the softmax warps' own arrivals: the Q rows may be overwritten
       };
@@ -242,8 +274,8 @@ vit_attention_tc2_kernel(const VitAttnParams p) {
       // score of key 256: lanes 0..10 take one 8-dim chunk each
       float part = 0.0f;
       if (lane < CH) {
-        const uint4 qa = *reinterpret_cast<const uint4*>(gQ0 + 16 * VA_G + lane * 128);
-        const uint4 ka = *reinterpret_cast<const uint4*>(gK + 32 * VA_G + lane * 128);
+        const uint4 qa = *qk_chunk(gQ0, V2_Q0_G, 128, lane);    // query row 256 = local row 128 of the first Q buffer
+        const uint4 ka = *qk_chunk(gK, V2_K_G, 256, lane);      // key row 256
         const __half2* q2 = reinterpret_cast<const __half2*>(&qa);
         const __half2* k2 = reinterpret_cast<const __half2*>(&ka);
 #pragma unroll
@@ -308,49 +340,46 @@ vit_attention_tc2_kernel(const VitAttnParams p) {
     const int rl = quarter * 32 + lane;               // row inside the tile: one full row (256 + 1 keys) per thread
     const int row = u * 128 + rl;
     const uint32_t trow = tmem + u * VA_TILE_COLS + ((uint32_t)(quarter * 32) << 16);
-    const uint8_t* qrow = (u == 0 ? gQ0 : gQ1) + (uint32_t)(rl >> 3) * VA_G + (rl & 7) * 16;
+    // ---- the 257th token on the CUDA cores: s256 = q_row . k_256 and t = q_256 . k_key (left in s_cls for warp 13).
+    //      The dot products of item n+1 run in the shadow of item n's P.V MMA (needs only Q and K in shared memory).
+    auto dots = [&](uint32_t nn) -> float {
+      const uint32_t pq = nn & 1;
+      mbar_wait_relaxed(q_full, pq);                                 // tile-0 rows and query row 256
+      if (u == 1) mbar_wait_relaxed(q_full + 8, pq);
+      mbar_wait_relaxed(k_full, pq);
+      float s256 = 0.0f, t256 = 0.0f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const uint4 qa = *qk_chunk(u == 0 ? gQ0 : gQ1, u == 0 ? V2_Q0_G : V2_Q1_G, rl, c);   // this thread's query row
+        const uint4 ka = *qk_chunk(gK, V2_K_G, 256, c);                                       // key 256
+        const uint4 qb = *qk_chunk(gQ0, V2_Q0_G, 128, c);                                     // query 256
+        const uint4 kb_ = *qk_chunk(gK, V2_K_G, row, c);                                      // key index == row index
+        const __half2* q2 = reinterpret_cast<const __half2*>(&qa);
+        const __half2* k2 = reinterpret_cast<const __half2*>(&ka);
+        const __half2* q3 = reinterpret_cast<const __half2*>(&qb);
+        const __half2* k3 = reinterpret_cast<const __half2*>(&kb_);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 qf = __half22float2(q2[j]), kf = __half22float2(k2[j]);
+          const float2 qg = __half22float2(q3[j]), kg = __half22float2(k3[j]);
+          s256 = fmaf(qf.x, kf.x, s256);
+          s256 = fmaf(qf.y, kf.y, s256);
+          t256 = fmaf(qg.x, kg.x, t256);
+          t256 = fmaf(qg.y, kg.y, t256);
+        }
+      }
+      s_clsb[(nn & 1) * VA_CLS_LD + row] = t256;
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(q_empty); if (u == 1) mbar_arrive(q_empty + 8); mbar_arrive(k_empty); mbar_arrive(cls_bar); }
+      return s256;
+    };
     uint32_t n = 0;
+    float s256 = 0.0f;
+    if ((int)blockIdx.x < p.items) s256 = dots(0);
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
       const int b = item / p.heads, h = item - b * p.heads;
       const uint32_t vb = n & 1, pn = n & 1;
-      // ---- the 257th token on the CUDA cores, before this tile's S is even issued (needs only Q and K in smem):
-      //      s256 = q_row . k_256 (key 256 for this thread's row) and t = q_256 . k_key (this thread's key for row 256)
       VA_STAMP(warp, 0);
-      mbar_wait_relaxed(q_full, pn);                                 // tile-0 rows and query row 256
-      if (u == 1) mbar_wait_relaxed(q_full + 8, pn);
-      mbar_wait_relaxed(k_full, pn);
-      VA_STAMP(warp, 1);
-      float s256 = 0.0f, t256 = 0.0f;
-      {
-        const uint8_t* k256 = gK + 32 * VA_G;              // row 256 = first row of group 32
-        const uint8_t* q256 = gQ0 + 16 * VA_G;             // group 16 of the first Q buffer
-        const uint8_t* krow = gK + (uint32_t)(row >> 3) * VA_G + (row & 7) * 16;    // key index == row index
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const uint4 qa = *reinterpret_cast<const uint4*>(qrow + c * 128);
-          const uint4 ka = *reinterpret_cast<const uint4*>(k256 + c * 128);
-          const uint4 qb = *reinterpret_cast<const uint4*>(q256 + c * 128);
-          const uint4 kb_ = *reinterpret_cast<const uint4*>(krow + c * 128);
-          const __half2* q2 = reinterpret_cast<const __half2*>(&qa);
-          const __half2* k2 = reinterpret_cast<const __half2*>(&ka);
-          const __half2* q3 = reinterpret_cast<const __half2*>(&qb);
-          const __half2* k3 = reinterpret_cast<const __half2*>(&kb_);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 qf = __half22float2(q2[j]), kf = __half22float2(k2[j]);
-            const float2 qg = __half22float2(q3[j]), kg = __half22float2(k3[j]);
-            s256 = fmaf(qf.x, kf.x, s256);
-            s256 = fmaf(qf.y, kf.y, s256);
-            t256 = fmaf(qg.x, kg.x, t256);
-            t256 = fmaf(qg.y, kg.y, t256);
-          }
-        }
-      }
-      s_clsb[(n & 1) * VA_CLS_LD + row] = t256;
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(q_empty); if (u == 1) mbar_arrive(q_empty + 8); mbar_arrive(k_empty); mbar_arrive(cls_bar); }
-
-      VA_STAMP(warp, 2);
       mbar_wait_relaxed(bar_s + 8 * u, pn);
       tc_fence_after();
       VA_STAMP(warp, 3);
@@ -459,6 +488,18 @@ vit_attention_tc2_kernel(const VitAttnParams p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(part_bar);
       }
+      VA_STAMP(warp, 1);
+      // next item's 257th-token dot products: now if its Q and K have already landed (tile 1: always; tile 0: K is
+      // only freed when S of tile 1 of THIS item has retired), otherwise after the read-out below
+      const bool has_next = item + (int)gridDim.x < p.items;
+      float s256_next = 0.0f;
+      bool dots_done = false;
+      if (has_next) {
+        const uint32_t pq = (n + 1) & 1;
+        const bool ready = mbar_try_wait(k_full, pq) && mbar_try_wait(q_full, pq) && (u == 0 || mbar_try_wait(q_full + 8, pq));
+        if (__all_sync(0xffffffffu, ready)) { s256_next = dots(n + 1); dots_done = true; }
+      }
+      VA_STAMP(warp, 2);
 
       mbar_wait_relaxed(bar_o + 8 * u, pn);
       tc_fence_after();
@@ -506,6 +547,8 @@ vit_attention_tc2_kernel(const VitAttnParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(v_empty + 8 * vb);         // row-256 share and V row 256 have been read
       VA_STAMP(warp, 7);
+      if (has_next && !dots_done) s256_next = dots(n + 1);
+      s256 = s256_next;
     }
   }
 
@@ -516,7 +559,13 @@ vit_attention_tc2_kernel(const VitAttnParams p) {
 
 long long get_option64(const char* key);
 
+int make_qkv_tmap(CUtensorMap* tm, const void* base, long long rows, long long pitch_elems, int box_elems, int box_rows,
+                  CUtensorMapSwizzle swz);
+bool vit_attention_packed_qkv(const seedb200_attn_desc& d);
+int vit_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream);
+
 int vit_attention_tc2(const seedb200_attn_desc& d, cudaStream_t stream) {
+  if (!vit_attention_packed_qkv(d)) return vit_attention_tc(d, stream);   // this variant takes Q / K by TMA only
   static bool attr_set_dev[SB_MAX_DEVICES] = {};   // cudaFuncSetAttribute is per device
   bool& attr_set = attr_set_dev[cur_device()];
   if (!attr_set) {
@@ -533,10 +582,16 @@ int vit_attention_tc2(const seedb200_attn_desc& d, cudaStream_t stream) {
   p.items = d.batch * d.heads; p.heads = d.heads;
   p.scale_log2 = d.scale * 1.4426950408889634f;
   p.dbg = reinterpret_cast<long long*>(static_cast<uintptr_t>(get_option64("vit_attention_dbg_ptr")));
+  CUtensorMap ta64, ta32, tr64, tr32;
+  const long long rows = (long long)d.batch * VA_N;
+  SB_PROPAGATE(make_qkv_tmap(&ta64, d.q, rows, d.q_ts, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B));
+  SB_PROPAGATE(make_qkv_tmap(&ta32, d.q, rows, d.q_ts, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B));
+  SB_PROPAGATE(make_qkv_tmap(&tr64, d.q, rows, d.q_ts, 64, 1, CU_TENSOR_MAP_SWIZZLE_128B));
+  SB_PROPAGATE(make_qkv_tmap(&tr32, d.q, rows, d.q_ts, 32, 1, CU_TENSOR_MAP_SWIZZLE_64B));
   int grid = num_sms();
   if (grid > p.items) grid = p.items;
   profile_mark_begin(1, stream);
-  vit_attention_tc2_kernel<<<grid, VA_THREADS, V2_SMEM, stream>>>(p);
+  vit_attention_tc2_kernel<<<grid, VA_THREADS, V2_SMEM, stream>>>(p, ta64, ta32, tr64, tr32);
   profile_mark_end(1, stream, 4.0 * (double)d.batch * d.heads * (double)d.nq * d.nk * d.head_dim);
   SB_LAUNCH_CHECK();
   return 0;

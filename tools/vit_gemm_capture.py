@@ -50,3 +50,18 @@ if "--time" in sys.argv:
             s.record(); fn(); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
         print(json.dumps({"shape": nm, "ms": round(min(ts), 4), "tflops": round(fl / min(ts) / 1e9, 1)}))
 print("vit_gemm_capture done")
+if "--ab" in sys.argv:
+    # LayerNorm-folded epilogue vs plain bias epilogue on the same shapes, interleaved (same clocks)
+    ln = L.layernorm(x, gamma, beta, 1e-6)
+    pairs = [("qkv", lambda: L.gemm(x, qkv_f[0], out=qkv, ctas=2, ln=(stats, qkv_f[1], qkv_f[2])),
+              lambda: L.gemm(ln, w_qkv, bias=b_qkv, out=qkv, ctas=2), flops[0]),
+             ("fc1", lambda: L.gemm(x, fc1_f[0], act=L.ACT_GELU, out=hid, ctas=2, ln=(stats, fc1_f[1], fc1_f[2])),
+              lambda: L.gemm(ln, w_fc1, bias=b_fc1, act=L.ACT_GELU, out=hid, ctas=2), flops[2])]
+    for nm, f_ln, f_bias, fl in pairs:
+        t = {"ln": [], "bias": []}
+        for _ in range(8):
+            for key, fn in (("ln", f_ln), ("bias", f_bias)):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(); fn(); e.record(); torch.cuda.synchronize(); t[key].append(s.elapsed_time(e))
+        print(json.dumps({"shape": nm, "lnfold_ms": round(min(t["ln"]), 4), "bias_ms": round(min(t["bias"]), 4),
+                          "lnfold_tflops": round(fl / min(t["ln"]) / 1e9, 1), "bias_tflops": round(fl / min(t["bias"]) / 1e9, 1)}))
