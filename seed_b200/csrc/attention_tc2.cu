@@ -214,14 +214,14 @@ vit_attention_tc2_kernel(const VitAttnParams p, const __grid_constant__ CUtensor
           const int n = st0 >> 1;
           const uint32_t par = n & 1;
           if ((st0 & 1) == 0) {
-            if (mbar_try_wait(q_full, par) && mbar_try_wait(k_full, par) && (n == 0 || mbar_try_wait(bar_free, par ^ 1))) {
+            if (mbar_test_wait(q_full, par) && mbar_test_wait(k_full, par) && (n == 0 || mbar_test_wait(bar_free, par ^ 1))) {
               tc_fence_after();
               VA_STAMP(8, 1);
               issue_s(0);
               ++st0; progress = true;
             }
           } else {
-            if (mbar_try_wait(bar_p, par) && mbar_try_wait(v_full + 8 * (n & 1), (n >> 1) & 1)) {
+            if (mbar_test_wait(bar_p, par) && mbar_test_wait(v_full + 8 * (n & 1), (n >> 1) & 1)) {
               tc_fence_after();
               VA_STAMP(8, 5);
               issue_pv(0, n & 1);
@@ -234,7 +234,7 @@ vit_attention_tc2_kernel(const VitAttnParams p, const __grid_constant__ CUtensor
           const uint32_t par = n & 1;
           if ((st1 & 1) == 0) {
             // the stagger: S of tile 1 only after P.V of tile 0 of the same item has been issued (st0 >= 2n + 2)
-            if (st0 >= 2 * n + 2 && mbar_try_wait(q_full + 8, par) && (n == 0 || mbar_try_wait(bar_free + 8, par ^ 1))) {
+            if (st0 >= 2 * n + 2 && mbar_test_wait(q_full + 8, par) && (n == 0 || mbar_test_wait(bar_free + 8, par ^ 1))) {
               tc_fence_after();
               VA_STAMP(8, 2);
               issue_s(1);
@@ -242,7 +242,7 @@ vit_attention_tc2_kernel(const VitAttnParams p, const __grid_constant__ CUtensor
               ++st1; progress = true;
             }
           } else {
-            if (mbar_try_wait(bar_p + 8, par)) {   // (V landed: P.V(0) of this item already waited for it)
+            if (mbar_test_wait(bar_p + 8, par)) {   // (V landed: P.V(0) of this item already waited for it)
               tc_fence_after();
               VA_STAMP(8, 6);
               issue_pv(1, n & 1);
@@ -496,7 +496,7 @@ vit_attention_tc2_kernel(const VitAttnParams p, const __grid_constant__ CUtensor
       bool dots_done = false;
       if (has_next) {
         const uint32_t pq = (n + 1) & 1;
-        const bool ready = mbar_try_wait(k_full, pq) && mbar_try_wait(q_full, pq) && (u == 0 || mbar_try_wait(q_full + 8, pq));
+        const bool ready = mbar_test_wait(k_full, pq) && mbar_test_wait(q_full, pq) && (u == 0 || mbar_test_wait(q_full + 8, pq));
         if (__all_sync(0xffffffffu, ready)) { s256_next = dots(n + 1); dots_done = true; }
       }
       VA_STAMP(warp, 2);

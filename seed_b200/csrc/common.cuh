@@ -160,6 +160,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking test of a phase (mbarrier.try_wait may park the thread for an implementation-defined time before it
+// answers "not yet": fine inside a wait loop, wrong for a poll that has something else to do)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded waits: a protocol bug traps (kernel error) instead of hanging the GPU.  The deadline is checked once every
 // 4096 polls only: a clock64() + compare per poll made the wait loops ~half of all instructions the attention kernel
 // issued (profiles/r02_attention.md) -- issue slots and power taken from the warps doing work.
