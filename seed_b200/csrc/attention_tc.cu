@@ -298,7 +298,8 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
       mbar_wait_relaxed(q_full + 8 * u, pq);
       if (u == 0) mbar_wait_relaxed(q_full + 8, pq);                // query row 256 lives in the second Q buffer
       mbar_wait_relaxed(k_full, pq);
-      float s256 = 0.0f, t256 = 0.0f;
+      // four independent accumulators per dot product: the 88-term FMA chains were latency-bound (2 chains x 88 x 4 cycles)
+      float sa[4] = {0.0f, 0.0f, 0.0f, 0.0f}, ta[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         const uint4 qa = *qk_chunk(u == 0 ? gQ0 : gQ1, u == 0 ? 16 : 17, rl, c);    // this thread's query row
@@ -313,12 +314,14 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
         for (int j = 0; j < 4; ++j) {
           const float2 qf = __half22float2(q2[j]), kf = __half22float2(k2[j]);
           const float2 qg = __half22float2(q3[j]), kg = __half22float2(k3[j]);
-          s256 = fmaf(qf.x, kf.x, s256);
-          s256 = fmaf(qf.y, kf.y, s256);
-          t256 = fmaf(qg.x, kg.x, t256);
-          t256 = fmaf(qg.y, kg.y, t256);
+          sa[j] = fmaf(qf.x, kf.x, sa[j]);
+          sa[j] = fmaf(qf.y, kf.y, sa[j]);
+          ta[j] = fmaf(qg.x, kg.x, ta[j]);
+          ta[j] = fmaf(qg.y, kg.y, ta[j]);
         }
       }
+      const float s256 = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+      const float t256 = (ta[0] + ta[1]) + (ta[2] + ta[3]);
       s_clsb[(nn & 1) * VA_CLS_LD + row] = t256;
       __syncwarp();
       if (lane == 0) { mbar_arrive(q_empty + 8 * u); if (u == 0) mbar_arrive(q_empty + 8); mbar_arrive(k_empty); mbar_arrive(cls_bar); }
@@ -407,8 +410,10 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
         for (int q = 0; q < 3; ++q)
 #pragma unroll
           for (int j = 0; j < 8; ++j) a[q][j] = 0.0f;
-#pragma unroll 1
-        for (int kg = warp; kg < 33; kg += 8) {            // keys 257..263 of the last group are zero rows, p = 0
+#pragma unroll
+        for (int kgi = 0; kgi < 5; ++kgi) {                // key groups warp, warp + 8, ... (keys 257..263 are zero rows, p = 0)
+          const int kg = warp + 8 * kgi;
+          if (kg >= 33) break;
           const float pk = pc[kg * 8 + k8];
           const uint8_t* vrow = gV + (uint32_t)kg * VA_G + k8 * 16 + c4 * 128;
 #pragma unroll
