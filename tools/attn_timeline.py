@@ -32,7 +32,7 @@ for var, tma in ((1, 1), (1, 0), (2, 0)):
         s.record(); L.attention(q, k, v, D ** -0.5, False); e.record(); torch.cuda.synchronize()
         ts.append(s.elapsed_time(e))
     ts.sort()
-    print(f"variant {var} (Q/K by {'TMA' if tma and var == 1 else 'cp.async'}): B=256 kernel time min {ts[0]:.4f} ms  median {ts[len(ts)//2]:.4f} ms "
+    print(f"variant {var} (Q/K by {'TMA' if (tma or var == 2) else 'cp.async'}): B=256 kernel time min {ts[0]:.4f} ms  median {ts[len(ts)//2]:.4f} ms "
           f"({4.0 * 256 * H * N * N * D / ts[0] / 1e9:.0f} TFLOP/s)")
 
 L.set_option("vit_attention_tc", variant)
