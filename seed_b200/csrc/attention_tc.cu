@@ -40,7 +40,8 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
   const uint32_t sK0 = base, sQ0 = sK0 + VA_K_BYTES, sQ1 = sQ0 + VA_Q0_BYTES, sV0 = sQ1 + VA_Q1_BYTES;
   const uint32_t misc = sV0 + 2 * VA_V_BYTES;
   float* s_clsb = reinterpret_cast<float*>(gen + (misc - base));    // [2][VA_CLS_LD]: scores, then probabilities of query row 256
-  float* s_part = s_clsb + 2 * VA_CLS_LD;                           // [8][VA_PART_LD]: per-warp partial P.V of row 256
+  __half* s_clsh = reinterpret_cast<__half*>(s_clsb + 2 * VA_CLS_LD);   // [2][VA_CLS_LD]: probabilities of row 256 as the fp16 A operand
+  float* s_sx = s_clsb + 2 * VA_CLS_LD + VA_CLS_LD;                 // [8][32]: per-warp hand-over of the key-256 scores
   const uint32_t bars = misc + 2 * VA_CLS_LD * 4 + 8 * VA_PART_LD * 4;
   const uint32_t bar_s = bars, bar_p = bars + 16, bar_o = bars + 32, bar_free = bars + 48;      // [2] each: per tile pipeline
   const uint32_t q_full = bars + 64 /*[2]*/, q_empty = bars + 80 /*[2]*/;
@@ -75,7 +76,7 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
       mbar_init(bar_s + 8 * u, 1); mbar_init(bar_p + 8 * u, 4); mbar_init(bar_o + 8 * u, 1); mbar_init(bar_free + 8 * u, 4);
       mbar_init(q_full + 8 * u, 1);
       mbar_init(v_full + 8 * u, 1);
-      mbar_init(v_empty + 8 * u, 9);       // P.V(1) retired + 8 softmax warps (row-256 partial P.V, value row 256)
+      mbar_init(v_empty + 8 * u, 10);      // P.V(1) retired + 8 softmax warps + row-256 warp (their shares of row 256's P.V)
     }
     mbar_init(q_empty, 5);                 // S(0) retired + 4 softmax warps of tile 0 (their q rows, for key 256)
     mbar_init(q_empty + 8, 10);            // S(1) retired + all 8 softmax warps (tile-1 rows, query row 256) + row-256 warp
@@ -87,8 +88,16 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
   }
   if (warp == 12) tmem_alloc<1>(tmem_slot, VA_TMEM_COLS);
   // zero every operand buffer once: the padding (head_dim 88..95, rows/keys 257..271) is never written again
-  for (uint32_t off = tid * 16; off < (uint32_t)VA_DATA_BYTES; off += VA_THREADS * 16)
-    *reinterpret_cast<uint4*>(gen + off) = make_uint4(0, 0, 0, 0);
+  // except the ones-column of V: head dim 88 (first element of the padding chunk) of keys 0..256 is 1.0, so that column
+  // 88 of O = P V is the row sum of the fp16-rounded probabilities, accumulated in fp32 by the tensor core
+  for (uint32_t off = tid * 16; off < (uint32_t)VA_DATA_BYTES; off += VA_THREADS * 16) {
+    uint32_t first = 0;
+    if (off >= sV0 - base) {
+      const uint32_t rel = (off - (sV0 - base)) % VA_V_BYTES, within = rel % VA_G;
+      if ((within >> 7) == 11 && (rel / VA_G) * 8 + ((within & 127) >> 4) < (uint32_t)VA_N) first = 0x3C00u;
+    }
+    *reinterpret_cast<uint4*>(gen + off) = make_uint4(first, 0, 0, 0);
+  }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -98,6 +107,32 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
   constexpr uint32_t IDESC_S256 = make_idesc_f16(128, 256);
   constexpr uint32_t IDESC_O = make_idesc_f16(128, 48) | (1u << 16);      // half of the head dim; B (= V) is MN-major
   constexpr int CH = VA_D / 8;            // 11 16-byte chunks per row
+
+  // O[256, 8 nt .. 8 nt + 7] = P[256, :] V on the legacy tensor pipe (mma.sync m16n8k16, only row 0 of A is populated):
+  // nine ldmatrix.x4.trans of the no-swizzle V image (four 8-key x 8-dim core matrices = two k-steps each) and 17 MMAs
+  // per 8 head dims.  The eight softmax warps take dims 0..63, the row-256 warp dims 64..87.
+  auto row256_pv = [&](int nt, const __half* ph, const uint8_t* gV, float inv256, __half* orow) {
+    float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const uint32_t* pw = reinterpret_cast<const uint32_t*>(ph);
+    const uint32_t va = smem_u32(gV) + nt * 128 + (lane & 7) * 16;
+    const int t4 = lane & 3;
+    const bool row0 = lane < 4;
+#pragma unroll
+    for (int kp = 0; kp < 9; ++kp) {
+      const int grp = kp < 8 ? 4 * kp + (lane >> 3) : 32 + ((lane >> 3) & 1);    // keys 256..271 are groups 32, 33
+      uint32_t bm[4];
+      va_ldsm_x4_t(bm, va + grp * VA_G);
+      uint32_t a0 = 0, a2 = 0;
+      if (row0) { a0 = pw[16 * kp + t4]; a2 = pw[16 * kp + 4 + t4]; }
+      va_mma16816(c, a0, 0u, a2, 0u, bm[0], bm[1]);
+      if (kp < 8) {
+        uint32_t a4 = 0, a6 = 0;
+        if (row0) { a4 = pw[16 * kp + 8 + t4]; a6 = pw[16 * kp + 12 + t4]; }
+        va_mma16816(c, a4, 0u, a6, 0u, bm[2], bm[3]);
+      }
+    }
+    if (row0) *reinterpret_cast<__half2*>(orow + nt * 8 + 2 * t4) = __floats2half2_rn(c[0] * inv256, c[1] * inv256);
+  };
 
   if (warp >= 8 && warp < 12) {
     // ======================= loaders: one warp per operand buffer, cp.async 16-byte copies =======================
@@ -196,6 +231,9 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
             umma_f16_ts(tb + VA_OLO_COL, pa, make_desc_nosw(sV + j * 2 * VA_G, VA_G, 128), IDESC_O, j > 0);
             umma_f16_ts(tb + VA_OHI_COL, pa, make_desc_nosw(sV + j * 2 * VA_G + 6 * 128, VA_G, 128), IDESC_O, j > 0);
           }
+          // keys 256..271: P of key 256 sits in its own 8 columns, V rows 257.. are zero
+          umma_f16_ts(tb + VA_OLO_COL, tb + VA_P256_COL, make_desc_nosw(sV + 32 * VA_G, VA_G, 128), IDESC_O, 1u);
+          umma_f16_ts(tb + VA_OHI_COL, tb + VA_P256_COL, make_desc_nosw(sV + 32 * VA_G + 6 * 128, VA_G, 128), IDESC_O, 1u);
           umma_commit<1>(bar_o + 8 * u);
         };
         VA_STAMP(8, 0);
@@ -231,6 +269,8 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
     uint32_t n = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
       float* cls = s_clsb + (n & 1) * VA_CLS_LD;
+      __half* clsh = s_clsh + (n & 1) * VA_CLS_LD;
+      const int b = item / p.heads, h = item - b * p.heads;
       VA_STAMP(9, 0);
       mbar_wait_relaxed(q_full + 8, n & 1);
       mbar_wait_relaxed(k_full, n & 1);
@@ -272,15 +312,27 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
         const int key = lane + 32 * i;
-        const float pr = __half2float(__float2half_rn(ex2f(sc[i] - mx)));   // P rounded to fp16 like the tile path
-        sum += pr;
-        if (key < VA_KP) cls[key] = pr;                    // 0 for keys 257..271
+        const __half ph = __float2half_rn(ex2f(sc[i] - mx));               // P rounded to fp16 like the tile path
+        sum += __half2float(ph);
+        if (key < VA_KP) clsh[key] = ph;                   // 0 for keys 257..271
       }
       sum = warp_sum(sum);
       if (lane == 0) cls[VA_KP] = sum;
       __syncwarp();
       if (lane == 0) mbar_arrive(cls_p);                  // release: the probabilities are visible to the waiters
       VA_STAMP(9, 4);
+      // this warp's share of the row's P.V: head dims 64..87
+      {
+        const uint32_t vb = n & 1;
+        mbar_wait_relaxed(v_full + 8 * vb, (n >> 1) & 1);
+        __half* orow = p.o + b * p.o_bs + h * p.o_hs + (long long)(VA_N - 1) * p.o_ts;
+        const float inv256 = 1.0f / sum;
+#pragma unroll 1
+        for (int nt = 8; nt < 11; ++nt) row256_pv(nt, clsh, gV0 + vb * VA_V_BYTES, inv256, orow);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(v_empty + 8 * vb);
+      }
+      VA_STAMP(9, 5);
     }
   } else {
     // ======================= softmax + epilogue: warps 0-3 own tile 0 (rows 0..127), warps 4-7 tile 1 =======================
@@ -298,31 +350,46 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
       mbar_wait_relaxed(q_full + 8 * u, pq);
       if (u == 0) mbar_wait_relaxed(q_full + 8, pq);                // query row 256 lives in the second Q buffer
       mbar_wait_relaxed(k_full, pq);
-      // four independent accumulators per dot product: the 88-term FMA chains were latency-bound (2 chains x 88 x 4 cycles)
-      float sa[4] = {0.0f, 0.0f, 0.0f, 0.0f}, ta[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      // both as 32 x 96 by 96 x 1 products on the legacy tensor pipe: A = this warp's 32 query rows (resp. key rows)
+      // through ldmatrix from the swizzled / core-matrix image, B = key 256 (resp. query 256) in column 0 of the n = 8
+      float sc[2][4] = {{0.0f, 0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};
+      float tc[2][4] = {{0.0f, 0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};
+      const uint8_t* qbuf = u == 0 ? gQ0 : gQ1;
+      const int qg = u == 0 ? 16 : 17;
+      const int ar = quarter * 32 + (lane & 15);          // ldmatrix row of this lane inside m-tile 0 (matrices 0/1: rows 0..15)
+      const int ac = lane >> 4;                           // matrices 2/3: the k-step's second 8-dim chunk
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const uint4 qa = *qk_chunk(u == 0 ? gQ0 : gQ1, u == 0 ? 16 : 17, rl, c);    // this thread's query row
-        const uint4 ka = *qk_chunk(gK, 33, 256, c);                                  // key 256
-        const uint4 qb = *qk_chunk(gQ1, 17, 128, c);                                 // query 256
-        const uint4 kb_ = *qk_chunk(gK, 33, row, c);                                 // key index == row index
-        const __half2* q2 = reinterpret_cast<const __half2*>(&qa);
-        const __half2* k2 = reinterpret_cast<const __half2*>(&ka);
-        const __half2* q3 = reinterpret_cast<const __half2*>(&qb);
-        const __half2* k3 = reinterpret_cast<const __half2*>(&kb_);
+      for (int ks = 0; ks < VA_DP / 16; ++ks) {
+        uint32_t bk0 = 0, bk1 = 0, bq0 = 0, bq1 = 0;
+        if (lane < 4) {
+          bk0 = reinterpret_cast<const uint32_t*>(qk_chunk(gK, 33, 256, 2 * ks))[lane];
+          bk1 = reinterpret_cast<const uint32_t*>(qk_chunk(gK, 33, 256, 2 * ks + 1))[lane];
+          bq0 = reinterpret_cast<const uint32_t*>(qk_chunk(gQ1, 17, 128, 2 * ks))[lane];
+          bq1 = reinterpret_cast<const uint32_t*>(qk_chunk(gQ1, 17, 128, 2 * ks + 1))[lane];
+        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 qf = __half22float2(q2[j]), kf = __half22float2(k2[j]);
-          const float2 qg = __half22float2(q3[j]), kg = __half22float2(k3[j]);
-          sa[j] = fmaf(qf.x, kf.x, sa[j]);
-          sa[j] = fmaf(qf.y, kf.y, sa[j]);
-          ta[j] = fmaf(qg.x, kg.x, ta[j]);
-          ta[j] = fmaf(qg.y, kg.y, ta[j]);
+        for (int mt = 0; mt < 2; ++mt) {
+          uint32_t a[4];
+          va_ldsm_x4(a, smem_u32(qk_chunk(qbuf, qg, ar + 16 * mt, 2 * ks + ac)));
+          va_mma16816(sc[mt], a[0], a[1], a[2], a[3], bk0, bk1);
+          va_ldsm_x4(a, smem_u32(qk_chunk(gK, 33, u * 128 + ar + 16 * mt, 2 * ks + ac)));
+          va_mma16816(tc[mt], a[0], a[1], a[2], a[3], bq0, bq1);
         }
       }
-      const float s256 = (sa[0] + sa[1]) + (sa[2] + sa[3]);
-      const float t256 = (ta[0] + ta[1]) + (ta[2] + ta[3]);
-      s_clsb[(nn & 1) * VA_CLS_LD + row] = t256;
+      // column 0 of the accumulators: lanes 0, 4, 8, ... hold rows g and g + 8 of each m-tile
+      if ((lane & 3) == 0) {
+        const int g = lane >> 2;
+        float* tdst = s_clsb + (nn & 1) * VA_CLS_LD + u * 128 + quarter * 32;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          s_sx[warp * 32 + mt * 16 + g] = sc[mt][0];
+          s_sx[warp * 32 + mt * 16 + g + 8] = sc[mt][2];
+          tdst[mt * 16 + g] = tc[mt][0];
+          tdst[mt * 16 + g + 8] = tc[mt][2];
+        }
+      }
+      __syncwarp();
+      const float s256 = s_sx[warp * 32 + lane];
       __syncwarp();
       if (lane == 0) { mbar_arrive(q_empty + 8 * u); if (u == 0) mbar_arrive(q_empty + 8); mbar_arrive(k_empty); mbar_arrive(cls_bar); }
       return s256;
@@ -366,15 +433,14 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
       const float m = mx * p.scale_log2;                 // scale > 0
       // pass 2: P = exp2(s*scale*log2e - m), rounded to fp16 (as the reference does under autocast), written in
       // place: chunk c of S (32 columns) becomes 16 packed columns that lie inside chunks already loaded
-      float sum = 0.0f;
       auto chunk_exp = [&](const uint32_t(&cur)[32], uint32_t dst) {
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {                   // two halves of 16 columns: bounds the live temporaries
           uint32_t pk[8];
 #pragma unroll
           for (int g = 0; g < 8; ++g)
-            pk[g] = pack2(ex2f(fmaf(__uint_as_float(cur[hf * 16 + 2 * g]), p.scale_log2, -m)),
-                          ex2f(fmaf(__uint_as_float(cur[hf * 16 + 2 * g + 1]), p.scale_log2, -m)), sum);
+            pk[g] = pack2n(ex2f(fmaf(__uint_as_float(cur[hf * 16 + 2 * g]), p.scale_log2, -m)),
+                           ex2f(fmaf(__uint_as_float(cur[hf * 16 + 2 * g + 1]), p.scale_log2, -m)));
           tmem_st8(dst + hf * 8, pk);
         }
       };
@@ -388,120 +454,72 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
         if (c + 2 < 8) tmem_ld32(trow + (c + 2) * 32, r0);
         chunk_exp(r1, dst + 16);
       }
-      const float p256 = __half2float(__float2half_rn(ex2f(fmaf(s256, p.scale_log2, -m))));
-      sum += p256;
+      {
+        // key 256: its probability as the A operand of a 17th P.V step (the 15 keys after it are zero rows of V)
+        uint32_t pk[8] = {pack2n(ex2f(fmaf(s256, p.scale_log2, -m)), 0.0f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        tmem_st8(trow + VA_P256_COL, pk);
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p + 8 * u);
       VA_STAMP(warp, 5);
 
-      // ---- query row 256: this warp's share of its P.V product, in the shadow of the tile's P.V MMA ----
-      // lane = (chunk quad c4, key k8): one LDS.128 per (8 keys x 4 dim chunks) is a contiguous 512 bytes of the
-      // canonical V image; warp w takes key groups w, w + 8, ... of the 33.
+      // ---- query row 256: this warp's share of its P.V product (8 of the 88 head dims), in the shadow of the tile's
+      //      P.V MMA ----
       {
         mbar_wait_relaxed(cls_p, pn);
         mbar_wait_relaxed(v_full + 8 * vb, (n >> 1) & 1);
         const float* pc = s_clsb + (n & 1) * VA_CLS_LD;
-        const uint8_t* gV = gV0 + vb * VA_V_BYTES;
-        const int k8 = lane & 7, c4 = lane >> 3;
-        float a[3][8];
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) a[q][j] = 0.0f;
-#pragma unroll
-        for (int kgi = 0; kgi < 5; ++kgi) {                // key groups warp, warp + 8, ... (keys 257..263 are zero rows, p = 0)
-          const int kg = warp + 8 * kgi;
-          if (kg >= 33) break;
-          const float pk = pc[kg * 8 + k8];
-          const uint8_t* vrow = gV + (uint32_t)kg * VA_G + k8 * 16 + c4 * 128;
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {                    // chunk q*4 + c4 (chunk 11 is the zero padding)
-            const uint4 vv = *reinterpret_cast<const uint4*>(vrow + q * 512);
-            const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 vf = __half22float2(v2[j]);
-              a[q][2 * j] = fmaf(pk, vf.x, a[q][2 * j]);
-              a[q][2 * j + 1] = fmaf(pk, vf.y, a[q][2 * j + 1]);
-            }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float v = a[q][j];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            a[q][j] = v;
-          }
-        if (k8 == 0) {
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            float* dst = s_part + warp * VA_PART_LD + (q * 4 + c4) * 8;
-            *reinterpret_cast<float4*>(dst) = make_float4(a[q][0], a[q][1], a[q][2], a[q][3]);
-            *reinterpret_cast<float4*>(dst + 4) = make_float4(a[q][4], a[q][5], a[q][6], a[q][7]);
-          }
-        }
-        asm volatile("bar.sync 2, 256;" ::: "memory");     // the 8 softmax warps
-        if (tid < VA_D) {
-          float acc = 0.0f;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) acc += s_part[w * VA_PART_LD + tid];
-          p.o[b * p.o_bs + h * p.o_hs + (long long)(VA_N - 1) * p.o_ts + tid] = __float2half_rn(acc / pc[VA_KP]);
-        }
+        row256_pv(warp, s_clsh + (n & 1) * VA_CLS_LD, gV0 + vb * VA_V_BYTES, 1.0f / pc[VA_KP],
+                  p.o + b * p.o_bs + h * p.o_hs + (long long)(VA_N - 1) * p.o_ts);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(v_empty + 8 * vb);         // this warp has read its share of V
       VA_STAMP(warp, 1);
       // next item's 257th-token dot products, in the same shadow
       float s256_next = 0.0f;
       if (item + (int)gridDim.x < p.items) s256_next = dots(n + 1);
       VA_STAMP(warp, 2);
-      const float inv = 1.0f / sum;
-      const float w256 = p256 * inv;
       mbar_wait_relaxed(bar_o + 8 * u, pn);
       tc_fence_after();
       VA_STAMP(warp, 6);
       __half* og = p.o + b * p.o_bs + h * p.o_hs + (long long)row * p.o_ts;
-      const uint8_t* v256 = gV0 + vb * VA_V_BYTES + 32 * VA_G;   // V row 256 = first row of group 32 (P.V needed v_full)
-      float unused = 0.0f;
+      {
+        // dims 80..95 first: column 88 holds the row sum (ones-column of V), all 257 keys included.  Three loads in
+        // flight at most (64 registers), each one overlapped with the stores of the previous.
+        auto store8 = [&](const uint32_t* src, int chunk, float inv) {
+          uint4 o;
+          o.x = pack2n(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+          o.y = pack2n(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+          o.z = pack2n(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+          o.w = pack2n(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+          *reinterpret_cast<uint4*>(og + chunk * 8) = o;
+        };
+        uint32_t a1[16], b0[32];
+        tmem_ld16(trow + VA_OHI_COL + 32, a1);             // dims 80..95
+        tmem_ld32(trow + VA_OLO_COL, b0);                  // dims 0..31
+        tmem_ld_wait16(a1);
+        tmem_ld_wait32(b0);
+        const float inv = 1.0f / __uint_as_float(a1[8]);
+        uint32_t b1[16];
+        tmem_ld16(trow + VA_OLO_COL + 32, b1);             // dims 32..47
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {                    // dims 0..47, then 48..95 (48..87 exist)
-        uint32_t r0[32], r1[16];
-        tmem_ld32(trow + (hh == 0 ? VA_OLO_COL : VA_OHI_COL), r0);
-        tmem_ld16(trow + (hh == 0 ? VA_OLO_COL : VA_OHI_COL) + 32, r1);
-        tmem_ld_wait();
-        if (hh == 1) {
-          // both halves of O are in registers / stored: hand the tile's TMEM columns back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_free + 8 * u);
-        }
+        for (int g = 0; g < 4; ++g) store8(&b0[g * 8], g, inv);
+        store8(&a1[0], 10, inv);                           // dims 80..87 (chunk 11 is padding)
+        tmem_ld_wait16(b1);
+        uint32_t a0[32];
+        tmem_ld32(trow + VA_OHI_COL, a0);                  // dims 48..79
+        store8(&b1[0], 4, inv);
+        store8(&b1[8], 5, inv);
+        tmem_ld_wait32(a0);
+        // every column of O is in registers: hand the tile's TMEM columns back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_free + 8 * u);
 #pragma unroll
-        for (int g = 0; g < 6; ++g) {
-          if (hh == 0 || g < 5) {                          // chunk 11 (dims 88..95) is padding
-            const uint4 vv = *reinterpret_cast<const uint4*>(v256 + (hh * 6 + g) * 128);
-            const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
-            float o8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o8[j] = __uint_as_float(g < 4 ? r0[g * 8 + j] : r1[(g - 4) * 8 + j]) * inv;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 vf = __half22float2(v2[j]);
-              o8[2 * j] = fmaf(w256, vf.x, o8[2 * j]);
-              o8[2 * j + 1] = fmaf(w256, vf.y, o8[2 * j + 1]);
-            }
-            uint4 o;
-            o.x = pack2(o8[0], o8[1], unused); o.y = pack2(o8[2], o8[3], unused);
-            o.z = pack2(o8[4], o8[5], unused); o.w = pack2(o8[6], o8[7], unused);
-            *reinterpret_cast<uint4*>(og + (hh * 6 + g) * 8) = o;
-          }
-        }
+        for (int g = 0; g < 4; ++g) store8(&a0[g * 8], 6 + g, inv);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(v_empty + 8 * vb);         // V row 256 has been read
       VA_STAMP(warp, 7);
       s256 = s256_next;
     }
