@@ -560,7 +560,7 @@ vit_attention_tc2_kernel(const VitAttnParams p, const __grid_constant__ CUtensor
 long long get_option64(const char* key);
 
 int make_qkv_tmap(CUtensorMap* tm, const void* base, long long rows, long long pitch_elems, int box_elems, int box_rows,
-                  CUtensorMapSwizzle swz);
+                  CUtensorMapSwizzle swz, int slots);
 bool vit_attention_packed_qkv(const seedb200_attn_desc& d);
 int vit_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream);
 
@@ -584,10 +584,10 @@ int vit_attention_tc2(const seedb200_attn_desc& d, cudaStream_t stream) {
   p.dbg = reinterpret_cast<long long*>(static_cast<uintptr_t>(get_option64("vit_attention_dbg_ptr")));
   CUtensorMap ta64, ta32, tr64, tr32;
   const long long rows = (long long)d.batch * VA_N;
-  SB_PROPAGATE(make_qkv_tmap(&ta64, d.q, rows, d.q_ts, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B));
-  SB_PROPAGATE(make_qkv_tmap(&ta32, d.q, rows, d.q_ts, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B));
-  SB_PROPAGATE(make_qkv_tmap(&tr64, d.q, rows, d.q_ts, 64, 1, CU_TENSOR_MAP_SWIZZLE_128B));
-  SB_PROPAGATE(make_qkv_tmap(&tr32, d.q, rows, d.q_ts, 32, 1, CU_TENSOR_MAP_SWIZZLE_64B));
+  SB_PROPAGATE(make_qkv_tmap(&ta64, d.q, rows, d.q_ts, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, 48));
+  SB_PROPAGATE(make_qkv_tmap(&ta32, d.q, rows, d.q_ts, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B, 48));
+  SB_PROPAGATE(make_qkv_tmap(&tr64, d.q, rows, d.q_ts, 64, 1, CU_TENSOR_MAP_SWIZZLE_128B, 48));
+  SB_PROPAGATE(make_qkv_tmap(&tr32, d.q, rows, d.q_ts, 32, 1, CU_TENSOR_MAP_SWIZZLE_64B, 48));
   int grid = num_sms();
   if (grid > p.items) grid = p.items;
   profile_mark_begin(1, stream);

@@ -35,6 +35,7 @@ struct VitAttnParams {
   long long q_bs, q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, o_bs, o_hs, o_ts;
   int items, heads;
   float scale_log2;
+  int o_tma;         // attention_tc.cu: the output is written by TMA stores (tensor map passed next to the params)
   long long* dbg;    // optional timeline of block 0: [16 slots][64 items][8 events] clock64 stamps (tools/attn_timeline.py)
 };
 

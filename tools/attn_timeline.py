@@ -57,11 +57,14 @@ if variant == 2:
     ev[4] = ev[0]; ev[13] = ev[10]
     t0 = int(t[0, 0, 0])
 else:
-    names = {0: "softmax w0", 4: "softmax w4", 8: "mma", 9: "row256", 10: "ld Q0", 11: "ld K", 12: "ld Q1", 13: "ld V"}
+    names = {0: "softmax w0", 4: "softmax w4", 8: "mma", 9: "row256", 10: "ld Q0", 11: "ld K", 12: "ld Q1", 13: "ld V",
+             14: "helper w8", 15: "helper w9"}
     ev = {8: ["start", "S0 issue", "S1 issue", "wait v", "v ok", "PV0 issue", "PV1 issue", "end"],
-          0: ["start", "row256 share done", "next item's dots done", "S ok", "max done", "P done", "O ok", "end"],
-          10: ["start", "empty ok", "issued", "full"], 9: ["start", "q,k ok", "key256", "scores ok", "p written"]}
-    ev[4] = ev[0]; ev[11] = ev[12] = ev[13] = ev[10]
+          0: ["start", "-", "-", "S ok", "max done", "P done", "O ok", "end"],
+          10: ["start", "empty ok", "-", "issued/full"],
+          9: ["start", "q,k ok", "key256", "scores ok", "p written", "share done"],
+          14: ["start", "q,k ok", "dots done", "p,v ok", "share done"]}
+    ev[4] = ev[0]; ev[11] = ev[12] = ev[13] = ev[10]; ev[15] = ev[14]
     t0 = int(t[8, 0, 0])
 print(f"--- timeline of block 0, variant {variant} (cycles since the first stamp)")
 for item in range(0, 6):
