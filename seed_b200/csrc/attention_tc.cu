@@ -331,11 +331,16 @@ vit_attention_tc_kernel(const VitAttnParams p, const __grid_constant__ CUtensorM
             dst[g + 8] = acc[q][2];
           }
         }
+        if (j0 < 16) {
+          // first round = this warp's four s-jobs: the softmax warps wait for these, the row-256 warp can wait longer
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s256_full);
+        }
       }
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(q_empty); mbar_arrive(q_empty + 8); mbar_arrive(k_empty);
-        mbar_arrive(cls_bar); mbar_arrive(s256_full);
+        mbar_arrive(cls_bar);
       }
       if (hw < 2) VA_STAMP(14 + hw, 2);
       // this warp's share of row 256's P.V: 16 of the head dims 0..63
