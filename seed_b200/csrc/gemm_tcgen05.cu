@@ -47,6 +47,8 @@ struct GemmParams {
   int tile_shift;            // round r of the persistent schedule hands unit u the tile r*units + (u + r*tile_shift) % units:
                              // with a cheap tail column the plain round robin (shift 0) gives some units all the cheap
                              // tiles and others none whenever units % n_tiles shares a factor with n_tiles
+  int out_tma;               // 1: the epilogue parks 32 x 32 output boxes in shared memory and TMA-stores them (tmap_o)
+  int res_tma;               // 1: ... and the residual boxes arrive by TMA as well (tmap_r), two boxes ahead
   int tail_w;                // > 0: the last n-tile is only tail_w (< BN) columns wide -- loaded through the tail tensor
                              // map, multiplied with a narrower UMMA and read out chunk-limited, so a ragged N (1408 =
                              // 5.5 x 256, 40194 = 157 x 256 + 2) costs its columns, not a whole tile
@@ -63,12 +65,23 @@ struct GemmCfg {
   static constexpr int A_BYTES = KSUB * A_SUB;
   static constexpr int B_BYTES = KSUB * B_SUB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  // Epilogue staging: each of the 8 epilogue warps owns one 32-row x 32-column fp16 box (2 KB, 64-byte rows, SWIZZLE_64B)
+  // that it fills with 16-byte shared-memory stores and hands to a TMA store -- a direct 16-byte global store per thread
+  // touches 32 different lines per instruction, and at 4096 such wavefronts per 128 x 256 tile (8192 with the residual
+  // loads) the SM's load/store unit, not the tensor pipe, set the tile time of the K = 1408 shapes (ncu: LSU data-pipe
+  // 41-50 % busy over the whole kernel, tensor pipe 58-74 %).  CTA pairs with 64-deep stages also have room for two
+  // residual boxes per warp, loaded by TMA two boxes ahead.
+  static constexpr bool STAGED_OUT = (BN % 64 == 0);
+  static constexpr bool STAGED_RES = STAGED_OUT && CTAS == 2 && KSUB == 1;
+  static constexpr int OUT_STAGE_BYTES = STAGED_OUT ? 8 * 2048 : 0;
+  static constexpr int RES_STAGE_BYTES = STAGED_RES ? 2 * 8 * 2048 : 0;
+  static constexpr int STAGES_RAW = (220 * 1024 - OUT_STAGE_BYTES - RES_STAGE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16 + 2 * 256 * 2 + 2 * 2 * 256 * 4;   // barriers, tmem slot, bias stage, LN-fold c / b' stages
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + BAR_BYTES;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16 + 2 * 256 * 2 + 2 * 2 * 256 * 4 + 16 * 8;   // barriers, tmem slot, bias stage, LN-fold c / b' stages, residual-box barriers
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + OUT_STAGE_BYTES + RES_STAGE_BYTES + BAR_BYTES;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   // keep one CTA per SM (TMEM is allocated per CTA): request more than half of the SM's smem
   static constexpr int SMEM_REQUEST = SMEM_BYTES < 120 * 1024 ? 120 * 1024 : SMEM_BYTES;
   static_assert(B_SUB % 1024 == 0, "W stage must keep 1024-byte alignment for SWIZZLE_128B");
@@ -209,10 +222,97 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
   }
 }
 
+// The arithmetic of epilogue_store16 for MODE 0 without the store: 16 accumulator columns of one row -> 16 fp16
+// values (two 16-byte words), same rounding points.  `res0/res1` are the row's 16 residual values when has_res.
+__device__ __forceinline__ void epilogue_compute16(const GemmParams& p, const uint32_t* acc, const __half* bias_s,
+                                                   const float* lnc_s, const float* lnb_s, float ln_mean, float ln_rstd,
+                                                   bool has_res, const uint4& res0, const uint4& res1, uint4& o0, uint4& o1) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+  if (lnc_s != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 c4 = *reinterpret_cast<const float4*>(lnc_s + j);
+      const float4 b4 = *reinterpret_cast<const float4*>(lnb_s + j);
+      v[j + 0] = fmaf(ln_rstd, fmaf(-ln_mean, c4.x, v[j + 0]), b4.x);
+      v[j + 1] = fmaf(ln_rstd, fmaf(-ln_mean, c4.y, v[j + 1]), b4.y);
+      v[j + 2] = fmaf(ln_rstd, fmaf(-ln_mean, c4.z, v[j + 2]), b4.z);
+      v[j + 3] = fmaf(ln_rstd, fmaf(-ln_mean, c4.w, v[j + 3]), b4.w);
+    }
+  }
+  if (bias_s != nullptr) {
+    const uint4 b0 = *reinterpret_cast<const uint4*>(bias_s);
+    const uint4 b1 = *reinterpret_cast<const uint4*>(bias_s + 8);
+    const __half2* bh0 = reinterpret_cast<const __half2*>(&b0);
+    const __half2* bh1 = reinterpret_cast<const __half2*>(&b1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f0 = __half22float2(bh0[j]);
+      const float2 f1 = __half22float2(bh1[j]);
+      v[2 * j] += f0.x; v[2 * j + 1] += f0.y;
+      v[8 + 2 * j] += f1.x; v[8 + 2 * j + 1] += f1.y;
+    }
+  }
+  __half h[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(v[j]);
+  if (p.act == SEEDB200_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(gelu_erf(__half2float(h[j])));
+  } else if (p.act != SEEDB200_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(apply_act(__half2float(h[j]), p.act));
+  }
+  if (has_res) {
+    const __half* rh0 = reinterpret_cast<const __half*>(&res0);
+    const __half* rh1 = reinterpret_cast<const __half*>(&res1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h[j] = __float2half_rn(__half2float(h[j]) + __half2float(rh0[j]));
+      h[8 + j] = __float2half_rn(__half2float(h[8 + j]) + __half2float(rh1[j]));
+    }
+  }
+  __half* oh0 = reinterpret_cast<__half*>(&o0);
+  __half* oh1 = reinterpret_cast<__half*>(&o1);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { oh0[j] = h[j]; oh1[j] = h[8 + j]; }
+}
+
+__device__ __forceinline__ void gm_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// tcgen05.wait::ld that names the registers it completes, so their uses cannot be scheduled above it while the next
+// box's load is already in flight
+__device__ __forceinline__ void gm_tmem_ld_wait32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 template <int BN, int CTAS, int MODE, int KSUB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_bt, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_bt, const __grid_constant__ CUtensorMap tmap_o,
+                    const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
   using Cfg = GemmCfg<BN, CTAS, KSUB>;
   constexpr int STAGE_K = GEMM_BLOCK_K * KSUB;
   constexpr int STAGES = Cfg::STAGES;
@@ -222,7 +322,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + STAGES * Cfg::A_BYTES;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t ostage_base = smem_base + STAGES * Cfg::STAGE_BYTES;          // [8 warps][2 KB] output boxes
+  const uint32_t rstage_base = ostage_base + Cfg::OUT_STAGE_BYTES;             // [8 warps][2][2 KB] residual boxes
+  const uint32_t bar_base = rstage_base + Cfg::RES_STAGE_BYTES;
   const uint32_t full_bar = bar_base;                   // [STAGES]
   const uint32_t empty_bar = bar_base + STAGES * 8;     // [STAGES]
   const uint32_t tfull_bar = bar_base + 2 * STAGES * 8; // [2]
@@ -231,6 +333,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t bias_off = tmem_slot + 16;             // [2][256] halves
   const uint32_t lnc_off = bias_off + 2 * 256 * 2;      // [2][256] floats
   const uint32_t lnb_off = lnc_off + 2 * 256 * 4;       // [2][256] floats
+  const uint32_t res_bar = lnb_off + 2 * 256 * 4;       // [8 warps][2] residual boxes landed
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -245,6 +348,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     if (p.tail_w > 0) tma_prefetch_desc(&tmap_bt);
+    if (p.out_tma) tma_prefetch_desc(&tmap_o);
+    if (p.res_tma) tma_prefetch_desc(&tmap_r);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -255,6 +360,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(tfull_bar + 8 * i, 1);
       mbar_init(tempty_bar + 8 * i, CTAS * (GEMM_EPI_THREADS / 32));   // one arrive per epilogue warp
     }
+    for (int i = 0; i < 16; ++i) mbar_init(res_bar + 8 * i, 1);
     fence_mbar_init();
   } else if (warp == 2) {
     tmem_alloc<CTAS>(tmem_slot, Cfg::TMEM_COLS);
@@ -377,6 +483,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
     int iter = 0;
+    uint32_t res_phase = 0;                    // bit s: parity to wait for on this warp's residual slot s
     for (int round = 0; round * units < total_tiles; ++round, ++iter) {
       const int tile = tile_of(round);
       if (tile >= total_tiles) break;
@@ -416,6 +523,103 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (has_ln) { lnc_next = p.ln_c[n]; lnb_next = p.ln_b[n]; }
             else bias_next = p.bias[n];
           }
+        }
+      }
+      if constexpr (MODE == 0 && Cfg::STAGED_OUT) {
+        if (p.out_tma) {
+          // ---------- staged read-out: 32 x 32 boxes through shared memory, TMA store (and TMA residual) ----------
+          const int nb = (c_end - c_begin) >> 1;           // boxes of this warp (the host guarantees even chunk counts)
+          const uint32_t obuf = ostage_base + ew * 2048;
+          uint8_t* obuf_g = smem_gen + (obuf - smem_base) + lane * 64;
+          const int sw = (lane >> 1) & 3;                  // SWIZZLE_64B: 16-byte chunk index ^ bits 1..2 of the row
+          const int m0 = (mt * CTAS + (int)cta_rank) * GEMM_BLOCK_M + quarter * 32;
+          const bool use_res = p.residual != nullptr;
+          const bool res_tma = Cfg::STAGED_RES && p.res_tma != 0;
+          auto res_issue = [&](int b) {                    // one thread: residual box b of this tile -> slot b & 1
+            const uint32_t slot = (uint32_t)(ew * 2 + (b & 1));
+            mbar_arrive_expect_tx(res_bar + 8 * slot, 2048u);
+            tma_load_2d(rstage_base + slot * 2048, &tmap_r, res_bar + 8 * slot, n_tile0 + (c_begin + 2 * b) * 16, m0);
+          };
+          if (res_tma && use_res && lane == 0) {           // two boxes ahead, before the accumulator is even ready
+            if (nb > 0) res_issue(0);
+            if (nb > 1) res_issue(1);
+          }
+          mbar_wait_relaxed(tfull_bar + 8 * as, aphase);
+          tc_fence_after();
+          const uint32_t t_acc = tmem_base + as * Cfg::ACC_STRIDE + lane_addr;
+          if (nb == 0) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (CTAS == 2) mbar_arrive_cluster(lead_tempty0 + 8 * as);
+              else mbar_arrive(tempty_bar + 8 * as);
+            }
+          }
+          uint32_t ra[32], rb[32];
+          auto box = [&](int b, uint32_t(&cur)[32], uint32_t(&nxt)[32]) {
+            const int cc = c_begin + 2 * b;
+            gm_tmem_ld_wait32(cur);
+            if (b + 1 < nb) {
+              gm_tmem_ld32(t_acc + (cc + 2) * 16, nxt);
+            } else {
+              // every TMEM read of this accumulator stage is done: hand it back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (CTAS == 2) mbar_arrive_cluster(lead_tempty0 + 8 * as);
+                else mbar_arrive(tempty_bar + 8 * as);
+              }
+            }
+            uint4 rs[4];
+            rs[0] = rs[1] = rs[2] = rs[3] = make_uint4(0, 0, 0, 0);
+            bool has_res = false;
+            if (use_res) {
+              if (res_tma) {
+                const uint32_t slot = (uint32_t)(ew * 2 + (b & 1));
+                mbar_wait_relaxed(res_bar + 8 * slot, (res_phase >> (b & 1)) & 1u);
+                res_phase ^= 1u << (b & 1);
+                const uint8_t* rp = smem_gen + (rstage_base + slot * 2048 - smem_base) + lane * 64;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) rs[q] = *reinterpret_cast<const uint4*>(rp + ((q ^ sw) << 4));
+                __syncwarp();
+                if (lane == 0 && b + 2 < nb) res_issue(b + 2);
+                has_res = true;
+              } else if (row_ok && n_tile0 + cc * 16 < p.N) {      // (N % 32 == 0: a box is inside or outside)
+                const __half* rr = res_row + n_tile0 + cc * 16;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) rs[q] = *reinterpret_cast<const uint4*>(rr + 8 * q);
+                has_res = true;
+              }
+            }
+            uint4 o[4];
+            epilogue_compute16(p, &cur[0], has_bias ? bias_smem + as * 256 + cc * 16 : nullptr,
+                               has_ln ? lnc_smem + as * 256 + cc * 16 : nullptr, lnb_smem + as * 256 + cc * 16, ln_st.x,
+                               ln_st.y, has_res, rs[0], rs[1], o[0], o[1]);
+            epilogue_compute16(p, &cur[16], has_bias ? bias_smem + as * 256 + (cc + 1) * 16 : nullptr,
+                               has_ln ? lnc_smem + as * 256 + (cc + 1) * 16 : nullptr, lnb_smem + as * 256 + (cc + 1) * 16,
+                               ln_st.x, ln_st.y, has_res, rs[2], rs[3], o[2], o[3]);
+            // the previous box has left the staging buffer (its store only has to have READ shared memory)
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(obuf_g + ((q ^ sw) << 4)) = o[q];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_o, obuf, n_tile0 + cc * 16, m0);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          };
+          if (nb > 0) gm_tmem_ld32(t_acc + c_begin * 16, ra);
+          for (int b = 0; b < nb; b += 2) {
+            box(b, ra, rb);
+            if (b + 1 < nb) box(b + 1, rb, ra);
+          }
+          if (has_cols && etid < BN) {
+            if (has_ln) { lnc_smem[(as ^ 1) * 256 + etid] = lnc_next; lnb_smem[(as ^ 1) * 256 + etid] = lnb_next; }
+            else bias_smem[(as ^ 1) * 256 + etid] = bias_next;
+          }
+          continue;
         }
       }
       uint4 rn0 = make_uint4(0, 0, 0, 0), rn1 = rn0;
@@ -477,6 +681,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         else bias_smem[(as ^ 1) * 256 + etid] = bias_next;
       }
     }
+    if (p.out_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -529,6 +734,28 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t col
   return 0;
 }
 
+// fp16 [rows, cols] row-major, 32 x 32 boxes with 64-byte rows (SWIZZLE_64B): the epilogue's output / residual boxes
+static int make_box_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    return SEEDB200_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (epilogue box) failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r,
+              (long long)rows, (long long)cols, (long long)ld);
+    return SEEDB200_ERR_CUDA;
+  }
+  return 0;
+}
+
 template <int BN, int CTAS, int MODE, int KSUB>
 static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CTAS, KSUB>;
@@ -553,6 +780,23 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   if (tail_w > 0) SB_PROPAGATE(make_tmap(&tbt, d.W, d.N, d.K, d.ldw, tail_w / CTAS));
   else tbt = tb;
 
+  // staged read-out (see GemmCfg): plain row-major output, every epilogue warp owns whole 32-column boxes
+  CUtensorMap to, tr;
+  to = tb; tr = tb;
+  int out_tma = 0, res_tma = 0;
+  if (MODE == 0 && Cfg::STAGED_OUT && d.row_group == 0 && d.res_mod == 0 && get_option("gemm_out_tma") != 0 &&
+      (tail_w == 0 || tail_w % 64 == 0) && d.ldo % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
+      (d.residual == nullptr ||
+       (d.N % 32 == 0 && d.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(d.residual) & 15) == 0))) {
+    out_tma = 1;
+    SB_PROPAGATE(make_box_tmap(&to, d.out, d.M, d.N, d.ldo));
+    if (Cfg::STAGED_RES && d.residual != nullptr) {
+      res_tma = 1;
+      SB_PROPAGATE(make_box_tmap(&tr, d.residual, d.M, d.N, d.ldr));
+    }
+  }
+
   GemmParams p;
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.m_tiles = (d.M + GEMM_BLOCK_M * CTAS - 1) / (GEMM_BLOCK_M * CTAS);
@@ -566,6 +810,7 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   p.row_group = d.row_group; p.row_stride = d.row_stride; p.row_offset = d.row_offset;
   p.res_mod = d.res_mod; p.res_offset = d.res_offset;
   p.tail_w = tail_w;
+  p.out_tma = out_tma; p.res_tma = res_tma;
   p.tile_shift = 0;
   p.ln_stats = static_cast<const float2*>(d.ln_stats);
   p.ln_c = static_cast<const float*>(d.ln_c);
@@ -594,7 +839,7 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   profile_mark_begin(0, stream);
-  SB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tbt, p));
+  SB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tbt, to, tr, p));
   profile_mark_end(0, stream, 2.0 * (double)d.M * (double)d.N * (double)d.K);
   count_launch();
   return 0;
