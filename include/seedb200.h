@@ -120,6 +120,13 @@ typedef struct seedb200_gemm_desc {
    * The normalised activations are never materialised (no LN kernel, no fp16 LN tensor in HBM); the reference's
    * rounding of LN(x) to fp16 is replaced by the rounding of W gamma to fp16 -- same order, bounded in the tests. */
   const void* ln_stats; const void* ln_c; const void* ln_b;
+  /* optional: float2 [M, N/64] -- (sum, sum of squares) of every 64-column group of the OUTPUT row as stored (after
+   * bias / activation / residual, rounded to fp16); a warp that covers several groups writes its total into the first
+   * and zeros into the others.  seedb200_row_stats_from_moments turns the groups into the (mean, rstd) of the next
+   * LayerNorm-folded GEMM, so the residual stream is not re-read for its statistics (eva_vit.py:201-202: the output of
+   * x + attn(..) / x + mlp(..) is what norm2 / the next block's norm1 normalise).  Needs mode 0, N % 64 == 0, no row
+   * remap and a 64-column-divisible tiling (the staged epilogue); otherwise SEEDB200_ERR_UNSUPPORTED.              */
+  void* row_moments;
 } seedb200_gemm_desc;
 int seedb200_gemm(const seedb200_gemm_desc* d, void* stream);
 
@@ -130,6 +137,9 @@ int seedb200_gemm(const seedb200_gemm_desc* d, void* stream);
  * c [N] fp32 = row sums of the ROUNDED W' (so that acc - mean*c is exact for the operand the MMA really reads),
  * b' [N] fp32 = W beta + bias.                                                                                   */
 int seedb200_row_stats(const void* x, int64_t ldx, int rows, int cols, float eps, void* stats_out, void* stream);
+/* (mean, rstd) per row from the 64-column moments a GEMM epilogue left (seedb200_gemm_desc.row_moments): groups are
+ * summed in index order in fp32, mean and variance (E[x^2] - mean^2) finished in fp64; cols = the row length N.     */
+int seedb200_row_stats_from_moments(const void* moments, int rows, int cols, float eps, void* stats_out, void* stream);
 int seedb200_ln_fold_weights(const void* W, int64_t ldw, const void* gamma, const void* beta, const void* bias, int N,
                              int K, void* W_out, void* c_out, void* b_out, void* stream);
 

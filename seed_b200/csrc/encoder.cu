@@ -69,7 +69,9 @@ struct seedb200_encoder {
   __half *hq, *hq_t, *q_qkv, *q_ctx, *q_inter, *z, *quant, *dtmp;
   int64_t* ids_buf;
   float* row_stats;                // [T] (mean, rstd) pairs of the LayerNorm-folded GEMMs
+  float* row_mom;                  // [T][VIT_D / 64] (sum, sum of squares) groups left by the proj / fc2 epilogues
   int ln_fold;
+  int stats_fused;                 // option "encoder_stats_fused": statistics from the producing GEMM's epilogue
   __half* img_in;                  // staging for the host entry point
   int last_B;
   int device;                      // the device that was current at create (weights + workspace live there)
@@ -126,13 +128,14 @@ static int copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size
 
 static int linear(cudaStream_t st, int ctas, int M, int N, int K, const void* A, int64_t lda, const void* W,
                   const void* bias, void* out, int64_t ldo, int act = 0, const void* residual = nullptr,
-                  int64_t ldr = 0) {
+                  int64_t ldr = 0, void* row_moments = nullptr) {
   seedb200_gemm_desc d;
   memset(&d, 0, sizeof(d));
   d.M = M; d.N = N; d.K = K;
   d.A = A; d.lda = lda; d.W = W; d.ldw = K;
   d.out = out; d.ldo = ldo; d.bias = bias; d.residual = residual; d.ldr = ldr;
   d.act = act; d.ctas = ctas;
+  d.row_moments = row_moments;
   return gemm(d, st);
 }
 
@@ -315,6 +318,7 @@ static int build(seedb200_encoder* e) {
   SB_PROPAGATE(dev_alloc_t(e, &e->dtmp, Q * 256 + B * DT_OUT));
   SB_PROPAGATE(dev_alloc_t(e, &e->ids_buf, Q));
   SB_PROPAGATE(dev_alloc_t(e, &e->row_stats, 2 * T));
+  SB_PROPAGATE(dev_alloc_t(e, &e->row_mom, (size_t)2 * T * (VIT_D / 64)));
   SB_PROPAGATE(dev_alloc_t(e, &e->img_in, B * 3 * 224 * 224));
   SB_CHECK_CUDA(cudaStreamSynchronize(st));
   return 0;
@@ -359,8 +363,12 @@ static int run_vit(seedb200_encoder* e, const void* images, int B, cudaStream_t 
   const float scale = 0.10660035817780521f;   // 88^-0.5 (eva_vit.py:93)
   for (size_t i = 0; i < e->vit.size(); ++i) {
     const VitBlockW& b = e->vit[i];
+    // the statistics of norm1 / norm2: from the epilogue of the GEMM that wrote x (previous block's fc2, this block's
+    // proj) when stats_fused, else (and for the first block) from a pass over x
+    void* mom = (e->ln_fold && e->stats_fused) ? e->row_mom : nullptr;
     if (e->ln_fold) {
-      SB_PROPAGATE(row_stats(e->x, VIT_D, T, VIT_D, 1e-6f, e->row_stats, st));
+      if (mom != nullptr && i > 0) SB_PROPAGATE(row_stats_from_moments(mom, T, VIT_D, 1e-6f, e->row_stats, st));
+      else SB_PROPAGATE(row_stats(e->x, VIT_D, T, VIT_D, 1e-6f, e->row_stats, st));
       SB_PROPAGATE(linear_ln(st, ct, T, 3 * VIT_D, VIT_D, e->x, b.qkv_wf, e->row_stats, b.qkv_c, b.qkv_bf, qkv, 3 * VIT_D, 0));
     } else {
       SB_PROPAGATE(layernorm(e->x, VIT_D, b.n1w, b.n1b, e->ln, VIT_D, T, VIT_D, 1e-6f, st));
@@ -369,16 +377,18 @@ static int run_vit(seedb200_encoder* e, const void* images, int B, cudaStream_t 
     SB_PROPAGATE(attn_call(st, qkv, (int64_t)VIT_TOK * 3 * VIT_D, VIT_HD, 3 * VIT_D, qkv + VIT_D, qkv + 2 * VIT_D,
                            (int64_t)VIT_TOK * 3 * VIT_D, VIT_HD, 3 * VIT_D, e->att, (int64_t)VIT_TOK * VIT_D, VIT_HD,
                            VIT_D, B, VIT_H, VIT_TOK, VIT_TOK, VIT_HD, 0, scale));
-    SB_PROPAGATE(linear(st, ct, T, VIT_D, VIT_D, e->att, VIT_D, b.proj_w, b.proj_b, e->x, VIT_D, 0, e->x, VIT_D));
+    SB_PROPAGATE(linear(st, ct, T, VIT_D, VIT_D, e->att, VIT_D, b.proj_w, b.proj_b, e->x, VIT_D, 0, e->x, VIT_D, mom));
     if (e->ln_fold) {
-      SB_PROPAGATE(row_stats(e->x, VIT_D, T, VIT_D, 1e-6f, e->row_stats, st));
+      if (mom != nullptr) SB_PROPAGATE(row_stats_from_moments(mom, T, VIT_D, 1e-6f, e->row_stats, st));
+      else SB_PROPAGATE(row_stats(e->x, VIT_D, T, VIT_D, 1e-6f, e->row_stats, st));
       SB_PROPAGATE(linear_ln(st, ct, T, VIT_FF, VIT_D, e->x, b.fc1_wf, e->row_stats, b.fc1_c, b.fc1_bf, hid, VIT_FF,
                              SEEDB200_ACT_GELU));
     } else {
       SB_PROPAGATE(layernorm(e->x, VIT_D, b.n2w, b.n2b, e->ln, VIT_D, T, VIT_D, 1e-6f, st));
       SB_PROPAGATE(linear(st, ct, T, VIT_FF, VIT_D, e->ln, VIT_D, b.fc1_w, b.fc1_b, hid, VIT_FF, SEEDB200_ACT_GELU));
     }
-    SB_PROPAGATE(linear(st, ct, T, VIT_D, VIT_FF, hid, VIT_FF, b.fc2_w, b.fc2_b, e->x, VIT_D, 0, e->x, VIT_D));
+    SB_PROPAGATE(linear(st, ct, T, VIT_D, VIT_FF, hid, VIT_FF, b.fc2_w, b.fc2_b, e->x, VIT_D, 0, e->x, VIT_D,
+                        i + 1 < e->vit.size() ? mom : nullptr));
   }
   SB_PROPAGATE(layernorm(e->x, VIT_D, e->lnv_w, e->lnv_b, e->ln, VIT_D, T, VIT_D, 1e-5f, st));
   return 0;
@@ -498,6 +508,7 @@ int seedb200_encoder_create(const seedb200_encoder_config* cfg, const seedb200_t
   e->last_B = 0;
   e->device = sb::cur_device();
   e->ln_fold = sb::get_option("encoder_ln_fold") != 0;
+  e->stats_fused = sb::get_option("encoder_stats_fused") != 0 && sb::get_option("gemm_out_tma") != 0;
   for (int i = 0; i < n_weights; ++i) e->w[std::string(weights[i].name)] = weights[i];
   int s = sb::build(e);
   if (s != 0) {

@@ -47,6 +47,7 @@ struct GemmParams {
   int tile_shift;            // round r of the persistent schedule hands unit u the tile r*units + (u + r*tile_shift) % units:
                              // with a cheap tail column the plain round robin (shift 0) gives some units all the cheap
                              // tiles and others none whenever units % n_tiles shares a factor with n_tiles
+  float2* row_moments;       // staged epilogue only: (sum, sum of squares) per 64-column group of the stored output rows
   int out_tma;               // 1: the epilogue parks 32 x 32 output boxes in shared memory and TMA-stores them (tmap_o)
   int res_tma;               // 1: ... and the residual boxes arrive by TMA as well (tmap_r), two boxes ahead
   int tail_w;                // > 0: the last n-tile is only tail_w (< BN) columns wide -- loaded through the tail tensor
@@ -556,6 +557,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
           uint32_t ra[32], rb[32];
+          float mom_s = 0.0f, mom_q = 0.0f;               // moments of this thread's row over this warp's columns
           auto box = [&](int b, uint32_t(&cur)[32], uint32_t(&nxt)[32]) {
             const int cc = c_begin + 2 * b;
             gm_tmem_ld_wait32(cur);
@@ -598,6 +600,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             epilogue_compute16(p, &cur[16], has_bias ? bias_smem + as * 256 + (cc + 1) * 16 : nullptr,
                                has_ln ? lnc_smem + as * 256 + (cc + 1) * 16 : nullptr, lnb_smem + as * 256 + (cc + 1) * 16,
                                ln_st.x, ln_st.y, has_res, rs[2], rs[3], o[2], o[3]);
+            if (p.row_moments != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&o[q]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __half22float2(h2[j]);
+                  mom_s += f.x + f.y;
+                  mom_q = fmaf(f.x, f.x, mom_q);
+                  mom_q = fmaf(f.y, f.y, mom_q);
+                }
+              }
+            }
             // the previous box has left the staging buffer (its store only has to have READ shared memory)
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
@@ -614,6 +629,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int b = 0; b < nb; b += 2) {
             box(b, ra, rb);
             if (b + 1 < nb) box(b + 1, rb, ra);
+          }
+          if (p.row_moments != nullptr && row_ok && nb > 0) {
+            const int groups = p.N >> 6;                   // 64-column groups per row
+            const int g0 = (n_tile0 + c_begin * 16) >> 6, gn = (nb * 32 + 63) >> 6;
+            float2* mp = p.row_moments + (long long)m * groups + g0;
+            mp[0] = make_float2(mom_s, mom_q);
+            for (int g = 1; g < gn && g0 + g < groups; ++g) mp[g] = make_float2(0.0f, 0.0f);
           }
           if (has_cols && etid < BN) {
             if (has_ln) { lnc_smem[(as ^ 1) * 256 + etid] = lnc_next; lnb_smem[(as ^ 1) * 256 + etid] = lnb_next; }
@@ -811,6 +833,15 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   p.res_mod = d.res_mod; p.res_offset = d.res_offset;
   p.tail_w = tail_w;
   p.out_tma = out_tma; p.res_tma = res_tma;
+  p.row_moments = static_cast<float2*>(d.row_moments);
+  if (d.row_moments != nullptr) {
+    SB_REQUIRE(MODE == 0 && d.N % 64 == 0, "gemm: row_moments needs mode 0 and N %% 64 == 0 (N=%d)", d.N);
+    if (!out_tma) {
+      set_error("gemm: row_moments needs the staged epilogue (plain row-major output, 64-column-divisible tiles); "
+                "this call (N=%d bn=%d) takes the direct one", d.N, BN);
+      return SEEDB200_ERR_UNSUPPORTED;
+    }
+  }
   p.tile_shift = 0;
   p.ln_stats = static_cast<const float2*>(d.ln_stats);
   p.ln_c = static_cast<const float*>(d.ln_c);
@@ -880,6 +911,8 @@ int gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   SB_REQUIRE(ctas == 1 || ctas == 2, "gemm: ctas must be 1 or 2 (got %d)", ctas);
   if (ctas == 2 && d.M <= GEMM_BLOCK_M) ctas = 1;                 // pairs only pay off on big tiles
   int bn = d.bn > 0 ? d.bn : pick_bn(d.N, d.mode, ctas);
+  // the epilogue moments need whole 64-column groups per warp: 176-wide tiles (N = 1408 on single CTAs) do not have them
+  if (d.row_moments != nullptr && d.bn == 0 && bn % 64 != 0) bn = d.N % 128 == 0 ? 128 : 256;
   if (ctas == 2 && bn < 64) ctas = 1;
 
   // 128-deep stages pay off for CTA pairs on long reductions or exactly tiled wide outputs (measured on B200:

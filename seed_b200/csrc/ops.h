@@ -14,6 +14,7 @@ int attention(const seedb200_attn_desc& d, cudaStream_t stream);
 int layernorm(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy, int rows, int cols,
               float eps, cudaStream_t stream);
 int row_stats(const void* x, int64_t ldx, int rows, int cols, float eps, void* stats, cudaStream_t stream);
+int row_stats_from_moments(const void* moments, int rows, int cols, float eps, void* stats, cudaStream_t stream);
 int ln_fold_weights(const void* W, int64_t ldw, const void* gamma, const void* beta, const void* bias, int N, int K,
                     void* W_out, void* c_out, void* b_out, cudaStream_t stream);
 int rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int cols, float eps,

@@ -143,6 +143,33 @@ static int launch_norm(const void* x, int64_t ldx, const void* w, const void* b,
   return SEEDB200_ERR_UNSUPPORTED;
 }
 
+// (mean, rstd) from the 64-column (sum, sum of squares) groups a GEMM epilogue left behind (GemmParams::row_moments):
+// thread per row, groups added in index order (deterministic), the cancellation-prone E[x^2] - mean^2 in fp64
+__global__ void stats_from_moments_kernel(const float2* __restrict__ mom, int rows, int groups, float inv_cols, float eps,
+                                          float2* __restrict__ stats) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float2* mp = mom + (long long)r * groups;
+  float s = 0.0f, q = 0.0f;
+  for (int g = 0; g < groups; ++g) {
+    const float2 v = mp[g];
+    s += v.x;
+    q += v.y;
+  }
+  const double mean = (double)s * (double)inv_cols;
+  double var = (double)q * (double)inv_cols - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[r] = make_float2((float)mean, rsqrtf((float)var + eps));
+}
+
+int row_stats_from_moments(const void* moments, int rows, int cols, float eps, void* stats, cudaStream_t stream) {
+  SB_REQUIRE(moments && stats && rows > 0 && cols > 0 && cols % 64 == 0, "row_stats_from_moments: bad arguments (cols=%d)", cols);
+  stats_from_moments_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(static_cast<const float2*>(moments), rows, cols / 64,
+                                                                    1.0f / (float)cols, eps, static_cast<float2*>(stats));
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
 int row_stats(const void* x, int64_t ldx, int rows, int cols, float eps, void* stats, cudaStream_t stream) {
   SB_REQUIRE(x && stats && rows > 0 && cols > 0, "row_stats: bad arguments");
   SB_REQUIRE(cols % 8 == 0 && ldx % 8 == 0, "row_stats: cols/ld must be multiples of 8 (cols=%d)", cols);
@@ -436,6 +463,9 @@ extern "C" {
 int seedb200_layernorm(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy, int rows,
                        int cols, float eps, void* stream) {
   return sb::layernorm(x, ldx, w, b, y, ldy, rows, cols, eps, static_cast<cudaStream_t>(stream));
+}
+int seedb200_row_stats_from_moments(const void* moments, int rows, int cols, float eps, void* stats_out, void* stream) {
+  return sb::row_stats_from_moments(moments, rows, cols, eps, stats_out, static_cast<cudaStream_t>(stream));
 }
 int seedb200_row_stats(const void* x, int64_t ldx, int rows, int cols, float eps, void* stats_out, void* stream) {
   return sb::row_stats(x, ldx, rows, cols, eps, stats_out, static_cast<cudaStream_t>(stream));

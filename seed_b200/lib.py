@@ -33,7 +33,7 @@ EXPORTS = [
     "seedb200_gemv", "seedb200_decode_attention", "seedb200_decode_attention_workspace_bytes",
     "seedb200_sample", "seedb200_philox_uniform", "seedb200_image_ids_to_tokens", "seedb200_encoder_encode_tokens",
     "seedb200_llama_forward_ld", "seedb200_llama_generate", "seedb200_llama_generate_used_graph",
-    "seedb200_row_stats", "seedb200_ln_fold_weights",
+    "seedb200_row_stats", "seedb200_row_stats_from_moments", "seedb200_ln_fold_weights",
 ]
 
 
@@ -53,7 +53,8 @@ class GemmDesc(C.Structure):
                 ("row_group", C.c_int32), ("row_stride", C.c_int32), ("row_offset", C.c_int32),
                 ("res_mod", C.c_int32), ("res_offset", C.c_int32),
                 ("bn", C.c_int32), ("ctas", C.c_int32),
-                ("ln_stats", C.c_void_p), ("ln_c", C.c_void_p), ("ln_b", C.c_void_p)]
+                ("ln_stats", C.c_void_p), ("ln_c", C.c_void_p), ("ln_b", C.c_void_p),
+                ("row_moments", C.c_void_p)]
 
 
 class AttnDesc(C.Structure):
@@ -140,6 +141,7 @@ def load() -> C.CDLL:
     lib.seedb200_llama_tap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     lib.seedb200_llama_tap.restype = C.c_int64
     lib.seedb200_row_stats.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    lib.seedb200_row_stats_from_moments.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
     lib.seedb200_ln_fold_weights.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.seedb200_preprocess_create_ex.argtypes = [C.c_int] * 9 + [C.POINTER(C.c_void_p)]
@@ -227,9 +229,10 @@ def profile_end() -> dict:
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, mode: int = 0,
          bn: int = 0, ctas: int = 0, row_group: int = 0, row_stride: int = 0, row_offset: int = 0,
-         res_mod: int = 0, res_offset: int = 0, ln=None) -> torch.Tensor:
+         res_mod: int = 0, res_offset: int = 0, ln=None, row_moments: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = epilogue(a @ w.T); a [M,K], w [N,K] fp16 (nn.Linear layout).  ln = (stats [M,2] fp32, c [N] fp32,
-    b [N] fp32) selects the LayerNorm-folded epilogue (w must then be the folded weight of ln_fold_weights)."""
+    b [N] fp32) selects the LayerNorm-folded epilogue (w must then be the folded weight of ln_fold_weights).
+    row_moments: float32 [M, N/64, 2] that receives (sum, sum of squares) per 64-column group of the output rows."""
     _need_cuda_f16(a, "gemm.a"); _need_cuda_f16(w, "gemm.w")
     M, K = a.shape
     N = w.shape[0]
@@ -254,6 +257,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
             if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
                 raise RuntimeError("gemm: ln tensors must be contiguous CUDA float32")
         d.ln_stats, d.ln_c, d.ln_b = stats.data_ptr(), cvec.data_ptr(), bvec.data_ptr()
+    if row_moments is not None:
+        if (row_moments.dtype != torch.float32 or not row_moments.is_cuda or not row_moments.is_contiguous()
+                or row_moments.numel() != M * (N // 64) * 2):
+            raise RuntimeError("gemm: row_moments must be contiguous CUDA float32 [M, N/64, 2]")
+        d.row_moments = row_moments.data_ptr()
     with on(a.device):
         check(load().seedb200_gemm(C.byref(d), stream_ptr(a.device)), "seedb200_gemm")
     return out
@@ -277,6 +285,16 @@ def row_stats(x: torch.Tensor, eps: float) -> torch.Tensor:
     with on(x.device):
         check(load().seedb200_row_stats(x.data_ptr(), x.stride(0), rows, cols, eps, out.data_ptr(), stream_ptr(x.device)),
               "seedb200_row_stats")
+    return out
+
+
+def row_stats_from_moments(moments: torch.Tensor, cols: int, eps: float) -> torch.Tensor:
+    """moments float32 [rows, cols/64, 2] (gemm(..., row_moments=)) -> (mean, rstd) float32 [rows, 2]."""
+    rows = moments.shape[0]
+    out = torch.empty((rows, 2), dtype=torch.float32, device=moments.device)
+    with on(moments.device):
+        check(load().seedb200_row_stats_from_moments(moments.data_ptr(), rows, cols, eps, out.data_ptr(),
+                                                     stream_ptr(moments.device)), "seedb200_row_stats_from_moments")
     return out
 
 

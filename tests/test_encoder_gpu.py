@@ -212,3 +212,30 @@ def test_layernorm_fold_option_agrees_with_standalone_layernorm():
         assert (z.float().cpu() - ref["z"].reshape(-1, 32)).abs().max().item() <= 1e-2
         outs[fold] = (ids.cpu(), taps["vit"].float().cpu())
     assert rel(outs[1][1], outs[0][1]) <= 3e-3
+
+
+def test_epilogue_statistics_option_agrees_with_the_statistics_pass():
+    """option "encoder_stats_fused": the (mean, rstd) of norm1 / norm2 from the proj / fc2 epilogues
+    (seedb200_gemm_desc.row_moments) vs a pass over x -- same ids above the margin, activations equal up to the fp16 roundings a last-bit change of rstd moves"""
+    from seed_b200 import lib as L
+
+    sd = synth.encoder_state_dict(4, 2, 0)
+    x = synth.images(3, seed=92)
+    with torch.no_grad():
+        ref = R.encode(x, sd, 4, 2)
+    outs = {}
+    for fused in (1, 0):
+        L.set_option("encoder_stats_fused", fused)
+        try:
+            model = make_model(sd, max_batch=4, vq_mode=1)
+        finally:
+            L.set_option("encoder_stats_fused", 1)
+        ids, z = model.encode_ids(x.cuda(), return_z=True)
+        taps = model.taps(3)
+        torch.cuda.synchronize()
+        check_ids(ids, ref["ids"], ref["margin"], f"stats_fused={fused}")
+        outs[fused] = (ids.cpu(), taps["vit"].float().cpu())
+    # (the two differ in the last bits of rstd, which moves fp16 roundings downstream: ids may differ only where
+    # check_ids allows it -- under the margin)
+    assert (outs[1][0] != outs[0][0]).sum().item() <= 2
+    assert rel(outs[1][1], outs[0][1]) <= 1e-3

@@ -583,3 +583,43 @@ def test_gemm_layernorm_folded(lib, M, N, K, act, ctas):
     assert e_ours <= 1.5 * e_ref + 1e-4, (e_ours, e_ref)      # as close to exact arithmetic as the reference's own rounding
     assert rel_err(out, ref16) < 1.5e-3
     assert_close16(out, ref16, ulps=6.0, atol=2e-3, what="LN-folded GEMM vs rounding-point reference")
+
+
+@pytest.mark.parametrize("M,N,K,ctas", [(2056, 1408, 1408, 2), (2056, 1408, 6144, 2), (300, 1408, 1408, 1), (257, 512, 768, 1)])
+def test_gemm_row_moments_give_the_layernorm_statistics_of_the_output(lib, M, N, K, ctas):
+    """x += linear(a) with the (sum, sum of squares) of every 64-column group of the NEW x left by the epilogue
+    (seedb200_gemm_desc.row_moments): row_stats_from_moments == row_stats of the stored rows, so the next
+    LayerNorm-folded GEMM does not have to re-read x (eva_vit.py:201-202)."""
+    a = rand16(M, K, seed=85)
+    w = rand16(N, K, scale=K ** -0.5, seed=86)
+    bias = rand16(N, scale=0.1, seed=87)
+    x = rand16(M, N, scale=2.0, seed=88) + 0.25
+    x[:, 7] += 20.0
+    plain = lib.gemm(a, w, bias, residual=x, ctas=ctas)
+    mom = torch.full((M, N // 64, 2), float("nan"), dtype=torch.float32, device=DEV)
+    out = lib.gemm(a, w, bias, residual=x, out=x, ctas=ctas, row_moments=mom)          # in place, like proj / fc2
+    torch.cuda.synchronize()
+    assert torch.equal(out, plain)                             # the moments do not change the result
+    assert not torch.isnan(mom).any()                          # every group slot was written
+    of = out.float()
+    assert torch.allclose(mom[:, :, 0].sum(-1), of.sum(-1), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(mom[:, :, 1].sum(-1), (of * of).sum(-1), rtol=1e-5, atol=1e-2)
+    st = lib.row_stats_from_moments(mom, N, 1e-6)
+    st2 = lib.row_stats(out, 1e-6)
+    assert torch.allclose(st[:, 0], st2[:, 0], rtol=0, atol=4e-6 * of.abs().max().item())
+    assert torch.allclose(st[:, 1], st2[:, 1], rtol=2e-5, atol=0)
+    # same call twice: bit-identical moments (fixed slots, fixed order -- no atomics)
+    x2 = rand16(M, N, scale=2.0, seed=88) + 0.25
+    x2[:, 7] += 20.0
+    mom2 = torch.empty_like(mom)
+    lib.gemm(a, w, bias, residual=x2, out=x2, ctas=ctas, row_moments=mom2)
+    torch.cuda.synchronize()
+    assert torch.equal(mom, mom2)
+
+
+def test_gemm_row_moments_refused_where_the_epilogue_cannot_provide_them(lib):
+    a = rand16(64, 256, seed=89)
+    w = rand16(96, 256, seed=90)
+    mom = torch.empty((64, 1, 2), dtype=torch.float32, device=DEV)
+    with pytest.raises(RuntimeError):
+        lib.gemm(a, w, row_moments=mom)                        # N = 96 is not a multiple of 64
