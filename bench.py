@@ -113,6 +113,10 @@ def dist_setup(n_gpus: int):
     if world > 1:
         import torch.distributed as dist
 
+        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION, which some images export)
+        # goes to stdout too
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return world, rank, local
