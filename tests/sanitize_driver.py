@@ -39,6 +39,15 @@ def gemm():
         res = r16(M, N, seed=4)
         out = L.gemm(a, w, bias=b, act=L.ACT_GELU, residual=res, bn=bn, ctas=ctas)
         assert rel(out, R.linear_ref(a, w, b, 1, res)) < 2e-3, (M, N, K)
+    # staged epilogue with TMA residual boxes, in place, leaving the row moments (the encoder's proj / fc2 calls)
+    a, w, b = r16(520, 768, seed=1), r16(1408, 768, scale=768 ** -0.5, seed=2), r16(1408, seed=3)
+    x = r16(520, 1408, seed=4)
+    want = R.linear_ref(a, w, b, 0, x)
+    mom = torch.empty((520, 1408 // 64, 2), dtype=torch.float32, device=DEV)
+    out = L.gemm(a, w, bias=b, residual=x, out=x, ctas=2, row_moments=mom)
+    assert rel(out, want) < 2e-3
+    st = L.row_stats_from_moments(mom, 1408, 1e-6)
+    assert torch.allclose(st, L.row_stats(out, 1e-6), rtol=1e-4, atol=1e-4)
     a = r16(300, 512, seed=5)
     wg, wu = r16(1408, 512, scale=0.04, seed=6), r16(1408, 512, scale=0.04, seed=7)
     out = L.gemm(a, R.interleave_gate_up(wg, wu), mode=1, ctas=2)
@@ -54,6 +63,12 @@ def attention():
         q, k, v = r16(B, H, Nq, D, seed=11), r16(B, H, Nk, D, seed=12), r16(B, H, Nk, D, seed=13)
         out = L.attention(q, k, v, D ** -0.5, causal)
         assert rel(out, R.attention_ref(q, k, v, D ** -0.5, causal)) < 3e-3, (B, H, Nq, Nk, D, causal)
+    # the ViT shape on the packed projection buffer: Q / K / V by TMA, O by TMA store (what the encoder launches)
+    B, H, N, D = 2, 16, 257, 88
+    qkv = r16(B * N, 3 * H * D, seed=14)
+    q, k, v = (qkv.view(B, N, 3, H, D)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    out = L.attention(q, k, v, D ** -0.5, False)
+    assert rel(out, R.attention_ref(q, k, v, D ** -0.5, False)) < 3e-3
 
 
 def rowwise():
