@@ -67,6 +67,8 @@ void seedb200_reset_launch_count(void);
  * serialization (each starts while its predecessor drains and waits on griddepcontrol before reading activations).
  * "gemm_ksub": 0 (default) = heuristic, 1 = 64-deep GEMM pipeline stages, 2 = 128-deep.
  * "gemm_tail": 1 (default) = a ragged last column of tiles runs at its own width, 0 = as a full tile.
+ * "gemm_sched": 1 (default) = GEMMs with few tiles per SM (LLaMA prefill) pick tile width / pairing / schedule from
+ * a load-balance model (seedb200_gemm_plan), 0 = the fixed heuristics, 2 = balanced-tail order with an explicit bn.
  * "encoder_ln_fold" (read by seedb200_encoder_create): 1 (default) = norm1 / norm2 of the ViT blocks are folded
  * into the qkv / fc1 GEMMs (seedb200_gemm_desc.ln_stats), 0 = standalone LayerNorm kernels.                    */
 int seedb200_set_option(const char* key, int value);
@@ -129,6 +131,14 @@ typedef struct seedb200_gemm_desc {
   void* row_moments;
 } seedb200_gemm_desc;
 int seedb200_gemm(const seedb200_gemm_desc* d, void* stream);
+/* Host-only views of the GEMM's persistent tile schedule (no GPU needed; tests/test_capi_cpu.py checks that every
+ * tile is handed out exactly once).  gemm_plan: what seedb200_gemm would pick for `d` on a device with `sms` SMs --
+ * out9 = {bn, ctas, sched, ksub, m_tiles, n_tiles, units, tile_shift, tail_w}; pointers in `d` are not dereferenced.
+ * gemm_schedule_tile: the tile (mt * n_tiles + nt) of unit `unit`'s round-th iteration, m_tiles * n_tiles when the
+ * unit is done.  sched 0 = rotated round robin, 1 = balanced tail (full-width tiles round robin, then the units that
+ * got one fewer take the narrow last-column tiles: the M = 2048 LLaMA prefill shapes, llama_xformer.py:223-225,258). */
+int seedb200_gemm_plan(const seedb200_gemm_desc* d, int sms, int32_t* out9);
+int seedb200_gemm_schedule_tile(int sched, int round, int unit, int units, int m_tiles, int n_tiles, int tile_shift);
 
 /* The two helpers of the LayerNorm-folded GEMM (seedb200_gemm_desc.ln_stats):
  * row_stats: (mean, rstd = 1/sqrt(var + eps)) of every row of x [rows, cols] fp16, two-pass in fp32 exactly like

@@ -47,6 +47,10 @@ struct GemmParams {
   int tile_shift;            // round r of the persistent schedule hands unit u the tile r*units + (u + r*tile_shift) % units:
                              // with a cheap tail column the plain round robin (shift 0) gives some units all the cheap
                              // tiles and others none whenever units % n_tiles shares a factor with n_tiles
+  int sched;                 // 0: round robin (above).  1: balanced tail -- the full-width tiles go round robin over the units
+                             // first, then the units that got one full tile fewer take the narrow tail tiles; with few tiles
+                             // per unit (M = 2048 prefill: 128 tiles of 256 x 256 on 74 CTA pairs = 2 rounds, the second
+                             // 27 % empty) a narrower tile + this order lands every unit within ~1 % of the mean
   float2* row_moments;       // staged epilogue only: (sum, sum of squares) per 64-column group of the stored output rows
   int out_tma;               // 1: the epilogue parks 32 x 32 output boxes in shared memory and TMA-stores them (tmap_o)
   int res_tma;               // 1: ... and the residual boxes arrive by TMA as well (tmap_r), two boxes ahead
@@ -54,6 +58,28 @@ struct GemmParams {
                              // map, multiplied with a narrower UMMA and read out chunk-limited, so a ragged N (1408 =
                              // 5.5 x 256, 40194 = 157 x 256 + 2) costs its columns, not a whole tile
 };
+
+// Persistent schedule: the tile (mt * n_tiles + nt) of unit `unit`'s round-th iteration, >= m_tiles * n_tiles when the
+// unit is done.  sched 0: round robin with a per-round rotation (GemmParams::tile_shift).  sched 1: balanced tail.
+__host__ __device__ inline int sched_tile(int sched, int round, int unit, int units, int m_tiles, int n_tiles, int tile_shift) {
+  const int total_tiles = m_tiles * n_tiles;
+  if (sched == 0) {
+    const int t = round * units + (unit + round * tile_shift) % units;
+    return t < total_tiles ? t : total_tiles;
+  }
+  const int ncol_full = n_tiles - 1;
+  const int F = m_tiles * ncol_full;               // full-width tiles; the m_tiles tiles of the last column come last
+  const int q = F / units, r = F % units;
+  const int nf = q + (unit < r ? 1 : 0);
+  if (round < nf) {
+    const int f = round * units + unit;
+    return (f / ncol_full) * n_tiles + (f % ncol_full);
+  }
+  if (r != 0 && unit < r) return total_tiles;      // already has one full tile more than the others
+  const int S = (r == 0) ? units : units - r;
+  const int t = (unit - (r == 0 ? 0 : r)) + (round - nf) * S;
+  return t < m_tiles ? t * n_tiles + ncol_full : total_tiles;
+}
 
 // KSUB: 64-wide K sub-blocks per pipeline stage.  KSUB = 2 halves the per-stage fixed cost in the MMA issuer
 // (one mbarrier wait + one tcgen05.commit per 8 MMAs instead of per 4), which is what bounded the
@@ -375,16 +401,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int unit = (CTAS == 2) ? (blockIdx.x >> 1) : blockIdx.x;
   const int units = (CTAS == 2) ? (gridDim.x >> 1) : gridDim.x;
-  auto tile_of = [&](int round) { return round * units + (unit + round * p.tile_shift) % units; };
+  auto tile_of = [&](int round) -> int {
+    return sched_tile(p.sched, round, unit, units, p.m_tiles, p.n_tiles, p.tile_shift);
+  };
   const int tile0 = tile_of(0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int round = 0; round * units < total_tiles; ++round) {
+      for (int round = 0;; ++round) {
         const int tile = tile_of(round);
-        if (tile >= total_tiles) break;            // only the last round is partial
+        if (tile >= total_tiles) break;
         const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
         const int m_idx = (mt * CTAS + (int)cta_rank) * GEMM_BLOCK_M;
         const bool tail_tile = p.tail_w > 0 && nt == p.n_tiles - 1;
@@ -423,7 +451,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       constexpr uint32_t idesc_full = make_idesc_f16(GEMM_BLOCK_M * CTAS, BN);
       const uint32_t idesc_tail = make_idesc_f16(GEMM_BLOCK_M * CTAS, p.tail_w > 0 ? p.tail_w : BN);
       int stage = 0; uint32_t phase = 0; int iter = 0;
-      for (int round = 0; round * units < total_tiles; ++round, ++iter) {
+      for (int round = 0;; ++round, ++iter) {
         const int tile = tile_of(round);
         if (tile >= total_tiles) break;
         const int as = iter & 1;
@@ -485,7 +513,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     int iter = 0;
     uint32_t res_phase = 0;                    // bit s: parity to wait for on this warp's residual slot s
-    for (int round = 0; round * units < total_tiles; ++round, ++iter) {
+    for (int round = 0;; ++round, ++iter) {
       const int tile = tile_of(round);
       if (tile >= total_tiles) break;
       const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
@@ -518,7 +546,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // this tile's vectors were staged one tile ago (or in the prologue); the barrier publishes them
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int next = tile_of(round + 1);
-        if ((round + 1) * units < total_tiles && next < total_tiles && etid < BN) {     // issue the load now, consume it after the chunk loop
+        if (next < total_tiles && etid < BN) {     // issue the load now, consume it after the chunk loop
           const int n = (next % p.n_tiles) * BN + etid;
           if (n < p.N) {
             if (has_ln) { lnc_next = p.ln_c[n]; lnb_next = p.ln_b[n]; }
@@ -778,8 +806,39 @@ static int make_box_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t
   return 0;
 }
 
+// Host side of the persistent schedule: tile grid, ragged tail width, units and the round-robin rotation.
+struct TileSchedule { int m_tiles, n_tiles, tail_w, units, tile_shift, sched; };
+
+static TileSchedule make_schedule(int M, int N, int bn, int ctas, int mode, int sched, int sms, bool tail_opt) {
+  TileSchedule t;
+  t.m_tiles = (M + GEMM_BLOCK_M * ctas - 1) / (GEMM_BLOCK_M * ctas);
+  t.n_tiles = (N + bn - 1) / bn;
+  // ragged N: the last n-tile is loaded / multiplied / read out at its own width (rounded up to what UMMA and the
+  // 8-row core-matrix groups allow: 16 columns per CTA of the pair)
+  t.tail_w = 0;
+  if (mode == 0 && N % bn != 0 && tail_opt) {
+    const int q = 16 * ctas;
+    t.tail_w = (N % bn + q - 1) / q * q;
+    if (t.tail_w >= bn) t.tail_w = 0;
+  }
+  const int tiles = t.m_tiles * t.n_tiles;
+  t.units = sms / ctas;
+  if (t.units > tiles) t.units = tiles;
+  if (t.units < 1) t.units = 1;
+  t.sched = (sched == 1 && t.n_tiles >= 2) ? 1 : 0;
+  t.tile_shift = 0;
+  if (t.sched == 0 && t.tail_w > 0 && t.n_tiles > 1) {
+    // advance of a unit's n-tile index per round = (units + shift) mod n_tiles: make it coprime with n_tiles so that
+    // every unit meets the cheap tail column once every n_tiles rounds
+    auto gcd = [](int a, int b) { while (b) { const int x = a % b; a = b; b = x; } return a; };
+    for (int sft = 0; sft < t.n_tiles; ++sft)
+      if (gcd((t.units + sft) % t.n_tiles, t.n_tiles) == 1) { t.tile_shift = sft; break; }
+  }
+  return t;
+}
+
 template <int BN, int CTAS, int MODE, int KSUB>
-static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
+static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream, int sched) {
   using Cfg = GemmCfg<BN, CTAS, KSUB>;
   static bool attr_set_dev[SB_MAX_DEVICES] = {};   // cudaFuncSetAttribute is per device
   bool& attr_set = attr_set_dev[cur_device()];
@@ -791,14 +850,8 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   CUtensorMap ta, tb, tbt;
   SB_PROPAGATE(make_tmap(&ta, d.A, d.M, d.K, d.lda, GEMM_BLOCK_M));
   SB_PROPAGATE(make_tmap(&tb, d.W, d.N, d.K, d.ldw, Cfg::LOAD_N));
-  // ragged N: the last n-tile is loaded / multiplied / read out at its own width (rounded up to what UMMA and the
-  // 8-row core-matrix groups allow: 16 columns per CTA of the pair)
-  int tail_w = 0;
-  if (MODE == 0 && d.N % BN != 0 && get_option("gemm_tail") != 0) {
-    const int q = 16 * CTAS;
-    tail_w = (d.N % BN + q - 1) / q * q;
-    if (tail_w >= BN) tail_w = 0;
-  }
+  const TileSchedule ts = make_schedule(d.M, d.N, BN, CTAS, MODE, sched, num_sms(), get_option("gemm_tail") != 0);
+  const int tail_w = ts.tail_w;
   if (tail_w > 0) SB_PROPAGATE(make_tmap(&tbt, d.W, d.N, d.K, d.ldw, tail_w / CTAS));
   else tbt = tb;
 
@@ -821,8 +874,8 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
 
   GemmParams p;
   p.M = d.M; p.N = d.N; p.K = d.K;
-  p.m_tiles = (d.M + GEMM_BLOCK_M * CTAS - 1) / (GEMM_BLOCK_M * CTAS);
-  p.n_tiles = (d.N + BN - 1) / BN;
+  p.m_tiles = ts.m_tiles;
+  p.n_tiles = ts.n_tiles;
   p.bias = static_cast<const __half*>(d.bias);
   p.residual = static_cast<const __half*>(d.residual);
   p.ldr = d.ldr;
@@ -842,23 +895,13 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
       return SEEDB200_ERR_UNSUPPORTED;
     }
   }
-  p.tile_shift = 0;
+  p.tile_shift = ts.tile_shift;
+  p.sched = ts.sched;
   p.ln_stats = static_cast<const float2*>(d.ln_stats);
   p.ln_c = static_cast<const float*>(d.ln_c);
   p.ln_b = static_cast<const float*>(d.ln_b);
 
-  const int sms = num_sms();
-  const int tiles = p.m_tiles * p.n_tiles;
-  int units = sms / CTAS;
-  if (units > tiles) units = tiles;
-  if (units < 1) units = 1;
-  if (tail_w > 0 && p.n_tiles > 1) {
-    // advance of a unit's n-tile index per round = (units + shift) mod n_tiles: make it coprime with n_tiles so that
-    // every unit meets the cheap tail column once every n_tiles rounds
-    auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
-    for (int sft = 0; sft < p.n_tiles; ++sft)
-      if (gcd((units + sft) % p.n_tiles, p.n_tiles) == 1) { p.tile_shift = sft; break; }
-  }
+  const int units = ts.units;
 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(units * CTAS);
@@ -894,9 +937,43 @@ static int pick_bn(int N, int mode, int ctas) {
 
 int get_option(const char* key);
 
-int gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
+// Largest number of output columns any unit of the persistent schedule works through.
+static int plan_max_cols(int M, int N, int bn, int ctas, int sched, int sms) {
+  const TileSchedule t = make_schedule(M, N, bn, ctas, 0, sched, sms, true);
+  const int tiles = t.m_tiles * t.n_tiles, w_last = t.tail_w > 0 ? t.tail_w : bn;
+  int worst = 0;
+  for (int u = 0; u < t.units; ++u) {
+    int cols = 0;
+    for (int round = 0;; ++round) {
+      const int tile = sched_tile(t.sched, round, u, t.units, t.m_tiles, t.n_tiles, t.tile_shift);
+      if (tile >= tiles) break;
+      cols += (tile % t.n_tiles == t.n_tiles - 1) ? w_last : bn;
+    }
+    if (cols > worst) worst = cols;
+  }
+  return worst;
+}
+
+// Few tiles per unit (LLaMA prefill: M = 2048 or a 256-token prompt): pick the tile width / pairing / schedule whose
+// busiest unit finishes first.  Rough per-shape efficiencies of the narrower tiles (tools/llama_gemm_ab.py) break ties.
+static void plan_small_problem(const seedb200_gemm_desc& d, int sms, int& bn, int& ctas, int& sched) {
+  struct Cand { int bn, ctas; double eff; };
+  static const Cand cands[] = {{256, 2, 1.00}, {224, 2, 0.985}, {192, 2, 0.97}, {128, 2, 0.90}, {64, 2, 0.72},
+                               {256, 1, 0.93}, {192, 1, 0.90},  {128, 1, 0.84}, {64, 1, 0.65}};
+  double best = 1e30;
+  for (const Cand& c : cands) {
+    if (c.ctas > ctas) continue;                       // the caller asked for single CTAs
+    if (c.ctas == 2 && d.M <= GEMM_BLOCK_M) continue;
+    for (int sc = 0; sc < 2; ++sc) {
+      const double cost = plan_max_cols(d.M, d.N, c.bn, c.ctas, sc, sms) / c.eff * (sc == 1 ? 1.0 : 1.0005);
+      if (cost < best) { best = cost; bn = c.bn; ctas = c.ctas; sched = sc; }
+    }
+  }
+}
+
+struct GemmPlan { int bn, ctas, sched, ksub; };
+static int choose_plan(const seedb200_gemm_desc& d, int sms, GemmPlan& plan) {
   SB_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "gemm: non-positive shape M=%d N=%d K=%d", d.M, d.N, d.K);
-  SB_REQUIRE(d.A && d.W && d.out, "gemm: null operand");
   SB_REQUIRE(d.mode == 0 || d.mode == 1, "gemm: unknown mode %d", d.mode);
   SB_REQUIRE(d.K % 8 == 0, "gemm: K=%d must be a multiple of 8 (16-byte TMA rows)", d.K);
   if (d.ln_stats != nullptr) {
@@ -914,6 +991,14 @@ int gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   // the epilogue moments need whole 64-column groups per warp: 176-wide tiles (N = 1408 on single CTAs) do not have them
   if (d.row_moments != nullptr && d.bn == 0 && bn % 64 != 0) bn = d.N % 128 == 0 ? 128 : 256;
   if (ctas == 2 && bn < 64) ctas = 1;
+  int sched = 0;
+  if (d.bn == 0 && d.mode == 0 && d.N >= 1024 && get_option("gemm_sched") != 0 && d.ln_stats == nullptr &&
+      d.row_moments == nullptr && d.row_group == 0 && d.res_mod == 0 && get_option("gemm_tail") != 0) {
+    const long long tiles256 = (long long)((d.M + GEMM_BLOCK_M * ctas - 1) / (GEMM_BLOCK_M * ctas)) * ((d.N + 255) / 256);
+    if (tiles256 < 8LL * (sms / ctas)) plan_small_problem(d, sms, bn, ctas, sched);
+  } else if (d.bn != 0 && get_option("gemm_sched") == 2) {
+    sched = 1;                                           // A/B runs with an explicit tile width
+  }
 
   // 128-deep stages pay off for CTA pairs on long reductions or exactly tiled wide outputs (measured on B200:
   // qkv/fc1/fc2 +5..10%); they lose on short-K ragged tilings (proj BN=256: -26%) and on single CTAs (-5%).
@@ -921,12 +1006,22 @@ int gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   int ksub = (d.K > 64 && ctas == 2 && ((bn >= 192 && d.N % bn == 0) || d.K >= 4096)) ? 2 : 1;
   if (get_option("gemm_ksub") == 1) ksub = 1;
   if (get_option("gemm_ksub") == 2 && d.K > 64) ksub = 2;
+  plan.bn = bn; plan.ctas = ctas; plan.sched = sched; plan.ksub = ksub;
+  return 0;
+}
+
+int gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
+  GemmPlan plan;
+  SB_PROPAGATE(choose_plan(d, num_sms(), plan));
+  SB_REQUIRE(d.A && d.W && d.out, "gemm: null operand");
+  const int bn = plan.bn, ctas = plan.ctas, sched = plan.sched, ksub = plan.ksub;
 #define SB_GEMM_CASE(BN_, CT_, MD_)                                                   \
   if (bn == BN_ && ctas == CT_ && d.mode == MD_) {                                    \
-    if (ksub == 2) return launch_gemm<BN_, CT_, MD_, 2>(d, stream);                   \
-    return launch_gemm<BN_, CT_, MD_, 1>(d, stream);                                  \
+    if (ksub == 2) return launch_gemm<BN_, CT_, MD_, 2>(d, stream, sched);            \
+    return launch_gemm<BN_, CT_, MD_, 1>(d, stream, sched);                           \
   }
   SB_GEMM_CASE(256, 1, 0) SB_GEMM_CASE(256, 2, 0)
+  SB_GEMM_CASE(224, 2, 0)
   SB_GEMM_CASE(192, 1, 0) SB_GEMM_CASE(192, 2, 0)
   SB_GEMM_CASE(176, 1, 0) SB_GEMM_CASE(176, 2, 0)
   SB_GEMM_CASE(128, 1, 0) SB_GEMM_CASE(128, 2, 0)
@@ -939,6 +1034,25 @@ int gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
 }
 
 }  // namespace sb
+
+extern "C" int seedb200_gemm_plan(const seedb200_gemm_desc* d, int sms, int32_t* out9) {
+  if (d == nullptr || out9 == nullptr || sms <= 0) {
+    sb::set_error("seedb200_gemm_plan: null argument or sms <= 0");
+    return SEEDB200_ERR_INVALID;
+  }
+  sb::GemmPlan plan;
+  SB_PROPAGATE(sb::choose_plan(*d, sms, plan));
+  const sb::TileSchedule t = sb::make_schedule(d->M, d->N, plan.bn, plan.ctas, d->mode, plan.sched, sms,
+                                               sb::get_option("gemm_tail") != 0);
+  const int32_t v[9] = {plan.bn, plan.ctas, t.sched, plan.ksub, t.m_tiles, t.n_tiles, t.units, t.tile_shift, t.tail_w};
+  for (int i = 0; i < 9; ++i) out9[i] = v[i];
+  return 0;
+}
+
+extern "C" int seedb200_gemm_schedule_tile(int sched, int round, int unit, int units, int m_tiles, int n_tiles,
+                                           int tile_shift) {
+  return sb::sched_tile(sched, round, unit, units, m_tiles, n_tiles, tile_shift);
+}
 
 extern "C" int seedb200_gemm(const seedb200_gemm_desc* d, void* stream) {
   if (d == nullptr) {

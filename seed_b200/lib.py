@@ -34,6 +34,7 @@ EXPORTS = [
     "seedb200_sample", "seedb200_philox_uniform", "seedb200_image_ids_to_tokens", "seedb200_encoder_encode_tokens",
     "seedb200_llama_forward_ld", "seedb200_llama_generate", "seedb200_llama_generate_used_graph",
     "seedb200_row_stats", "seedb200_row_stats_from_moments", "seedb200_ln_fold_weights",
+    "seedb200_gemm_plan", "seedb200_gemm_schedule_tile",
 ]
 
 

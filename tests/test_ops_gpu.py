@@ -91,6 +91,49 @@ def test_gemm_plain(lib, M, N, K, bn, ctas):
     assert_close16(out, ref, what="gemm")
 
 
+# few tiles per CTA pair (LLaMA prefill, M = 2048 or a 256-token prompt): the load-balance model picks the tiling
+# (224-wide tiles + tail, balanced-tail order); K kept short so the fp32 oracle stays cheap
+PLANNED_SHAPES = [(2048, 4096, 320), (2048, 12288, 128), (256, 5120, 320), (256, 15360, 128), (2048, 5120, 192),
+                  (1000, 3072, 768), (2048, 4098, 64)]
+
+
+@pytest.mark.parametrize("residual", [False, True])
+@pytest.mark.parametrize("M,N,K", PLANNED_SHAPES)
+def test_gemm_planned_tilings(lib, M, N, K, residual):
+    a = rand16(M, K, seed=21)
+    w = rand16(N, K, scale=K ** -0.5, seed=22)
+    res = rand16(M, N, seed=23) if residual else None
+    out = lib.gemm(a, w, residual=res, ctas=2)
+    torch.cuda.synchronize()
+    ref = R.linear_ref(a, w, None, 0, res)
+    assert_close16(out, ref, mags=(R.linear_ref(a, w),) + ((res,) if residual else ()), ulps=3.0, what="planned gemm")
+    # ... and the fixed heuristics (option off) give bit-identical results: the tiling never changes the k order
+    lib.set_option("gemm_sched", 0)
+    try:
+        out0 = lib.gemm(a, w, residual=res, ctas=2)
+        torch.cuda.synchronize()
+    finally:
+        lib.set_option("gemm_sched", 1)
+    assert torch.equal(out, out0)
+
+
+@pytest.mark.parametrize("bn", [224, 192, 256, 128])
+def test_gemm_balanced_tail_order_with_explicit_width(lib, bn):
+    M, N, K = 2048, 4096, 256
+    a = rand16(M, K, seed=24)
+    w = rand16(N, K, scale=K ** -0.5, seed=25)
+    bias = rand16(N, scale=0.5, seed=26)
+    ref = lib.gemm(a, w, bias=bias, bn=256, ctas=2)
+    lib.set_option("gemm_sched", 2)
+    try:
+        out = lib.gemm(a, w, bias=bias, bn=bn, ctas=2)
+        torch.cuda.synchronize()
+    finally:
+        lib.set_option("gemm_sched", 1)
+    assert torch.equal(out, ref)
+    assert_close16(out, R.linear_ref(a, w, bias), what="balanced tail")
+
+
 @pytest.mark.parametrize("act", [0, 1, 2, 3])
 @pytest.mark.parametrize("ctas", [1, 2])
 def test_gemm_bias_act_residual(lib, act, ctas):
