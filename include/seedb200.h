@@ -67,6 +67,8 @@ void seedb200_reset_launch_count(void);
  * serialization (each starts while its predecessor drains and waits on griddepcontrol before reading activations).
  * "gemm_ksub": 0 (default) = heuristic, 1 = 64-deep GEMM pipeline stages, 2 = 128-deep.
  * "gemm_tail": 1 (default) = a ragged last column of tiles runs at its own width, 0 = as a full tile.
+ * "decode_fused_attention": 1 (default) = the cached decode step runs RoPE + KV append + attention as one kernel per
+ * layer when max_seq <= 2048 (seedb200_decode_attention_rope), 0 = rope_kv_append + split-KV decode attention.
  * "gemm_sched": 1 (default) = GEMMs with few tiles per SM (LLaMA prefill) pick tile width / pairing / schedule from
  * a load-balance model (seedb200_gemm_plan), 0 = the fixed heuristics, 2 = balanced-tail order with an explicit bn.
  * "encoder_ln_fold" (read by seedb200_encoder_create): 1 (default) = norm1 / norm2 of the ViT blocks are folded
@@ -217,6 +219,15 @@ int seedb200_gemv(const void* x, const void* W, int64_t ldw, void* out, const vo
 int64_t seedb200_decode_attention_workspace_bytes(int B, int H, int max_seq);
 int seedb200_decode_attention(const void* q, const void* k_cache, const void* v_cache, void* out, int B, int H, int D,
                               int kv_len, int max_seq, float scale, void* workspace, void* stream);
+
+/* The same step fused with what precedes it in the decode form of LlamaAttention.forward: apply_rotary_pos_emb on
+ * the new token's q / k (llama_xformer.py:152-161), the KV-cache append (:234-239) and the attention (:240-256) in one
+ * launch.  qkv [B, 3*H*D] (q | k | v of ONE new token per sequence), positions [B] int64 or NULL (= past_len); K (post-
+ * RoPE) and V are appended at cache row past_len of caches [B,H,max_seq,D]; out [B, H*D] fp16.  D = 128 and
+ * max_seq <= 2048 (longer caches: seedb200_rope_kv_append + seedb200_decode_attention); for caches of at most 512 keys
+ * the result is bit-identical to that pair.                                                                       */
+int seedb200_decode_attention_rope(const void* qkv, const int64_t* positions, int B, int H, int D, int past_len,
+                                   int max_seq, void* k_cache, void* v_cache, void* out, float scale, void* stream);
 
 /* Next-token selection, on the device.  Replaces what the reference gets from HF GenerationMixin at its call
  * site scripts/seed_llama_inference_8B.py:33 / gradio_demo/seed_llama_flask.py:172 (temperature, top_p,

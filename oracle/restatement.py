@@ -86,7 +86,7 @@ def qformer_forward(image_embeds: torch.Tensor, sd: SD, layers: int) -> torch.Te
     q = sd["query_tokens"].expand(B, -1, -1)
     h = F.layer_norm(q, (768,), sd[pre + "embeddings.LayerNorm.weight"], sd[pre + "embeddings.LayerNorm.bias"], 1e-12)
     n = h.shape[1]
-    ids = torch.arange(n)
+    ids = torch.arange(n, device=h.device)
     causal = (ids[None, :] <= ids[:, None]).to(h.dtype)
     mask = ((1.0 - causal) * -10000.0)[None, None]
     for l in range(layers):

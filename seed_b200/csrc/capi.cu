@@ -50,7 +50,7 @@ void profile_mark_end(int kind, cudaStream_t stream, double flops) {
 static std::map<std::string, int>& options() {
   static std::map<std::string, int> o = [] {
     std::map<std::string, int> m = {{"vit_attention_tc", 1}, {"causal_attention_tc", 1}, {"decode_pdl", 1}, {"gemv_ksplit", 0},
-                                    {"gemm_ksub", 0}, {"gemm_tail", 1}, {"encoder_ln_fold", 1}, {"gemv_prefetch_mb", 0}, {"vit_attention_tma", 1}, {"gemm_out_tma", 1}, {"encoder_stats_fused", 1}, {"gemm_sched", 1}};
+                                    {"gemm_ksub", 0}, {"gemm_tail", 1}, {"encoder_ln_fold", 1}, {"gemv_prefetch_mb", 0}, {"vit_attention_tma", 1}, {"gemm_out_tma", 1}, {"encoder_stats_fused", 1}, {"gemm_sched", 1}, {"decode_fused_attention", 1}, {"gemv_occupancy", 0}, {"gemv_deep", 0}};
     // A/B runs of unmodified commands (bench.py): SEEDB200_OPT_<KEY>=<int> overrides a default at load time
     for (auto& kv : m) {
       std::string env = "SEEDB200_OPT_";
@@ -186,6 +186,17 @@ int seedb200_rope_kv_append(const void* qkv, const int64_t* positions, int B, in
   SB_PROPAGATE(sb::get_rope_tables(D, 10000.0f, max_seq, &cos_t, &sin_t, &max_pos, st));
   return sb::rope_kv_append_tables(qkv, positions, B, S, H, D, past_len, max_seq, max_pos, cos_t, sin_t, q_out,
                                    k_cache, v_cache, st);
+}
+
+/* the fused decode form: RoPE + append + attention of one new token per sequence, one launch */
+int seedb200_decode_attention_rope(const void* qkv, const int64_t* positions, int B, int H, int D, int past_len,
+                                   int max_seq, void* k_cache, void* v_cache, void* out, float scale, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const void *cos_t, *sin_t;
+  int max_pos;
+  SB_PROPAGATE(sb::get_rope_tables(D, 10000.0f, max_seq, &cos_t, &sin_t, &max_pos, st));
+  return sb::decode_attention_rope(qkv, positions, B, H, D, past_len, max_seq, max_pos, cos_t, sin_t, k_cache, v_cache,
+                                   out, scale, st);
 }
 
 }  // extern "C"

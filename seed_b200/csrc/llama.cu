@@ -182,6 +182,7 @@ static int llama_forward(seedb200_llama* m, const int64_t* input_ids, const void
   const int kv_len = past_len + S;
   const bool fuse_norm = T <= 4;     // decode: RMSNorm folded into the GEMV that consumes it
   PdlScope pdl(T <= 4 && get_option("decode_pdl") != 0);   // decode chain: programmatic dependent launches
+  const bool fused_attn = S == 1 && get_option("decode_fused_attention") != 0 && decode_attention_rope_supported(D, c.max_seq);
   for (int l = 0; l < c.layers; ++l) {
     const LlamaLayerW& L = m->layers[l];
     if (fuse_norm) {
@@ -191,6 +192,11 @@ static int llama_forward(seedb200_llama* m, const int64_t* input_ids, const void
       SB_PROPAGATE(lin(st, ct, T, 3 * h, h, m->nb, L.qkv_w, m->qkv, 3 * h, nullptr, 0));
     }
     // qkv rows are [q | k | v] per token, each [H, D]
+    if (fused_attn) {
+      // cached decode step: RoPE + append + attention in one launch (bit-identical to the pair below up to 512 keys)
+      SB_PROPAGATE(decode_attention_rope(m->qkv, position_ids, B, H, D, past_len, c.max_seq, m->max_pos, m->cos_t,
+                                         m->sin_t, L.k_cache, L.v_cache, m->att, scale, st, dyn));
+    } else {
     SB_PROPAGATE(rope_kv_append_tables(m->qkv, position_ids, B, S, H, D, past_len, c.max_seq, m->max_pos, m->cos_t,
                                        m->sin_t, m->q, L.k_cache, L.v_cache, st, dyn));
     if (S == 1) {
@@ -206,6 +212,7 @@ static int llama_forward(seedb200_llama* m, const int64_t* input_ids, const void
       a.o_bs = (int64_t)S * h; a.o_hs = D; a.o_ts = h;
       a.batch = B; a.heads = H; a.nq = S; a.nk = kv_len; a.head_dim = D; a.causal = 1; a.scale = scale;
       SB_PROPAGATE(attention(a, st));
+    }
     }
     SB_PROPAGATE(lin(st, ct, T, h, h, m->att, L.o_w, m->x, h, m->x, 0));
     if (fuse_norm) {

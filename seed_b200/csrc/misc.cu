@@ -54,7 +54,9 @@ __device__ __forceinline__ void dot8(const uint4& w, const uint4& x, float& acc)
   }
 }
 
-template <int M, int MODE, bool NORM>
+// U: 16-byte vectors per weight row a lane keeps in flight (4 = 128 bytes per lane; 8 for the short-N projections
+// whose few warps cannot cover the HBM latency otherwise).  CTAs are 256 or 128 threads (nw warps).
+template <int M, int MODE, bool NORM, int U>
 __global__ void __launch_bounds__(256)
 gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long long ldw, __half* __restrict__ out,
             const __half* __restrict__ residual, const __half* __restrict__ norm_w, float eps, int N, int K,
@@ -70,7 +72,8 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
   // the 8 warps of a CTA work on 8/ksplit row pairs at a time; warp = (pair, K slice).  Short-N projections
   // (o_proj, down_proj: 2560 row pairs for ~3500 resident warps) would otherwise be one long dependent chain of
   // load batches per warp.
-  const int tpi = 8 / ksplit;                         // row pairs per CTA iteration
+  const int nw = blockDim.x >> 5, nthr = blockDim.x;
+  const int tpi = nw / ksplit;                        // row pairs per CTA iteration
   const int slice = warp % ksplit, tin = warp / ksplit;
   const int vps = (((nvec + ksplit - 1) / ksplit) + 31) / 32 * 32;
   const int v0 = slice * vps, v1 = min(nvec, v0 + vps);
@@ -79,7 +82,7 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
     else { r0 = 2LL * t; r1 = min(r0 + 1, (long long)N - 1); }
   };
   // first batch of this warp's first task: in flight while the activations are staged
-  uint4 wa[4], wb[4];
+  uint4 wa[U], wb[U];
   const int t_first = blockIdx.x * tpi + tin;
   if (t_first < n_tasks) {
     long long r0, r1;
@@ -87,7 +90,7 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
     const uint4* w0 = reinterpret_cast<const uint4*>(W + r0 * ldw);
     const uint4* w1 = reinterpret_cast<const uint4*>(W + r1 * ldw);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int vi = v0 + lane + u * 32;
       if (vi < v1) { wa[u] = __ldg(w0 + vi); wb[u] = __ldg(w1 + vi); }
     }
@@ -95,7 +98,7 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
     // resident long before its predecessor has finished, and the dependency wait + activation staging below would
     // otherwise leave HBM idle (weights never depend on the predecessor).  Sized by the host to ~24 MB per launch.
     for (int l = lane; l < pf_lines; l += 32) {
-      const int vi = v0 + 128 + l * 8;
+      const int vi = v0 + 32 * U + l * 8;
       if (vi < v1) { prefetch_l2(w0 + vi); prefetch_l2(w1 + vi); }
     }
   }
@@ -105,7 +108,7 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
 #pragma unroll 1
     for (int m = 0; m < M; ++m) {
       float ss = 0.0f;
-      for (int i = threadIdx.x; i < nvec; i += 256) {
+      for (int i = threadIdx.x; i < nvec; i += nthr) {
         const uint4 raw = reinterpret_cast<const uint4*>(x)[m * nvec + i];
         const __half2* h = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
@@ -116,10 +119,9 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
       if (lane == 0) red[warp] = ss;
       __syncthreads();
       float tot = 0.0f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) tot += red[i];
+      for (int i = 0; i < nw; ++i) tot += red[i];
       const float rstd = rsqrtf(tot * (1.0f / (float)K) + eps);
-      for (int i = threadIdx.x; i < nvec; i += 256) {
+      for (int i = threadIdx.x; i < nvec; i += nthr) {
         const uint4 raw = reinterpret_cast<const uint4*>(x)[m * nvec + i];
         const uint4 wraw = __ldg(reinterpret_cast<const uint4*>(norm_w) + i);
         const __half* h = reinterpret_cast<const __half*>(&raw);
@@ -135,7 +137,7 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
       }
     }
   } else {
-    for (int i = threadIdx.x; i < M * nvec; i += 256) xs[i] = reinterpret_cast<const uint4*>(x)[i];
+    for (int i = threadIdx.x; i < M * nvec; i += nthr) xs[i] = reinterpret_cast<const uint4*>(x)[i];
   }
   __syncthreads();
 
@@ -150,16 +152,16 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
       rows_of(t, r0, r1);
       const uint4* w0 = reinterpret_cast<const uint4*>(W + r0 * ldw);
       const uint4* w1 = reinterpret_cast<const uint4*>(W + r1 * ldw);
-      for (int v = v0 + lane; v < v1; v += 128) {
+      for (int v = v0 + lane; v < v1; v += 32 * U) {
         if (it != 0 || v != v0 + lane) {    // the very first batch is already in registers
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < U; ++u) {
             const int vi = v + u * 32;
             if (vi < v1) { wa[u] = __ldg(w0 + vi); wb[u] = __ldg(w1 + vi); }
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
           const int vi = v + u * 32;
           if (vi < v1) {
 #pragma unroll
@@ -225,14 +227,19 @@ int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* resid
   SB_REQUIRE(smem <= 200 * 1024, "gemv: activation rows do not fit shared memory (M=%d K=%d)", M, K);
   const int n_tasks = mode == 1 ? N / 2 : (N + 1) / 2;
   const int force_split = get_option("gemv_ksplit");
+  // option gemv_deep: row-pair count below which the 8-vectors-in-flight / 128-thread form is used (0 = never):
+  // o_proj / down_proj of the decode step have 2560 pairs for ~2400 resident warps, one dependent chain of 128-byte
+  // loads per lane each
+  const bool deep = M <= 2 && get_option("gemv_deep") > 0 && n_tasks <= get_option("gemv_deep");
   const __half* xp = static_cast<const __half*>(x);
   const __half* wp = static_cast<const __half*>(W);
   const __half* rp = static_cast<const __half*>(residual);
   const __half* np = static_cast<const __half*>(norm_w);
   __half* op = static_cast<__half*>(out);
-#define SB_GEMV_LAUNCH(M_, MD_, NM_)                                                                       \
+#define SB_GEMV_LAUNCH(M_, MD_, NM_, U_)                                                                   \
   {                                                                                                        \
-    auto kern = gemv_kernel<M_, MD_, NM_>;                                                                 \
+    auto kern = gemv_kernel<M_, MD_, NM_, U_>;                                                             \
+    const int threads = (U_ == 8) ? 128 : 256;                                                             \
     static size_t attr_smem_dev[SB_MAX_DEVICES] = {};   /* per device: cudaFuncSetAttribute is */          \
     const int dev_ = cur_device();                                                                         \
     size_t& attr_smem = attr_smem_dev[dev_];                                                               \
@@ -246,16 +253,19 @@ int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* resid
     int& occ = occ_dev[dev_]; size_t& occ_smem = occ_smem_dev[dev_];                                       \
     if (occ == 0) occ_smem = (size_t)-1;                                                                   \
     if (occ_smem != smem) {                                                                                \
-      SB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));                 \
+      SB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));             \
       occ_smem = smem;                                                                                     \
       if (occ < 1) occ = 1;                                                                                \
     }                                                                                                      \
-    const int resident = num_sms() * occ;                                                                  \
+    /* option gemv_occupancy: cap the CTAs per SM so that the next kernel of a programmatic-launch chain */   \
+    /* finds room to become resident (and prefetch its first weight batch) while this one is streaming */    \
+    const int occ_cap = get_option("gemv_occupancy");                                                      \
+    const int resident = num_sms() * ((occ_cap > 0 && occ_cap < occ) ? occ_cap : occ);                     \
     /* K can be split over 2 or 4 warps per row pair (option gemv_ksplit); measured on the 13B decode step it  */ \
     /* loses (5.19 ms/token unsplit, 5.44 / 5.62 with 2 / 4 slices), so the default stays one warp per pair */ \
     int ksplit = 1;                                                                                        \
     if (force_split == 1 || force_split == 2 || force_split == 4) ksplit = force_split;                    \
-    const int tpi = 8 / ksplit;                                                                            \
+    const int tpi = (threads / 32) / ksplit;                                                               \
     int blocks = (n_tasks + tpi - 1) / tpi;                                                                \
     if (blocks > resident) blocks = resident;                                                              \
     const int iters = (n_tasks + blocks * tpi - 1) / (blocks * tpi);                                       \
@@ -263,15 +273,19 @@ int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* resid
     int pf_lines = get_option("gemv_prefetch_mb") > 0                                                       \
                        ? (int)(((long long)get_option("gemv_prefetch_mb") << 20) / (2LL * n_tasks * 128)) : 0; \
     if (pf_lines > (K * 2 / ksplit) / 128) pf_lines = (K * 2 / ksplit) / 128;                               \
-    SB_CHECK_CUDA(launch_chain(kern, dim3(blocks), dim3(256), smem, stream, xp, wp, (long long)ldw, op, rp, np, eps, N, K, \
+    SB_CHECK_CUDA(launch_chain(kern, dim3(blocks), dim3(threads), smem, stream, xp, wp, (long long)ldw, op, rp, np, eps, N, K, \
                                ksplit, iters, (long long)ldo, pf_lines));                                  \
     SB_LAUNCH_CHECK();                                                                                     \
     return 0;                                                                                              \
   }
 #define SB_GEMV(M_, MD_)                                                                                   \
   if (M == M_ && mode == MD_) {                                                                            \
-    if (norm_w != nullptr) SB_GEMV_LAUNCH(M_, MD_, true)                                                   \
-    SB_GEMV_LAUNCH(M_, MD_, false)                                                                         \
+    if (deep) {                                                                                            \
+      if (norm_w != nullptr) SB_GEMV_LAUNCH(M_, MD_, true, 8)                                              \
+      SB_GEMV_LAUNCH(M_, MD_, false, 8)                                                                    \
+    }                                                                                                      \
+    if (norm_w != nullptr) SB_GEMV_LAUNCH(M_, MD_, true, 4)                                                \
+    SB_GEMV_LAUNCH(M_, MD_, false, 4)                                                                      \
   }
   SB_GEMV(1, 0) SB_GEMV(2, 0) SB_GEMV(3, 0) SB_GEMV(4, 0)
   SB_GEMV(1, 1) SB_GEMV(2, 1) SB_GEMV(3, 1) SB_GEMV(4, 1)
@@ -440,6 +454,193 @@ decode_attn_merge(const float* __restrict__ ws, __half* __restrict__ out, int ns
     acc += src[s * (DA_D + 2) + 2 + d] * c;
   }
   out[bh * DA_D + d] = __float2half_rn(ll > 0.0f ? acc / ll : 0.0f);
+}
+
+// ----------------------------------------------------------------------------
+// Fused decode attention: apply_rotary_pos_emb on the new token's q / k (llama_xformer.py:152-161), the KV-cache append
+// (:234-239) and the attention of that one query against the cache (:240-256) in ONE launch per layer: CTA (h, b) of
+// ng x 128 threads.  Thread group g walks the 128-key blocks g, g + ng, ... exactly like decode_attn_partial walks a
+// split (same arithmetic per block, so for caches of <= ng*128 keys the result is bit-identical to
+// rope_kv_kernel -> decode_attn_partial -> merge); the groups' (m, l, o) meet in shared memory instead of a global
+// workspace + ticket.  The new key / value never make a round trip through HBM: the group that owns cache row
+// `past_len` takes them from shared memory (they are also written to the caches for the following steps).
+// Used for max_seq <= 2048 (the decode step is latency-bound there: 2 launches, a global partial buffer and an atomic
+// ticket per layer become 1 launch); longer caches keep the split-KV kernels, which spread a head over more SMs.
+// ----------------------------------------------------------------------------
+constexpr int DAF_MAX_GROUPS = 4;
+
+__global__ void __launch_bounds__(DAF_MAX_GROUPS * 128)
+decode_attn_rope_kernel(const __half* __restrict__ qkv, const long long* __restrict__ positions,
+                        const __half* __restrict__ cos_t, const __half* __restrict__ sin_t, int max_pos,
+                        __half* __restrict__ kc, __half* __restrict__ vc, int H, int past_len, int max_seq,
+                        float scale_log2, const int* __restrict__ dyn, __half* __restrict__ out) {
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, grp = tid >> 7, gt = tid & 127, ng = blockDim.x >> 7;
+  const int warp = gt >> 5, lane = tid & 31;
+  __shared__ __align__(16) float s_q[DA_D];
+  __shared__ __align__(16) __half s_kn[DA_D];
+  __shared__ __align__(16) __half s_vn[DA_D];
+  __shared__ float s_p[DAF_MAX_GROUPS][DA_BLK];
+  __shared__ float s_red[DAF_MAX_GROUPS][2][4];
+  __shared__ __align__(16) float s_o[DAF_MAX_GROUPS][8][DA_D];
+  __shared__ float s_ml[DAF_MAX_GROUPS][2];
+  __shared__ float s_part[DAF_MAX_GROUPS][DA_D];
+  pdl_trigger();
+  pdl_wait();
+  if (dyn != nullptr) past_len = dyn[0];      // graph-replayed decode step: the cache length lives in device memory
+  int crow = past_len;
+  if (crow >= max_seq) crow = max_seq - 1;    // only reachable through dyn (host-checked otherwise)
+  const int kv_len = crow + 1;
+  const long long HD = (long long)H * DA_D;
+  const __half* row = qkv + (long long)b * 3 * HD + (long long)h * DA_D;
+  const long long base = ((long long)b * H + h) * max_seq * DA_D;
+  const long long cache_row = base + (long long)crow * DA_D;
+  for (int i = tid; i < 2 * DA_D; i += blockDim.x) {
+    if (i < DA_D) {
+      // q (i < 64) and k (i >= 64): dims (j, j + 64) of the rotate-half pair, every op rounded to fp16 like rope_kv_kernel
+      const int which = i >> 6, j = i & 63;
+      long long pos = positions ? positions[b] : (long long)past_len;
+      if (pos < 0) pos = 0;
+      if (pos >= max_pos) pos = max_pos - 1;
+      const float c = __half2float(cos_t[pos * (DA_D / 2) + j]), sn = __half2float(sin_t[pos * (DA_D / 2) + j]);
+      const float xl = __half2float(row[which * HD + j]), xh = __half2float(row[which * HD + DA_D / 2 + j]);
+      const float a_lo = __half2float(__float2half_rn(xl * c));
+      const float b_lo = __half2float(__float2half_rn(-xh * sn));
+      const float a_hi = __half2float(__float2half_rn(xh * c));
+      const float b_hi = __half2float(__float2half_rn(xl * sn));
+      const __half olo = __float2half_rn(a_lo + b_lo), ohi = __float2half_rn(a_hi + b_hi);
+      if (which == 0) {
+        s_q[j] = __half2float(olo); s_q[j + DA_D / 2] = __half2float(ohi);
+      } else {
+        s_kn[j] = olo; s_kn[j + DA_D / 2] = ohi;
+        kc[cache_row + j] = olo; kc[cache_row + DA_D / 2 + j] = ohi;
+      }
+    } else {
+      const int j = i - DA_D;
+      const __half v = row[2 * HD + j];
+      s_vn[j] = v;
+      vc[cache_row + j] = v;
+    }
+  }
+  __syncthreads();
+  const int g = gt >> 4, c = gt & 15;              // P.V role inside the group: key group (8 groups), 8-dim chunk
+  const int bar_id = 1 + grp;                       // the groups run different trip counts: one named barrier each
+  float m_run = -INFINITY, l_run = 0.0f, o_run = 0.0f;     // o_run: dim `gt`
+  for (int kb = grp * DA_BLK; kb < kv_len; kb += ng * DA_BLK) {
+    const int cnt = min(DA_BLK, kv_len - kb);
+    uint4 vv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int t = g + 8 * i;
+      if (t >= cnt) vv[i] = make_uint4(0, 0, 0, 0);
+      else if (kb + t == crow) vv[i] = *(reinterpret_cast<const uint4*>(s_vn) + c);
+      else vv[i] = __ldg(reinterpret_cast<const uint4*>(vc + base + (long long)(kb + t) * DA_D) + c);
+    }
+    float s = -INFINITY;
+    if (gt < cnt) {
+      const bool fresh = (kb + gt == crow);
+      const uint4* kr = fresh ? reinterpret_cast<const uint4*>(s_kn)
+                              : reinterpret_cast<const uint4*>(kc + base + (long long)(kb + gt) * DA_D);
+      uint4 kk[16];
+      if (fresh) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) kk[i] = kr[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) kk[i] = __ldg(kr + i);
+      }
+      float acc = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 qa = *reinterpret_cast<const float4*>(s_q + i * 8);
+        const float4 qb = *reinterpret_cast<const float4*>(s_q + i * 8 + 4);
+        const __half2* kh = reinterpret_cast<const __half2*>(&kk[i]);
+        const float2 f0 = __half22float2(kh[0]), f1 = __half22float2(kh[1]);
+        const float2 f2 = __half22float2(kh[2]), f3 = __half22float2(kh[3]);
+        acc = fmaf(qa.x, f0.x, acc); acc = fmaf(qa.y, f0.y, acc); acc = fmaf(qa.z, f1.x, acc); acc = fmaf(qa.w, f1.y, acc);
+        acc = fmaf(qb.x, f2.x, acc); acc = fmaf(qb.y, f2.y, acc); acc = fmaf(qb.z, f3.x, acc); acc = fmaf(qb.w, f3.y, acc);
+      }
+      s = acc * scale_log2;
+    }
+    const float wm = warp_max(s);
+    if (lane == 0) s_red[grp][0][warp] = wm;
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+    const float bm = fmaxf(fmaxf(s_red[grp][0][0], s_red[grp][0][1]), fmaxf(s_red[grp][0][2], s_red[grp][0][3]));
+    const float m_new = fmaxf(m_run, bm);
+    const float corr = exp2f(m_run - m_new);
+    const float p = exp2f(s - m_new);
+    s_p[grp][gt] = p;
+    const float ws_ = warp_sum(p);
+    if (lane == 0) s_red[grp][1][warp] = ws_;
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+    l_run = l_run * corr + (s_red[grp][1][0] + s_red[grp][1][1] + s_red[grp][1][2] + s_red[grp][1][3]);
+    m_run = m_new;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float pk = s_p[grp][g + 8 * i];
+      const __half2* vh = reinterpret_cast<const __half2*>(&vv[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(vh[j]);
+        acc[2 * j] = fmaf(pk, f.x, acc[2 * j]);
+        acc[2 * j + 1] = fmaf(pk, f.y, acc[2 * j + 1]);
+      }
+    }
+    *reinterpret_cast<float4*>(&s_o[grp][g][c * 8]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(&s_o[grp][g][c * 8 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+    float od = 0.0f;
+#pragma unroll
+    for (int gg = 0; gg < 8; ++gg) od += s_o[grp][gg][gt];
+    o_run = o_run * corr + od;
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // s_p / s_o / s_red are rewritten by the next block
+  }
+  if (gt == 0) { s_ml[grp][0] = m_run; s_ml[grp][1] = l_run; }
+  s_part[grp][gt] = o_run;
+  __syncthreads();
+  if (grp != 0) return;
+  // merge the groups in index order: the arithmetic of decode_attn_merge over the non-empty "splits"
+  const int nsplit = min(ng, (kv_len + DA_BLK - 1) / DA_BLK);
+  float mm = -INFINITY;
+  for (int sidx = 0; sidx < nsplit; ++sidx) mm = fmaxf(mm, s_ml[sidx][0]);
+  const float mu = (mm == -INFINITY) ? 0.0f : mm;
+  float ll = 0.0f, acc = 0.0f;
+  for (int sidx = 0; sidx < nsplit; ++sidx) {
+    const float cc = exp2f(s_ml[sidx][0] - mu);
+    ll += s_ml[sidx][1] * cc;
+    acc += s_part[sidx][gt] * cc;
+  }
+  out[((long long)b * H + h) * DA_D + gt] = __float2half_rn(ll > 0.0f ? acc / ll : 0.0f);
+}
+
+bool decode_attention_rope_supported(int D, int max_seq) {
+  return D == DA_D && max_seq >= 1 && (max_seq + DA_BLK - 1) / DA_BLK <= 4 * DAF_MAX_GROUPS;
+}
+
+// qkv [B, 3*H*D] (one new token per sequence: q | k | v), positions [B] or NULL (= past_len); appends K (post-RoPE) and
+// V at cache row past_len (dyn: dyn[0]) of caches [B,H,max_seq,D] and writes the attention output out [B, H*D].
+// The thread-group count depends on max_seq only, so eager launches and the captured decode step run the same code.
+int decode_attention_rope(const void* qkv, const int64_t* positions, int B, int H, int D, int past_len, int max_seq,
+                          int max_pos, const void* cos_t, const void* sin_t, void* k_cache, void* v_cache, void* out,
+                          float scale, cudaStream_t stream, const int* dyn) {
+  SB_REQUIRE(qkv && k_cache && v_cache && out && cos_t && sin_t, "decode_attention_rope: null operand");
+  SB_REQUIRE(decode_attention_rope_supported(D, max_seq),
+             "decode_attention_rope: head_dim %d / max_seq %d unsupported (head_dim 128, max_seq <= %d)", D, max_seq,
+             4 * DAF_MAX_GROUPS * DA_BLK);
+  SB_REQUIRE(dyn != nullptr || (past_len >= 0 && past_len < max_seq), "decode_attention_rope: past_len %d outside [0,%d)",
+             past_len, max_seq);
+  int ng = (max_seq + DA_BLK - 1) / DA_BLK;
+  if (ng > DAF_MAX_GROUPS) ng = DAF_MAX_GROUPS;
+  SB_CHECK_CUDA(launch_chain(decode_attn_rope_kernel, dim3(H, B), dim3(ng * 128), 0, stream,
+                             static_cast<const __half*>(qkv), reinterpret_cast<const long long*>(positions),
+                             static_cast<const __half*>(cos_t), static_cast<const __half*>(sin_t), max_pos,
+                             static_cast<__half*>(k_cache), static_cast<__half*>(v_cache), H, past_len, max_seq,
+                             scale * 1.4426950408889634f, dyn, static_cast<__half*>(out)));
+  SB_LAUNCH_CHECK();
+  return 0;
 }
 
 int decode_attention_max_splits(int max_seq) {

@@ -42,6 +42,11 @@ int decode_attention(const void* q, const void* k_cache, const void* v_cache, vo
                      int kv_len, int max_seq, float scale, void* workspace, cudaStream_t stream,
                      const int* dyn = nullptr, int* tickets = nullptr);
 int decode_attention_max_splits(int max_seq);
+// RoPE of the new token's q / k + KV append + attention in one launch (max_seq <= 2048); dyn as above (past_len = dyn[0])
+bool decode_attention_rope_supported(int D, int max_seq);
+int decode_attention_rope(const void* qkv, const int64_t* positions, int B, int H, int D, int past_len, int max_seq,
+                          int max_pos, const void* cos_t, const void* sin_t, void* k_cache, void* v_cache, void* out,
+                          float scale, cudaStream_t stream, const int* dyn = nullptr);
 // sampler.cu
 struct GenParams { seedb200_sample_params sp; long long eos, pad; };
 // gp (host, by value) or gp_dev (device, read at run time); state (device, optional) = {cache length, step, arrive,

@@ -34,7 +34,7 @@ EXPORTS = [
     "seedb200_sample", "seedb200_philox_uniform", "seedb200_image_ids_to_tokens", "seedb200_encoder_encode_tokens",
     "seedb200_llama_forward_ld", "seedb200_llama_generate", "seedb200_llama_generate_used_graph",
     "seedb200_row_stats", "seedb200_row_stats_from_moments", "seedb200_ln_fold_weights",
-    "seedb200_gemm_plan", "seedb200_gemm_schedule_tile",
+    "seedb200_gemm_plan", "seedb200_gemm_schedule_tile", "seedb200_decode_attention_rope",
 ]
 
 
@@ -469,6 +469,26 @@ def decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tens
         check(load().seedb200_decode_attention(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(),
                                                B, H, D, kv_len, max_seq, scale, ws.data_ptr(), stream_ptr(q.device)),
               "seedb200_decode_attention")
+    return out
+
+
+def decode_attention_rope(qkv: torch.Tensor, positions: Optional[torch.Tensor], H: int, past_len: int,
+                          k_cache: torch.Tensor, v_cache: torch.Tensor, scale: float) -> torch.Tensor:
+    """RoPE + KV append + attention of one new token per sequence: qkv [B, 3*H*D] -> [B, H*D] (caches updated)."""
+    _need_cuda_f16(qkv, "decode_attention_rope.qkv")
+    B = qkv.shape[0]
+    D = qkv.shape[1] // (3 * H)
+    max_seq = k_cache.shape[2]
+    if not (k_cache.is_contiguous() and v_cache.is_contiguous() and qkv.is_contiguous()):
+        raise RuntimeError("decode_attention_rope: qkv and the caches must be contiguous")
+    out = torch.empty((B, H * D), dtype=torch.float16, device=qkv.device)
+    lib = load()
+    lib.seedb200_decode_attention_rope.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    with on(qkv.device):
+        check(lib.seedb200_decode_attention_rope(qkv.data_ptr(), _p(positions), B, H, D, past_len, max_seq,
+                                                 k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(), scale,
+                                                 stream_ptr(qkv.device)), "seedb200_decode_attention_rope")
     return out
 
 

@@ -512,6 +512,45 @@ def test_decode_attention_cache_lengths(lib, B, H, kv_len, max_seq):
     assert_close16(out.view(B, H, D), ref.view(B, H, D), ulps=2.0, atol=2e-4, what=f"decode attention kv={kv_len}")
 
 
+@pytest.mark.parametrize("B,H,past,max_seq,use_pos", [(1, 40, 256, 392, False), (1, 40, 299, 392, True), (2, 8, 0, 64, False),
+                                                      (1, 4, 127, 128, False), (1, 4, 128, 512, True), (3, 5, 511, 512, False),
+                                                      (1, 8, 1500, 2048, False), (2, 4, 600, 1100, True)])
+def test_decode_attention_rope_fused_matches_the_two_kernel_form(lib, B, H, past, max_seq, use_pos):
+    """RoPE + KV append + attention in one launch (the cached decode step) vs rope_kv_append -> decode_attention on the
+    same inputs: caches identical, output bit-identical while one 128-key block per thread group covers the cache
+    (<= 512 keys), within 2 fp16 ulps beyond; both against the fp32 oracle (llama_xformer.py:152-161,234-256)."""
+    D = 128
+    qkv = rand16(B, 3 * H * D, seed=61)
+    kc = rand16(B, H, max_seq, D, seed=62)
+    vc = rand16(B, H, max_seq, D, seed=63)
+    kc[:, :, past:] = 0
+    vc[:, :, past:] = 0
+    kc2, vc2 = kc.clone(), vc.clone()
+    pos = torch.full((B, 1), past, dtype=torch.int64, device=DEV)
+    if use_pos:
+        pos = pos - torch.arange(B, device=DEV)[:, None].clamp(max=past)       # left-padded rows: position < cache row
+    scale = D ** -0.5
+    q_rot = lib.rope_kv_append(qkv, pos, B, 1, H, D, past, kc, vc)
+    ref2 = lib.decode_attention(q_rot.view(B, H, D), kc, vc, past + 1, scale)
+    out = lib.decode_attention_rope(qkv, pos if use_pos else None, H, past, kc2, vc2, scale)
+    torch.cuda.synchronize()
+    assert torch.equal(kc, kc2) and torch.equal(vc, vc2)
+    if past + 1 <= 512:
+        assert torch.equal(out, ref2)
+    assert_close16(out, ref2, ulps=2.0, atol=2e-4, what="fused vs two-kernel decode attention")
+    v5 = qkv.view(B, 1, 3, H, D)
+    q = R.rope_ref(v5[:, :, 0].permute(0, 2, 1, 3), pos)
+    ref = R.attention_ref(q, kc[:, :, :past + 1], vc[:, :, :past + 1], scale)
+    assert_close16(out.view(B, H, D), ref.view(B, H, D), ulps=3.0, atol=4e-4, what="fused decode attention")
+
+
+def test_decode_attention_rope_rejects_long_caches(lib):
+    qkv = rand16(1, 3 * 2 * 128, seed=64)
+    kc = torch.zeros((1, 2, 2049, 128), dtype=torch.float16, device=DEV)
+    with pytest.raises(RuntimeError, match="max_seq"):
+        lib.decode_attention_rope(qkv, None, 2, 5, kc, kc.clone(), 0.1)
+
+
 # ----------------------------------------------------------------------------------------------
 # token side of the generation loop: sampler and id -> token arithmetic
 # ----------------------------------------------------------------------------------------------
