@@ -69,8 +69,9 @@ void seedb200_reset_launch_count(void);
  * "gemm_tail": 1 (default) = a ragged last column of tiles runs at its own width, 0 = as a full tile.
  * "decode_fused_attention": 1 (default) = the cached decode step runs RoPE + KV append + attention as one kernel per
  * layer when max_seq <= 2048 (seedb200_decode_attention_rope), 0 = rope_kv_append + split-KV decode attention.
- * "gemm_sched": 1 (default) = GEMMs with few tiles per SM (LLaMA prefill) pick tile width / pairing / schedule from
- * a load-balance model (seedb200_gemm_plan), 0 = the fixed heuristics, 2 = balanced-tail order with an explicit bn.
+ * "gemm_sched": 1 (default) = a GEMM with a single row of tiles (M <= 256: a short LLaMA prompt) picks its tile width
+ * from a busy-SM model (seedb200_gemm_plan), 0 = the fixed heuristics, 2 = balanced-tail tile order with an explicit
+ * bn (A/B runs: measured equal to the rotated round robin, tools/llama_gemm_ab.py).
  * "encoder_ln_fold" (read by seedb200_encoder_create): 1 (default) = norm1 / norm2 of the ViT blocks are folded
  * into the qkv / fc1 GEMMs (seedb200_gemm_desc.ln_stats), 0 = standalone LayerNorm kernels.                    */
 int seedb200_set_option(const char* key, int value);
@@ -137,8 +138,8 @@ int seedb200_gemm(const seedb200_gemm_desc* d, void* stream);
  * tile is handed out exactly once).  gemm_plan: what seedb200_gemm would pick for `d` on a device with `sms` SMs --
  * out9 = {bn, ctas, sched, ksub, m_tiles, n_tiles, units, tile_shift, tail_w}; pointers in `d` are not dereferenced.
  * gemm_schedule_tile: the tile (mt * n_tiles + nt) of unit `unit`'s round-th iteration, m_tiles * n_tiles when the
- * unit is done.  sched 0 = rotated round robin, 1 = balanced tail (full-width tiles round robin, then the units that
- * got one fewer take the narrow last-column tiles: the M = 2048 LLaMA prefill shapes, llama_xformer.py:223-225,258). */
+ * unit is done.  sched 0 = rotated round robin (default), 1 = balanced tail (full-width tiles round robin, then the
+ * units that got one fewer take the last-column tiles; option "gemm_sched" = 2).                                    */
 int seedb200_gemm_plan(const seedb200_gemm_desc* d, int sms, int32_t* out9);
 int seedb200_gemm_schedule_tile(int sched, int round, int unit, int units, int m_tiles, int n_tiles, int tile_shift);
 

@@ -954,21 +954,25 @@ static int plan_max_cols(int M, int N, int bn, int ctas, int sched, int sms) {
   return worst;
 }
 
-// Few tiles per unit (LLaMA prefill: M = 2048 or a 256-token prompt): pick the tile width / pairing / schedule whose
-// busiest unit finishes first.  Rough per-shape efficiencies of the narrower tiles (tools/llama_gemm_ab.py) break ties.
-static void plan_small_problem(const seedb200_gemm_desc& d, int sms, int& bn, int& ctas, int& sched) {
-  struct Cand { int bn, ctas; double eff; };
-  static const Cand cands[] = {{256, 2, 1.00}, {224, 2, 0.985}, {192, 2, 0.97}, {128, 2, 0.90}, {64, 2, 0.72},
-                               {256, 1, 0.93}, {192, 1, 0.90},  {128, 1, 0.84}, {64, 1, 0.65}};
+// One row of tiles (M <= 256 on a CTA pair: the 256-token prompt of config #5 on the 13B shapes): with 256-wide tiles
+// N = 5120 keeps 20 CTA pairs busy; 128-wide tiles double that and won on the GPU (tools/llama_gemm_ab.py, r02:
+// o_proj 0.048 -> 0.042 ms, down_proj 0.087 -> 0.070 ms), while N = 15360 (60 pairs busy) stays on 256.
+// Narrower tiles for the M = 2048 prefill shapes (128 tiles of 256 x 256 on 74 pairs = two rounds, the second 27 %
+// empty) were measured and lost: a 224-wide tile costs the tensor core as much as a 256-wide one, 192 / 128-wide
+// tiles lose more per tile than the better balance returns (profiles/r02_summary.md).
+static void plan_single_row(const seedb200_gemm_desc& d, int sms, int& bn, int& ctas, int& sched) {
+  struct Cand { int bn; double eff; };
+  static const Cand cands[] = {{256, 1.00}, {128, 0.80}};
   double best = 1e30;
   for (const Cand& c : cands) {
-    if (c.ctas > ctas) continue;                       // the caller asked for single CTAs
-    if (c.ctas == 2 && d.M <= GEMM_BLOCK_M) continue;
-    for (int sc = 0; sc < 2; ++sc) {
-      const double cost = plan_max_cols(d.M, d.N, c.bn, c.ctas, sc, sms) / c.eff * (sc == 1 ? 1.0 : 1.0005);
-      if (cost < best) { best = cost; bn = c.bn; ctas = c.ctas; sched = sc; }
-    }
+    const double cost = plan_max_cols(d.M, d.N, c.bn, ctas, 0, sms) / c.eff;
+    // busy units matter as much as the busiest one's columns: the shapes are half HBM-bound (every W byte once)
+    const int tiles = (d.N + c.bn - 1) / c.bn, units = sms / ctas;
+    const double busy = tiles >= units ? 1.0 : (double)tiles / units;
+    const double score = cost / (0.5 + 0.5 * busy);
+    if (score < best) { best = score; bn = c.bn; }
   }
+  sched = 0;
 }
 
 struct GemmPlan { int bn, ctas, sched, ksub; };
@@ -994,8 +998,7 @@ static int choose_plan(const seedb200_gemm_desc& d, int sms, GemmPlan& plan) {
   int sched = 0;
   if (d.bn == 0 && d.mode == 0 && d.N >= 1024 && get_option("gemm_sched") != 0 && d.ln_stats == nullptr &&
       d.row_moments == nullptr && d.row_group == 0 && d.res_mod == 0 && get_option("gemm_tail") != 0) {
-    const long long tiles256 = (long long)((d.M + GEMM_BLOCK_M * ctas - 1) / (GEMM_BLOCK_M * ctas)) * ((d.N + 255) / 256);
-    if (tiles256 < 8LL * (sms / ctas)) plan_small_problem(d, sms, bn, ctas, sched);
+    if (d.M <= GEMM_BLOCK_M * ctas && d.N % 128 == 0) plan_single_row(d, sms, bn, ctas, sched);
   } else if (d.bn != 0 && get_option("gemm_sched") == 2) {
     sched = 1;                                           // A/B runs with an explicit tile width
   }
@@ -1021,7 +1024,6 @@ int gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
     return launch_gemm<BN_, CT_, MD_, 1>(d, stream, sched);                           \
   }
   SB_GEMM_CASE(256, 1, 0) SB_GEMM_CASE(256, 2, 0)
-  SB_GEMM_CASE(224, 2, 0)
   SB_GEMM_CASE(192, 1, 0) SB_GEMM_CASE(192, 2, 0)
   SB_GEMM_CASE(176, 1, 0) SB_GEMM_CASE(176, 2, 0)
   SB_GEMM_CASE(128, 1, 0) SB_GEMM_CASE(128, 2, 0)

@@ -91,10 +91,9 @@ def test_gemm_plain(lib, M, N, K, bn, ctas):
     assert_close16(out, ref, what="gemm")
 
 
-# few tiles per CTA pair (LLaMA prefill, M = 2048 or a 256-token prompt): the load-balance model picks the tiling
-# (224-wide tiles + tail, balanced-tail order); K kept short so the fp32 oracle stays cheap
-PLANNED_SHAPES = [(2048, 4096, 320), (2048, 12288, 128), (256, 5120, 320), (256, 15360, 128), (2048, 5120, 192),
-                  (1000, 3072, 768), (2048, 4098, 64)]
+# one row of tiles (a 256-token prompt on the 13B shapes): the plan picks 128-wide tiles when 256-wide ones leave most
+# CTA pairs idle; the M = 2048 shapes keep the 256-wide tiling.  K kept short so the fp32 oracle stays cheap
+PLANNED_SHAPES = [(256, 5120, 320), (256, 15360, 128), (200, 5120, 192), (2048, 4096, 320), (2048, 5120, 192)]
 
 
 @pytest.mark.parametrize("residual", [False, True])
@@ -117,7 +116,7 @@ def test_gemm_planned_tilings(lib, M, N, K, residual):
     assert torch.equal(out, out0)
 
 
-@pytest.mark.parametrize("bn", [224, 192, 256, 128])
+@pytest.mark.parametrize("bn", [192, 256, 128])
 def test_gemm_balanced_tail_order_with_explicit_width(lib, bn):
     M, N, K = 2048, 4096, 256
     a = rand16(M, K, seed=24)
