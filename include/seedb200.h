@@ -63,6 +63,8 @@ void seedb200_reset_launch_count(void);
  * mma.sync kernel (attention.cu).
  * "causal_attention_tc": 1 (default) routes causal head_dim-128 attention with nq >= 128 (LLaMA prefill) to the
  * tcgen05 kernel (attention_causal_tc.cu), 0 to the mma.sync kernel.
+ * "causal_attention_tma": 1 (default) = that kernel's Q / K / V tiles arrive by TMA when the layouts fit a 4-D tensor
+ * map (the LLaMA projection buffer and KV caches do), 0 = cp.async loader warps.
  * "decode_pdl": 1 (default) launches the kernels of the cached decode step (q_len 1) with programmatic stream
  * serialization (each starts while its predecessor drains and waits on griddepcontrol before reading activations).
  * "gemm_ksub": 0 (default) = heuristic, 1 = 64-deep GEMM pipeline stages, 2 = 128-deep.

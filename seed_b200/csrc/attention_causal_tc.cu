@@ -7,7 +7,8 @@
 // One persistent CTA per SM walks work items = (batch, head, pair of 128-row query tiles), longest items first
 // and dealt to the CTAs in snake order so that the causal triangle balances.  Roles (416 threads):
 //   warps 0-3 / 4-7   softmax + correction + epilogue of query tile 0 / 1 (one query row per thread)
-//   warps 8-11        cp.async loaders (Q once per item, then K and V tiles of 128 keys, double buffered)
+//   warps 8-11        loaders (Q once per item, then K and V tiles of 128 keys, double buffered): one TMA issuing
+//                     thread per operand when the layout allows it (below), else four cp.async warps
 //   warp 12           tcgen05.mma issuer: S_u = Q_u K_j^T (SS form), O_u += P_u V_j (TS form: P stays in TMEM)
 // TMEM (512 columns): per tile u  S [256u, 256u+128) fp32, P aliased in place (fp16 x2 / column, 64 columns),
 // O [256u+128, 256u+256) fp32.  The two tiles ping-pong: while the softmax warps of one tile work, the tensor
@@ -18,6 +19,14 @@
 // Operands sit in shared memory in the canonical non-swizzled UMMA layout (8 x 16-byte core matrices):
 //   byte(r, c) = (r / 8) * 2048 + (c / 8) * 128 + (r % 8) * 16 + (c % 8) * 2        (r = token, c = head dim)
 // read K-major for Q and K (LBO 128, SBO 2048) and MN-major for V (SBO 128, LBO 2048), so V needs no transpose.
+//
+// TMA writes that image directly: a 4-D tensor map (8 elements = one 16-byte chunk | token rows | 16 chunks of a head |
+// heads / batches) whose 8 x 8 x 16 x 1 box IS one 8-row group (2 KB); a 128-row tile is 16 such boxes on one
+// mbarrier, rows past the end of the sequence are zero-filled by the out-of-bounds rule.  The cp.async loaders (2048
+// 16-byte copies per tile, ~78 cycles of the SM's load/store unit per 512-byte warp instruction = ~10 k cycles per
+// K + V block against ~2 k cycles of MMAs) were what bounded the kernel.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -36,6 +45,9 @@ struct CausalAttnParams {
   long long q_bs, q_hs, q_ts, k_bs, k_hs, k_ts, v_bs, v_hs, v_ts, o_bs, o_hs, o_ts;
   int batch_heads, heads, nq, nk, past, pairs, items;
   float scale_log2;
+  int use_tma;               // 1: Q / K / V tiles by TMA (tensor maps passed beside this struct)
+  int q_span, k_span, v_span;   // tensor-map form per operand: 1 = chunks span the heads (coords: chunk = h*16, outer = b),
+                                // 0 = heads in the outer dimension (coords: chunk = 0, outer = b*heads + h)
 };
 
 struct CaItem { int b, h, pair, n0, n1; };
@@ -121,7 +133,8 @@ __device__ __forceinline__ uint32_t ca_pack2(float a, float b, float& sum) {
 }
 
 __global__ void __launch_bounds__(CA_THREADS, 1)
-causal_attention_tc_kernel(const CausalAttnParams p) {
+causal_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                           const __grid_constant__ CUtensorMap tm_v, const CausalAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -139,9 +152,10 @@ causal_attention_tc_kernel(const CausalAttnParams p) {
   if (tid == 0) {
     for (int u = 0; u < 2; ++u) {
       mbar_init(bar_s + 8 * u, 1); mbar_init(bar_p + 8 * u, 4); mbar_init(bar_o + 8 * u, 1);
-      mbar_init(q_full + 8 * u, 2); mbar_init(q_empty + 8 * u, 1);
-      mbar_init(k_full + 8 * u, 2); mbar_init(k_empty + 8 * u, 1);
-      mbar_init(v_full + 8 * u, 2); mbar_init(v_empty + 8 * u, 1);
+      const uint32_t producers = p.use_tma ? 1u : 2u;     // one expect-tx arrive, or one arrive per cp.async warp
+      mbar_init(q_full + 8 * u, producers); mbar_init(q_empty + 8 * u, 1);
+      mbar_init(k_full + 8 * u, producers); mbar_init(k_empty + 8 * u, 1);
+      mbar_init(v_full + 8 * u, producers); mbar_init(v_empty + 8 * u, 1);
     }
     fence_mbar_init();
   }
@@ -154,8 +168,43 @@ causal_attention_tc_kernel(const CausalAttnParams p) {
   constexpr uint32_t IDESC_S = make_idesc_f16(128, 128);
   constexpr uint32_t IDESC_O = make_idesc_f16(128, 128) | (1u << 16);       // B (= V) is MN-major
 
-  if (warp >= 8 && warp < 12) {
-    // ======================= loaders =======================
+  if (warp >= 8 && warp < 12 && p.use_tma) {
+    // ======================= loaders (TMA) =======================
+    // warp 8: Q tile 0 then the K tiles; warp 10: Q tile 1 then the V tiles; one thread each
+    const int isv = (warp - 8) >> 1;
+    if (((warp - 8) & 1) == 0 && lane == 0) {
+      tma_prefetch_desc(&tm_q);
+      tma_prefetch_desc(isv ? &tm_v : &tm_k);
+      const CUtensorMap* tm = isv ? &tm_v : &tm_k;
+      const int span = isv ? p.v_span : p.k_span;
+      auto load_tile = [&](const CUtensorMap* map, int sp, const CaItem& it, int row0, uint32_t dst, uint32_t bar) {
+        const int c2 = sp ? it.h * (CA_D / 8) : 0, c3 = sp ? it.b : it.b * p.heads + it.h;
+        mbar_arrive_expect_tx(bar, CA_TILE_BYTES);
+#pragma unroll 4
+        for (int g = 0; g < CA_T / 8; ++g) tma_load_4d(dst + g * CA_G, map, bar, 0, row0 + 8 * g, c2, c3);
+      };
+      uint32_t kc = 0, qc = 0;
+      for (int round = 0;; ++round) {
+        const int i = ca_next(round, cta, G);
+        if (i >= p.items) break;
+        const CaItem it = ca_item(p, i);
+        const int nu = isv ? it.n1 : it.n0, nmax = max(it.n0, it.n1);
+        if (nu > 0) {
+          mbar_wait_relaxed(q_empty + 8 * isv, (qc & 1) ^ 1);
+          load_tile(&tm_q, p.q_span, it, it.pair * 2 * CA_T + isv * CA_T, sQ + isv * CA_TILE_BYTES, q_full + 8 * isv);
+          ++qc;
+        }
+        const uint32_t dst0 = isv ? sV : sK, full = isv ? v_full : k_full, empty = isv ? v_empty : k_empty;
+        for (int j = 0; j < nmax; ++j, ++kc) {
+          const uint32_t s = kc & 1;
+          mbar_wait_relaxed(empty + 8 * s, ((kc >> 1) & 1) ^ 1);
+          load_tile(tm, span, it, j * CA_T, dst0 + s * CA_TILE_BYTES, full + 8 * s);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 8 && warp < 12) {
+    // ======================= loaders (cp.async: layouts the tensor maps cannot describe) =======================
     // warps 8,9: Q tile 0 then the K tiles (rows 0..63 / 64..127 of each); warps 10,11: Q tile 1 then the V tiles.
     const int lw = warp - 8, half = lw & 1, isv = lw >> 1;
     const int r8 = lane & 7, cq = lane >> 3;
@@ -374,6 +423,52 @@ bool causal_attention_tc_applicable(const seedb200_attn_desc& d) {
          d.o_bs % 8 == 0 && (reinterpret_cast<uintptr_t>(d.o) & 15) == 0 && d.scale > 0.0f;
 }
 
+int get_option(const char* key);
+
+typedef CUresult (*EncodeTiledFnC)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 4-D map of one operand [batch][head][rows][128] with element strides (bs, hs, ts): (8 elements | rows | chunks | outer).
+// span = 1: the heads of a token are contiguous (hs == 128) -> the chunk dimension runs over all heads, outer = batch;
+// span = 0: batch and head merge into one outer dimension (bs == heads * hs, or a single batch).
+// Returns 1 when the layout fits (map written), 0 when it does not (caller keeps cp.async), < 0 on a driver error.
+static int make_causal_tmap(CUtensorMap* tm, int* span, const void* base, long long bs, long long hs, long long ts,
+                            int batch, int heads, int rows) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ts % 8 != 0 || hs % 8 != 0 || bs % 8 != 0 || ts < CA_D) return 0;
+  cuuint64_t gdim[4], gstr[3];
+  gdim[0] = 8; gdim[1] = (cuuint64_t)rows; gstr[0] = (cuuint64_t)ts * 2; gstr[1] = 16;
+  if (hs == CA_D && ts >= (long long)heads * CA_D) {
+    *span = 1;
+    gdim[2] = (cuuint64_t)heads * (CA_D / 8); gdim[3] = (cuuint64_t)batch; gstr[2] = (cuuint64_t)(batch > 1 ? bs : ts) * 2;
+  } else if (batch == 1 || bs == (long long)heads * hs) {
+    *span = 0;
+    gdim[2] = CA_D / 8; gdim[3] = (cuuint64_t)batch * heads; gstr[2] = (cuuint64_t)hs * 2;
+  } else {
+    return 0;
+  }
+  if (gstr[0] >= (1ull << 40) || gstr[2] >= (1ull << 40)) return 0;
+  static EncodeTiledFnC fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFnC>(ptr);
+  }
+  if (fn == nullptr) return 0;
+  cuuint32_t box[4] = {8, 8, CA_D / 8, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("causal_attention: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return -1;
+  }
+  return 1;
+}
+
 int causal_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream) {
   static bool attr_set_dev[SB_MAX_DEVICES] = {};   // cudaFuncSetAttribute is per device
   bool& attr_set = attr_set_dev[cur_device()];
@@ -392,10 +487,22 @@ int causal_attention_tc(const seedb200_attn_desc& d, cudaStream_t stream) {
   p.pairs = (d.nq + 2 * CA_T - 1) / (2 * CA_T);
   p.items = p.pairs * p.batch_heads;
   p.scale_log2 = d.scale * 1.4426950408889634f;
+  // TMA loaders when all three operands fit a 4-D tensor map (the LLaMA layouts do: q rows of the projection buffer,
+  // K / V rows of the [B,H,max_seq,128] caches); option causal_attention_tma = 0 keeps the cp.async warps
+  CUtensorMap tq, tk, tv;
+  memset(&tq, 0, sizeof(tq)); memset(&tk, 0, sizeof(tk)); memset(&tv, 0, sizeof(tv));
+  p.use_tma = 0; p.q_span = p.k_span = p.v_span = 0;
+  if (get_option("causal_attention_tma") != 0) {
+    const int rq = make_causal_tmap(&tq, &p.q_span, d.q, d.q_bs, d.q_hs, d.q_ts, d.batch, d.heads, d.nq);
+    const int rk = rq == 1 ? make_causal_tmap(&tk, &p.k_span, d.k, d.k_bs, d.k_hs, d.k_ts, d.batch, d.heads, d.nk) : 0;
+    const int rv = rk == 1 ? make_causal_tmap(&tv, &p.v_span, d.v, d.v_bs, d.v_hs, d.v_ts, d.batch, d.heads, d.nk) : 0;
+    if (rq < 0 || rk < 0 || rv < 0) return SEEDB200_ERR_CUDA;
+    p.use_tma = (rq == 1 && rk == 1 && rv == 1) ? 1 : 0;
+  }
   int grid = num_sms();
   if (grid > p.items) grid = p.items;
   profile_mark_begin(1, stream);
-  causal_attention_tc_kernel<<<grid, CA_THREADS, CA_SMEM, stream>>>(p);
+  causal_attention_tc_kernel<<<grid, CA_THREADS, CA_SMEM, stream>>>(tq, tk, tv, p);
   profile_mark_end(1, stream, 4.0 * (double)d.batch * d.heads * (double)d.nq * d.nk * d.head_dim * 0.5);
   SB_LAUNCH_CHECK();
   return 0;

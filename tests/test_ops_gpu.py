@@ -313,25 +313,48 @@ def test_vit_attention_variants_agree_on_large_scores(lib):
         assert rel_err(o, ref) < 3e-3, (use_tc, rel_err(o, ref))
 
 
-@pytest.mark.parametrize("use_tc", [1, 0])
-def test_causal_attention_tcgen05_vs_mma_paths(lib, use_tc):
+@pytest.mark.parametrize("B,S,past,max_seq", [(2, 700, 333, 1200), (1, 2048, 0, 2048), (3, 130, 7, 200)])
+@pytest.mark.parametrize("use_tc,use_tma", [(1, 1), (1, 0), (0, 0)])
+def test_causal_attention_tcgen05_vs_mma_paths(lib, use_tc, use_tma, B, S, past, max_seq):
     """LLaMA prefill layout (q from a fused projection buffer, K/V in a [B,H,max_seq,D] cache with a past) on the
-    tcgen05 kernel (attention_causal_tc.cu) and on the mma.sync kernel"""
-    B, H, S, D, past, max_seq = 2, 4, 700, 128, 333, 1200
+    tcgen05 kernel (attention_causal_tc.cu) with TMA and with cp.async loaders, and on the mma.sync kernel"""
+    H, D = 4, 128
     qbuf = rand16(B * S, H * D, seed=35)
     kc = rand16(B, H, max_seq, D, seed=36)
     vc = rand16(B, H, max_seq, D, seed=37)
     q = qbuf.view(B, S, H, D).permute(0, 2, 1, 3)
     k, v = kc[:, :, :past + S], vc[:, :, :past + S]
+    kc[:, :, past + S:] = float("nan")          # rows past the sequence must never reach the MMAs
+    vc[:, :, past + S:] = float("nan")
     lib.set_option("causal_attention_tc", use_tc)
+    lib.set_option("causal_attention_tma", use_tma)
     try:
         o = lib.attention(q, k, v, D ** -0.5, True)
         torch.cuda.synchronize()
     finally:
         lib.set_option("causal_attention_tc", 1)
+        lib.set_option("causal_attention_tma", 1)
     ref = R.attention_ref(q, k, v, D ** -0.5, True)
+    assert torch.isfinite(o.float()).all()
     assert rel_err(o, ref) < 2e-3, rel_err(o, ref)
     assert (o.float() - ref.float()).abs().max().item() < 1e-2
+
+
+def test_causal_attention_tma_and_cp_async_loaders_agree_bitwise(lib):
+    B, H, S, D = 2, 3, 515, 128
+    qbuf = rand16(B * S, H * D, seed=41)
+    kc = rand16(B, H, 600, D, seed=42)
+    vc = rand16(B, H, 600, D, seed=43)
+    q = qbuf.view(B, S, H, D).permute(0, 2, 1, 3)
+    outs = []
+    for tma in (1, 0):
+        lib.set_option("causal_attention_tma", tma)
+        try:
+            outs.append(lib.attention(q, kc[:, :, :S], vc[:, :, :S], D ** -0.5, True))
+            torch.cuda.synchronize()
+        finally:
+            lib.set_option("causal_attention_tma", 1)
+    assert torch.equal(outs[0], outs[1])
 
 
 def test_causal_attention_large_scores_rescale(lib):

@@ -1,4 +1,5 @@
-"""Time the LLaMA-7B prefill attention shape (B=1, H=32, S, D=128, causal) on both kernels."""
+"""Time the LLaMA-7B prefill attention shape (B=1, H=32, S, D=128, causal): tcgen05 kernel with TMA / cp.async loaders,
+mma.sync kernel."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -16,10 +17,17 @@ def timeit(fn, iters=10):
         s.record(); fn(); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
     return min(ts)
 outs = {}
-for tc in (1, 0):
+rows = []
+for tc, tma in ((1, 1), (1, 0), (0, 0)):
     L.set_option("causal_attention_tc", tc)
+    L.set_option("causal_attention_tma", tma)
     o = L.attention(q, k, v, D ** -0.5, True); torch.cuda.synchronize()
-    outs[tc] = o.float()
+    outs[(tc, tma)] = o.float()
     t = timeit(lambda: L.attention(q, k, v, D ** -0.5, True))
-    print(json.dumps({"tc": tc, "S": S, "ms": round(t, 4), "tflops_causal": round(2.0 * H * S * S * D * 2 / 2 / t / 1e9, 1)}), flush=True)
-print("rel diff tc vs mma:", ((outs[1] - outs[0]).norm() / outs[0].norm()).item())
+    rows.append({"tc": tc, "tma": tma, "S": S, "ms": round(t, 4), "tflops_causal": round(2.0 * H * S * S * D * 2 / 2 / t / 1e9, 1)})
+    print(json.dumps(rows[-1]), flush=True)
+L.set_option("causal_attention_tc", 1); L.set_option("causal_attention_tma", 1)
+print("rel diff tc vs mma:", ((outs[(1, 1)] - outs[(0, 0)]).norm() / outs[(0, 0)].norm()).item(),
+      "tma == cp.async:", bool(torch.equal(outs[(1, 1)], outs[(1, 0)])))
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(rows, open(f"gpurun_out/one_causal_{S}.json", "w"), indent=1)
