@@ -65,3 +65,24 @@ if "--ab" in sys.argv:
                 s.record(); fn(); e.record(); torch.cuda.synchronize(); t[key].append(s.elapsed_time(e))
         print(json.dumps({"shape": nm, "lnfold_ms": round(min(t["ln"]), 4), "bias_ms": round(min(t["bias"]), 4),
                           "lnfold_tflops": round(fl / min(t["ln"]) / 1e9, 1), "bias_tflops": round(fl / min(t["bias"]) / 1e9, 1)}))
+
+if "--ksub" in sys.argv:
+    # pipeline-stage depth per shape (option gemm_ksub: 0 = heuristic, 1 = 64-deep stages, 2 = 128-deep), interleaved
+    fns = [lambda: L.gemm(x, qkv_f[0], out=qkv, ctas=2, ln=(stats, qkv_f[1], qkv_f[2])),
+           lambda: L.gemm(att, w_proj, bias=b_proj, residual=x, out=x, ctas=2),
+           lambda: L.gemm(x, fc1_f[0], act=L.ACT_GELU, out=hid, ctas=2, ln=(stats, fc1_f[1], fc1_f[2])),
+           lambda: L.gemm(hid, w_fc2, bias=b_fc2, residual=x, out=x, ctas=2)]
+    rows = []
+    for nm, fl, fn in zip(names, flops, fns):
+        t = {0: [], 1: [], 2: []}
+        for _ in range(8):
+            for ks in (0, 1, 2):
+                L.set_option("gemm_ksub", ks)
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(); fn(); e.record(); torch.cuda.synchronize(); t[ks].append(s.elapsed_time(e))
+        L.set_option("gemm_ksub", 0)
+        rows.append({"shape": nm, **{f"ksub{ks}_ms": round(min(v), 4) for ks, v in t.items()},
+                     **{f"ksub{ks}_tflops": round(fl / min(v) / 1e9, 1) for ks, v in t.items()}})
+        print(json.dumps(rows[-1]), flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(rows, open("gpurun_out/vit_gemm_ksub.json", "w"), indent=1)
