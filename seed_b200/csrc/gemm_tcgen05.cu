@@ -1004,9 +1004,11 @@ static int choose_plan(const seedb200_gemm_desc& d, int sms, GemmPlan& plan) {
   }
 
   // 128-deep stages pay off for CTA pairs on long reductions or exactly tiled wide outputs (measured on B200:
-  // qkv/fc1/fc2 +5..10%); they lose on short-K ragged tilings (proj BN=256: -26%) and on single CTAs (-5%).
+  // qkv/fc1/fc2 +5..10%); they lose on single CTAs (-5%).
   // option gemm_ksub: 0 = this heuristic, 1 / 2 = force.
-  int ksub = (d.K > 64 && ctas == 2 && ((bn >= 192 && d.N % bn == 0) || d.K >= 4096)) ? 2 : 1;
+  // Re-measured after the staged epilogue (tools/vit_gemm_capture.py --ksub, r02): the ragged 256-wide tilings gain too
+  // (qkv 4224x1408: 0.607 -> 0.530 ms, proj 1408x1408: 0.226 -> 0.217 ms), so every wide CTA-pair tiling takes them.
+  int ksub = (d.K > 64 && ctas == 2 && (bn >= 192 || d.K >= 4096)) ? 2 : 1;
   if (get_option("gemm_ksub") == 1) ksub = 1;
   if (get_option("gemm_ksub") == 2 && d.K > 64) ksub = 2;
   plan.bn = bn; plan.ctas = ctas; plan.sched = sched; plan.ksub = ksub;
