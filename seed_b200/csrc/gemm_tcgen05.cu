@@ -47,9 +47,6 @@ struct GemmParams {
   int tile_shift;            // round r of the persistent schedule hands unit u the tile r*units + (u + r*tile_shift) % units:
                              // with a cheap tail column the plain round robin (shift 0) gives some units all the cheap
                              // tiles and others none whenever units % n_tiles shares a factor with n_tiles
-  int prefetch_a;            // bit 0: while a tile's k-blocks stream through the ring, the producer pulls the NEXT tile's rows of A
-                             // into L2 (cp.async.bulk.prefetch.tensor): A is streamed from HBM once, and the ~16 units that
-                             // share an m-tile reach a fresh A block together, so every one of them waited out a DRAM miss
   int sched;                 // 0: round robin (above).  1: balanced tail -- the full-width tiles go round robin over the units
                              // first, then the units that got one full tile fewer take the narrow tail tiles; with few tiles
                              // per unit (M = 2048 prefill: 128 tiles of 256 x 256 on 74 CTA pairs = 2 rounds, the second
@@ -423,16 +420,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const CUtensorMap* tb = tail_tile ? &tmap_bt : &tmap_b;
         const uint32_t stage_tx = (uint32_t)(Cfg::A_BYTES + KSUB * load_n * GEMM_BLOCK_K * 2);
         const int n_idx = nt * BN + (int)cta_rank * load_n;
-        const int next_tile = tile_of(round + 1);
-        const int next_mt = next_tile < total_tiles ? next_tile / p.n_tiles : mt;
-        const bool pf = (p.prefetch_a & 1) != 0 && next_mt != mt;
-        const int m_next = (next_mt * CTAS + (int)cta_rank) * GEMM_BLOCK_M;
-        // ... and (bit 1) the next tile's rows of W, for shapes whose W is the operand streamed from HBM (LLaMA prefill)
-        const int next_nt = next_tile < total_tiles ? next_tile % p.n_tiles : nt;
-        const bool pfw = (p.prefetch_a & 2) != 0 && next_nt != nt;
-        const bool next_tail = p.tail_w > 0 && next_nt == p.n_tiles - 1;
-        const CUtensorMap* tb_next = next_tail ? &tmap_bt : &tmap_b;
-        const int n_next = next_nt * BN + (int)cta_rank * (next_tail ? p.tail_w / CTAS : Cfg::LOAD_N);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait_relaxed(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_a + stage * Cfg::A_BYTES;
@@ -453,14 +440,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               tma_load_2d_2cta(sb_ + ks * Cfg::B_SUB, tb, lead_bar, kb * STAGE_K + ks * GEMM_BLOCK_K, n_idx);
             }
             if (!leader) mbar_arrive_cluster(lead_bar);
-          }
-          if (pf) {
-#pragma unroll
-            for (int ks = 0; ks < KSUB; ++ks) tma_prefetch_2d(&tmap_a, kb * STAGE_K + ks * GEMM_BLOCK_K, m_next);
-          }
-          if (pfw) {
-#pragma unroll
-            for (int ks = 0; ks < KSUB; ++ks) tma_prefetch_2d(tb_next, kb * STAGE_K + ks * GEMM_BLOCK_K, n_next);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -918,7 +897,6 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream, int sch
   }
   p.tile_shift = ts.tile_shift;
   p.sched = ts.sched;
-  p.prefetch_a = get_option("gemm_prefetch_a") & 3;
   p.ln_stats = static_cast<const float2*>(d.ln_stats);
   p.ln_c = static_cast<const float*>(d.ln_c);
   p.ln_b = static_cast<const float*>(d.ln_b);

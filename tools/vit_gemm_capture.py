@@ -86,35 +86,3 @@ if "--ksub" in sys.argv:
         print(json.dumps(rows[-1]), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(rows, open("gpurun_out/vit_gemm_ksub.json", "w"), indent=1)
-
-if "--prefetch" in sys.argv:
-    # L2 prefetch of the next tile's operand rows by the producer (option gemm_prefetch_a: bit 0 = A, bit 1 = W), interleaved
-    fns = [lambda: L.gemm(x, qkv_f[0], out=qkv, ctas=2, ln=(stats, qkv_f[1], qkv_f[2])),
-           lambda: L.gemm(att, w_proj, bias=b_proj, residual=x, out=x, ctas=2),
-           lambda: L.gemm(x, fc1_f[0], act=L.ACT_GELU, out=hid, ctas=2, ln=(stats, fc1_f[1], fc1_f[2])),
-           lambda: L.gemm(hid, w_fc2, bias=b_fc2, residual=x, out=x, ctas=2)]
-    shapes = list(zip(names, flops, fns))
-    a2 = torch.randn(2048, 4096, device="cuda", dtype=torch.float16)
-    a3 = torch.randn(2048, 11008, device="cuda", dtype=torch.float16)
-    for nm, N, K, a in (("7b_qkv", 12288, 4096, a2), ("7b_o", 4096, 4096, a2), ("7b_down", 4096, 11008, a3)):
-        # 16 different weight matrices per shape so that W really streams from HBM (as in the 32-layer model)
-        ws = [torch.randn(N, K, device="cuda", dtype=torch.float16) * K ** -0.5 for _ in range(8)]
-        o = torch.empty(2048, N, device="cuda", dtype=torch.float16)
-        def fn(ws=ws, a=a, o=o):
-            for w in ws:
-                L.gemm(a, w, out=o, ctas=2)
-        shapes.append((nm + "_x8", 8 * 2.0 * 2048 * N * K, fn))
-    rows = []
-    for nm, fl, fn in shapes:
-        t = {0: [], 1: [], 2: [], 3: []}
-        for _ in range(8):
-            for pf in (0, 1, 2, 3):
-                L.set_option("gemm_prefetch_a", pf)
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record(); fn(); e.record(); torch.cuda.synchronize(); t[pf].append(s.elapsed_time(e))
-        L.set_option("gemm_prefetch_a", 0)
-        rows.append({"shape": nm, **{f"pf{k}_ms": round(min(v), 4) for k, v in t.items()},
-                     **{f"pf{k}_tflops": round(fl / min(v) / 1e9, 1) for k, v in t.items()}})
-        print(json.dumps(rows[-1]), flush=True)
-    os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(rows, open("gpurun_out/vit_gemm_prefetch.json", "w"), indent=1)
