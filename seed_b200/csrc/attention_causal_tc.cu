@@ -89,17 +89,6 @@ __device__ __forceinline__ void ca_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
-// tcgen05.wait::ld that names the 32 destination registers of the chunk it completes: uses of r[] cannot be scheduled
-// above the wait once the NEXT chunk's load is already in flight
-__device__ __forceinline__ void ca_wait32(uint32_t (&r)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
-                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
-                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-               :
-               : "memory");
-}
 __device__ __forceinline__ void ca_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -332,11 +321,13 @@ causal_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
         tc_fence_after();
         const int kb = j * CA_T;
         const bool masked = kb + CA_T - 1 > warp_limit;       // warp-uniform
-        // pass 1: row maximum of the visible scores; the next 32-column chunk's tcgen05.ld is in flight while the
-        // current one is reduced (two register buffers)
+        // pass 1: row maximum of the visible scores
         float mx = -INFINITY;
-        uint32_t ra[32], rb[32];
-        auto max_chunk = [&](const uint32_t (&r)[32], int c) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          ca_ld32(tS + c * 32, r);
+          tmem_ld_wait();
           if (masked) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) if (kb + c * 32 + e <= limit) mx = fmaxf(mx, __uint_as_float(r[e]));
@@ -344,12 +335,7 @@ causal_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
 #pragma unroll
             for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
           }
-        };
-        ca_ld32(tS, ra);
-        ca_wait32(ra); ca_ld32(tS + 32, rb); max_chunk(ra, 0);
-        ca_wait32(rb); ca_ld32(tS + 64, ra); max_chunk(rb, 1);
-        ca_wait32(ra); ca_ld32(tS + 96, rb); max_chunk(ra, 2);
-        ca_wait32(rb); ca_ld32(tS, ra);      max_chunk(rb, 3);      // chunk 0 again: first chunk of pass 2
+        }
         const float m_new = fmaxf(m, mx * p.scale_log2);      // scale > 0
         if (j == 0) {
           m = m_new;                                          // key 0 is visible to every row: finite
@@ -370,10 +356,13 @@ causal_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
           l *= alpha;
           m = m_new;
         }
-        // pass 2: P = 2^(s * scale * log2e - m), fp16, in place over the S columns already consumed (chunk c + 1 is
-        // loaded before chunk c's P is stored, and P of chunk c only covers columns [16c, 16c + 16))
+        // pass 2: P = 2^(s * scale * log2e - m), fp16, in place over the S columns already consumed
         float sum = 0.0f;
-        auto exp_chunk = [&](const uint32_t (&r)[32], int c) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          ca_ld32(tS + c * 32, r);
+          tmem_ld_wait();
           uint32_t pk[16];
           if (masked) {
 #pragma unroll
@@ -390,11 +379,7 @@ causal_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
                                ca_ex2(fmaf(__uint_as_float(r[2 * g + 1]), p.scale_log2, -m)), sum);
           }
           ca_st16(tS + c * 16, pk);
-        };
-        ca_wait32(ra); ca_ld32(tS + 32, rb); exp_chunk(ra, 0);
-        ca_wait32(rb); ca_ld32(tS + 64, ra); exp_chunk(rb, 1);
-        ca_wait32(ra); ca_ld32(tS + 96, rb); exp_chunk(ra, 2);
-        ca_wait32(rb);                       exp_chunk(rb, 3);
+        }
         l += sum;
         ca_st_wait();
         tc_fence_before();
