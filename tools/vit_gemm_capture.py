@@ -86,3 +86,19 @@ if "--ksub" in sys.argv:
         print(json.dumps(rows[-1]), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(rows, open("gpurun_out/vit_gemm_ksub.json", "w"), indent=1)
+
+if "--act" in sys.argv:
+    # is the fc1 GEMM bound by its GELU epilogue?  same shape, LN-folded, with and without the activation, interleaved
+    f_gelu = lambda: L.gemm(x, fc1_f[0], act=L.ACT_GELU, out=hid, ctas=2, ln=(stats, fc1_f[1], fc1_f[2]))
+    f_none = lambda: L.gemm(x, fc1_f[0], act=L.ACT_NONE, out=hid, ctas=2, ln=(stats, fc1_f[1], fc1_f[2]))
+    f_relu = lambda: L.gemm(x, fc1_f[0], act=L.ACT_RELU, out=hid, ctas=2, ln=(stats, fc1_f[1], fc1_f[2]))
+    t = {"gelu": [], "none": [], "relu": []}
+    for _ in range(10):
+        for key, fn in (("gelu", f_gelu), ("none", f_none), ("relu", f_relu)):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record(); torch.cuda.synchronize(); t[key].append(s.elapsed_time(e))
+    row = {"shape": "fc1_6144x1408_lnfold", **{k + "_ms": round(min(v), 4) for k, v in t.items()},
+           **{k + "_tflops": round(flops[2] / min(v) / 1e9, 1) for k, v in t.items()}}
+    print(json.dumps(row), flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(row, open("gpurun_out/vit_gemm_act.json", "w"), indent=1)
