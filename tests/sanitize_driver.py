@@ -106,6 +106,13 @@ def decode():
     out = L.decode_attention(q, kc, vc, kv, D ** -0.5)
     ref = R.attention_ref(q[:, :, None], kc[:, :, :kv], vc[:, :, :kv], D ** -0.5)
     assert rel(out.view(B, H, D), ref.view(B, H, D)) < 3e-3
+    # fused RoPE + append + attention (three thread groups; the new key / value come from shared memory)
+    qkv = r16(B, 3 * H * D, seed=51)
+    kc2, vc2 = kc.clone(), vc.clone()
+    q_rot = L.rope_kv_append(qkv, None, B, 1, H, D, kv, kc, vc)
+    two = L.decode_attention(q_rot.view(B, H, D), kc, vc, kv + 1, D ** -0.5)
+    one = L.decode_attention_rope(qkv, None, H, kv, kc2, vc2, D ** -0.5)
+    assert torch.equal(one, two) and torch.equal(kc, kc2) and torch.equal(vc, vc2)
     logits = r16(4, 5000, scale=3.0, seed=50)
     L.sample(logits)
     L.sample(logits, do_sample=True, temperature=0.9, top_p=0.5, seed=1, offset=2, step=3)
