@@ -28,10 +28,22 @@ constexpr int VQ_LD = 36;          // padded fp32 row (16-byte aligned, 4-way in
 
 __device__ __forceinline__ float round16(float x) { return __half2float(__float2half_rn(x)); }
 
-template <int MODE>
+// (d, id) as one 64-bit key whose unsigned order is the lexicographic order (smaller d first, then the lower index):
+// the float is mapped to an order-preserving unsigned; NaN never wins (it never does in the strict `<` scan either)
+__device__ __forceinline__ unsigned long long vq_key(float d, int id) {
+  unsigned u = __float_as_uint(d);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  if (d != d) u = 0xffffffffu;
+  return ((unsigned long long)u << 32) | (unsigned)id;
+}
+
+// SPLIT: blockIdx.y owns the code range [y * codes_per_split, ...) and the per-row winners of the splits meet in
+// ids[] through a 64-bit atomicMin on the (d, id) key (ids[] preset to all ones, low word extracted by vq_finish_kernel).
+// Few rows (a single image = 32 rows) otherwise leave one CTA walking all 8192 codes: 167 us for 64 rows.
+template <int MODE, bool SPLIT>
 __global__ void __launch_bounds__(VQ_WARPS * 32)
 vq_argmin_kernel(const __half* __restrict__ z, const __half* __restrict__ codebook, int n, int n_codes,
-                 long long* __restrict__ ids) {
+                 long long* __restrict__ ids, int codes_per_split) {
   __shared__ __align__(16) float s_e[VQ_TILE * VQ_LD];
   __shared__ float s_b[VQ_TILE];
   __shared__ float s_d[VQ_WARPS][32];
@@ -62,7 +74,9 @@ vq_argmin_kernel(const __half* __restrict__ z, const __half* __restrict__ codebo
 
   float best = INFINITY;
   int best_i = 0x7fffffff;
-  for (int tile0 = 0; tile0 < n_codes; tile0 += VQ_TILE) {
+  const int code_begin = SPLIT ? blockIdx.y * codes_per_split : 0;
+  const int code_end = SPLIT ? min(n_codes, code_begin + codes_per_split) : n_codes;
+  for (int tile0 = code_begin; tile0 < code_end; tile0 += VQ_TILE) {
     __syncthreads();                               // the previous tile has been consumed
     // stage: 256 codes x 64 bytes = 1024 16-byte vectors, coalesced; fp16 -> fp32
 #pragma unroll
@@ -114,7 +128,7 @@ vq_argmin_kernel(const __half* __restrict__ z, const __half* __restrict__ codebo
         const float t = __fadd_rn(A, Bn);
         dist = __fsub_rn(t, __fmul_rn(2.0f, C));
       }
-      if (c < n_codes && dist < best) { best = dist; best_i = c; }   // ascending c per warp: strict < keeps the lowest index
+      if (c < code_end && dist < best) { best = dist; best_i = c; }   // ascending c per warp: strict < keeps the lowest index
     }
   }
   s_d[warp][lane] = best;
@@ -129,9 +143,20 @@ vq_argmin_kernel(const __half* __restrict__ z, const __half* __restrict__ codebo
       const int ii = s_i[w][lane];
       if (dd < bd || (dd == bd && ii < bi)) { bd = dd; bi = ii; }   // ties -> lowest index (torch.argmin)
     }
-    if (bi == 0x7fffffff) bi = 0;                    // all distances NaN/inf: torch.argmin returns 0 for all-inf
-    ids[row] = (long long)bi;
+    if constexpr (SPLIT) {
+      if (bi != 0x7fffffff) atomicMin(reinterpret_cast<unsigned long long*>(ids) + row, vq_key(bd, bi));
+    } else {
+      if (bi == 0x7fffffff) bi = 0;                  // all distances NaN/inf: torch.argmin returns 0 for all-inf
+      ids[row] = (long long)bi;
+    }
   }
+}
+
+__global__ void vq_finish_kernel(long long* __restrict__ ids, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = reinterpret_cast<unsigned long long*>(ids)[i];
+  ids[i] = (k == ~0ull) ? 0LL : (long long)(k & 0xffffffffull);     // no finite / inf distance at all: 0 like the scan
 }
 
 int vq_argmin(const void* z, const void* codebook, int n, int n_codes, int dim, int mode, int64_t* ids,
@@ -141,14 +166,34 @@ int vq_argmin(const void* z, const void* codebook, int n, int n_codes, int dim, 
   SB_REQUIRE(n > 0 && n_codes > 0, "vq_argmin: empty problem");
   SB_REQUIRE(mode == SEEDB200_VQ_FP16 || mode == SEEDB200_VQ_FP32, "vq_argmin: unknown mode %d", mode);
   const int blocks = (n + 31) / 32;
+  const int tiles = (n_codes + VQ_TILE - 1) / VQ_TILE;
+  const __half* zp = static_cast<const __half*>(z);
+  const __half* cp = static_cast<const __half*>(codebook);
+  long long* ip = reinterpret_cast<long long*>(ids);
+  // few row blocks: split the codebook over blockIdx.y so that about one CTA per SM is busy
+  int splits = 1;
+  if (blocks * 2 <= num_sms() && tiles > 1) {
+    splits = num_sms() / blocks;
+    if (splits > tiles) splits = tiles;
+  }
+  if (splits > 1) {
+    const int tiles_per_split = (tiles + splits - 1) / splits;
+    splits = (tiles + tiles_per_split - 1) / tiles_per_split;
+    const int cps = tiles_per_split * VQ_TILE;
+    SB_CHECK_CUDA(cudaMemsetAsync(ip, 0xff, (size_t)n * sizeof(long long), stream));
+    if (mode == SEEDB200_VQ_FP16)
+      vq_argmin_kernel<SEEDB200_VQ_FP16, true><<<dim3(blocks, splits), VQ_WARPS * 32, 0, stream>>>(zp, cp, n, n_codes, ip, cps);
+    else
+      vq_argmin_kernel<SEEDB200_VQ_FP32, true><<<dim3(blocks, splits), VQ_WARPS * 32, 0, stream>>>(zp, cp, n, n_codes, ip, cps);
+    SB_LAUNCH_CHECK();
+    vq_finish_kernel<<<(n + 255) / 256, 256, 0, stream>>>(ip, n);
+    SB_LAUNCH_CHECK();
+    return 0;
+  }
   if (mode == SEEDB200_VQ_FP16)
-    vq_argmin_kernel<SEEDB200_VQ_FP16><<<blocks, VQ_WARPS * 32, 0, stream>>>(
-        static_cast<const __half*>(z), static_cast<const __half*>(codebook), n, n_codes,
-        reinterpret_cast<long long*>(ids));
+    vq_argmin_kernel<SEEDB200_VQ_FP16, false><<<blocks, VQ_WARPS * 32, 0, stream>>>(zp, cp, n, n_codes, ip, n_codes);
   else
-    vq_argmin_kernel<SEEDB200_VQ_FP32><<<blocks, VQ_WARPS * 32, 0, stream>>>(
-        static_cast<const __half*>(z), static_cast<const __half*>(codebook), n, n_codes,
-        reinterpret_cast<long long*>(ids));
+    vq_argmin_kernel<SEEDB200_VQ_FP32, false><<<blocks, VQ_WARPS * 32, 0, stream>>>(zp, cp, n, n_codes, ip, n_codes);
   SB_LAUNCH_CHECK();
   return 0;
 }

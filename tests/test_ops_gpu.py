@@ -430,6 +430,26 @@ def test_vq_duplicate_codes_pick_lowest_index(lib):
 # ----------------------------------------------------------------------------------------------
 # patchify, embedding, RoPE + KV append
 # ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [0, 1])
+def test_vq_code_split_path_equals_the_single_cta_walk(lib, mode):
+    """few rows (a single image = 32 rows): the codebook is split over CTAs and the winners meet through a 64-bit
+    atomicMin on the (d, id) key; the same rows inside a full batch take the one-CTA walk -- identical ids, ties and
+    degenerate rows included"""
+    cb = rand16(8192, 32, scale=0.26, seed=83)
+    cb[4000] = cb[17]                               # duplicates in different splits: the lower index must win
+    cb[8191] = cb[300]
+    z = rand16(8192, 32, scale=0.3, seed=84)
+    z[3] = cb[17]
+    z[5] = cb[300]
+    z[7] = float("inf")                             # every distance inf / NaN: id 0 on both paths
+    full = lib.vq_argmin(z, cb, mode=mode)          # 256 row blocks: no split
+    for n in (32, 33, 64, 700):
+        part = lib.vq_argmin(z[:n].contiguous(), cb, mode=mode)
+        torch.cuda.synchronize()
+        assert torch.equal(part, full[:n]), n
+    assert full[3].item() == 17 and full[5].item() == 300 and full[7].item() == 0
+
+
 def test_patchify_exact(lib):
     img = rand16(3, 3, 224, 224, seed=50)
     cols = lib.patchify(img, 592)

@@ -102,3 +102,25 @@ if "--act" in sys.argv:
     print(json.dumps(row), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(row, open("gpurun_out/vit_gemm_act.json", "w"), indent=1)
+
+if "--bn" in sys.argv:
+    # tile width per shape with the current pipeline (the tuning table went stale once: re-measure), interleaved
+    def mk(bn):
+        return [lambda: L.gemm(x, qkv_f[0], out=qkv, ctas=2, bn=bn, ln=(stats, qkv_f[1], qkv_f[2])),
+                lambda: L.gemm(att, w_proj, bias=b_proj, residual=x, out=x, ctas=2, bn=bn),
+                lambda: L.gemm(x, fc1_f[0], act=L.ACT_GELU, out=hid, ctas=2, bn=bn, ln=(stats, fc1_f[1], fc1_f[2])),
+                lambda: L.gemm(hid, w_fc2, bias=b_fc2, residual=x, out=x, ctas=2, bn=bn)]
+    widths = (0, 256, 192, 128)
+    fns = {bn: mk(bn) for bn in widths}
+    rows = []
+    for i, (nm, fl) in enumerate(zip(names, flops)):
+        t = {bn: [] for bn in widths}
+        for _ in range(8):
+            for bn in widths:
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(); fns[bn][i](); e.record(); torch.cuda.synchronize(); t[bn].append(s.elapsed_time(e))
+        rows.append({"shape": nm, **{f"bn{k}_ms": round(min(v), 4) for k, v in t.items()},
+                     **{f"bn{k}_tflops": round(fl / min(v) / 1e9, 1) for k, v in t.items()}})
+        print(json.dumps(rows[-1]), flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(rows, open("gpurun_out/vit_gemm_bn.json", "w"), indent=1)
