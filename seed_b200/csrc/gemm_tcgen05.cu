@@ -26,9 +26,9 @@ namespace sb {
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
-constexpr int GEMM_EPI_WARP0 = 4;      // 4 control warps (TMA producer, MMA issuer, TMEM allocator, spare), then EW epilogue warps:
-                                       // 8 = two per TMEM lane quarter, 12 = three (the GELU epilogue of fc1 is bound by what two
-                                       // warps per scheduler can issue / hide: 0.839 ms with the activation, 0.759 ms without)
+constexpr int GEMM_THREADS = 384;      // 4 control warps + 8 epilogue warps
+constexpr int GEMM_EPI_WARP0 = 4;
+constexpr int GEMM_EPI_THREADS = 256;
 
 struct GemmParams {
   int M, N, K;
@@ -84,10 +84,8 @@ __host__ __device__ inline int sched_tile(int sched, int round, int unit, int un
 // KSUB: 64-wide K sub-blocks per pipeline stage.  KSUB = 2 halves the per-stage fixed cost in the MMA issuer
 // (one mbarrier wait + one tcgen05.commit per 8 MMAs instead of per 4), which is what bounded the
 // short-N tiles (ncu: tensor pipe 64% active with neither operands nor the epilogue late).
-template <int BN, int CTAS, int KSUB = 2, int EW = 8>
+template <int BN, int CTAS, int KSUB = 2>
 struct GemmCfg {
-  static constexpr int EPI_THREADS = EW * 32;
-  static constexpr int THREADS = GEMM_EPI_WARP0 * 32 + EPI_THREADS;
   static constexpr int LOAD_N = BN / CTAS;
   static constexpr int A_SUB = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;      // one 64-wide sub-block of A
   static constexpr int B_SUB = LOAD_N * GEMM_BLOCK_K * 2;
@@ -102,13 +100,13 @@ struct GemmCfg {
   // residual boxes per warp, loaded by TMA two boxes ahead.
   static constexpr bool STAGED_OUT = (BN % 64 == 0);
   static constexpr bool STAGED_RES = STAGED_OUT && CTAS == 2 && KSUB == 1;
-  static constexpr int OUT_STAGE_BYTES = STAGED_OUT ? EW * 2048 : 0;
-  static constexpr int RES_STAGE_BYTES = STAGED_RES ? 2 * EW * 2048 : 0;
+  static constexpr int OUT_STAGE_BYTES = STAGED_OUT ? 8 * 2048 : 0;
+  static constexpr int RES_STAGE_BYTES = STAGED_RES ? 2 * 8 * 2048 : 0;
   static constexpr int STAGES_RAW = (220 * 1024 - OUT_STAGE_BYTES - RES_STAGE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16 + 2 * 256 * 2 + 2 * 2 * 256 * 4 + 2 * EW * 8;   // barriers, tmem slot, bias stage, LN-fold c / b' stages, residual-box barriers
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16 + 2 * 256 * 2 + 2 * 2 * 256 * 4 + 16 * 8;   // barriers, tmem slot, bias stage, LN-fold c / b' stages, residual-box barriers
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + OUT_STAGE_BYTES + RES_STAGE_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   // keep one CTA per SM (TMEM is allocated per CTA): request more than half of the SM's smem
@@ -337,12 +335,12 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int
                : "memory");
 }
 
-template <int BN, int CTAS, int MODE, int KSUB, int EW>
-__global__ void __launch_bounds__(GEMM_EPI_WARP0 * 32 + EW * 32, 1)
+template <int BN, int CTAS, int MODE, int KSUB>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_bt, const __grid_constant__ CUtensorMap tmap_o,
                     const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
-  using Cfg = GemmCfg<BN, CTAS, KSUB, EW>;
+  using Cfg = GemmCfg<BN, CTAS, KSUB>;
   constexpr int STAGE_K = GEMM_BLOCK_K * KSUB;
   constexpr int STAGES = Cfg::STAGES;
 
@@ -387,9 +385,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + 8 * i, 1);
-      mbar_init(tempty_bar + 8 * i, CTAS * EW);   // one arrive per epilogue warp
+      mbar_init(tempty_bar + 8 * i, CTAS * (GEMM_EPI_THREADS / 32));   // one arrive per epilogue warp
     }
-    for (int i = 0; i < 2 * EW; ++i) mbar_init(res_bar + 8 * i, 1);
+    for (int i = 0; i < 16; ++i) mbar_init(res_bar + 8 * i, 1);
     fence_mbar_init();
   } else if (warp == 2) {
     tmem_alloc<CTAS>(tmem_slot, Cfg::TMEM_COLS);
@@ -490,10 +488,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp >= GEMM_EPI_WARP0) {
     // ===================== epilogue =====================
-    const int ew = warp - GEMM_EPI_WARP0;      // 0..EW-1
+    const int ew = warp - GEMM_EPI_WARP0;      // 0..7
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-    const int half_id = ew >> 2;               // which part of the column chunks (EW / 4 warps share a lane quarter)
-    const int etid = threadIdx.x - GEMM_EPI_WARP0 * 32;   // 0..EW*32-1
+    const int half_id = ew >> 2;               // which half of the column chunks
+    const int etid = threadIdx.x - GEMM_EPI_WARP0 * 32;   // 0..255
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const uint32_t lead_tempty0 = (CTAS == 2) ? mapa_shared(tempty_bar, 0) : tempty_bar;
     __half* bias_smem = reinterpret_cast<__half*>(smem_gen + (bias_off - smem_base));
@@ -523,17 +521,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t aphase = (iter >> 1) & 1;
       // the two warps of a TMEM lane quarter split the tile's 16-column chunks; the ragged last tile has fewer
       const int nchunk = (p.tail_w > 0 && nt == p.n_tiles - 1) ? p.tail_w / 16 : NCHUNK;
-      int c_begin, c_end;
-      if constexpr (EW == 8) {
-        const int ch0 = (nchunk + 1) / 2;
-        c_begin = half_id == 0 ? 0 : ch0;
-        c_end = half_id == 0 ? ch0 : nchunk;
-      } else {
-        // EW / 4 warps per lane quarter: whole 32-column boxes each (16 chunks -> 4 / 6 / 6)
-        constexpr int NPART = EW / 4;
-        c_begin = (half_id * nchunk / NPART) & ~1;
-        c_end = half_id == NPART - 1 ? nchunk : (((half_id + 1) * nchunk / NPART) & ~1);
-      }
+      const int ch0 = (nchunk + 1) / 2;
+      const int c_begin = half_id == 0 ? 0 : ch0;
+      const int c_end = half_id == 0 ? ch0 : nchunk;
       const int n_tile0 = (MODE == 1) ? nt * (BN / 2) : nt * BN;
       const int m = (mt * CTAS + (int)cta_rank) * GEMM_BLOCK_M + quarter * 32 + lane;
       const bool row_ok = m < p.M;
@@ -554,7 +544,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (has_ln && row_ok) ln_st = p.ln_stats[m];       // (mean, rstd) of this thread's row
       if (has_cols) {
         // this tile's vectors were staged one tile ago (or in the prologue); the barrier publishes them
-        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const int next = tile_of(round + 1);
         if (next < total_tiles && etid < BN) {     // issue the load now, consume it after the chunk loop
           const int n = (next % p.n_tiles) * BN + etid;
@@ -847,12 +837,12 @@ static TileSchedule make_schedule(int M, int N, int bn, int ctas, int mode, int 
   return t;
 }
 
-template <int BN, int CTAS, int MODE, int KSUB, int EW = 8>
+template <int BN, int CTAS, int MODE, int KSUB>
 static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream, int sched) {
-  using Cfg = GemmCfg<BN, CTAS, KSUB, EW>;
+  using Cfg = GemmCfg<BN, CTAS, KSUB>;
   static bool attr_set_dev[SB_MAX_DEVICES] = {};   // cudaFuncSetAttribute is per device
   bool& attr_set = attr_set_dev[cur_device()];
-  auto kern = gemm_tcgen05_kernel<BN, CTAS, MODE, KSUB, EW>;
+  auto kern = gemm_tcgen05_kernel<BN, CTAS, MODE, KSUB>;
   if (!attr_set) {
     SB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_REQUEST));
     attr_set = true;
@@ -915,7 +905,7 @@ static int launch_gemm(const seedb200_gemm_desc& d, cudaStream_t stream, int sch
 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(units * CTAS);
-  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_REQUEST;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1030,11 +1020,6 @@ int gemm(const seedb200_gemm_desc& d, cudaStream_t stream) {
   SB_PROPAGATE(choose_plan(d, num_sms(), plan));
   SB_REQUIRE(d.A && d.W && d.out, "gemm: null operand");
   const int bn = plan.bn, ctas = plan.ctas, sched = plan.sched, ksub = plan.ksub;
-  // twelve epilogue warps for the GELU epilogue on the wide CTA-pair tiles (fc1 of the ViT blocks); the 64-column moment
-  // groups of row_moments need the two-per-quarter split
-  if (bn == 256 && ctas == 2 && d.mode == 0 && ksub == 2 && d.act == SEEDB200_ACT_GELU && d.row_moments == nullptr &&
-      get_option("gemm_epi_warps") == 12)
-    return launch_gemm<256, 2, 0, 2, 12>(d, stream, sched);
 #define SB_GEMM_CASE(BN_, CT_, MD_)                                                   \
   if (bn == BN_ && ctas == CT_ && d.mode == MD_) {                                    \
     if (ksub == 2) return launch_gemm<BN_, CT_, MD_, 2>(d, stream, sched);            \

@@ -124,23 +124,3 @@ if "--bn" in sys.argv:
         print(json.dumps(rows[-1]), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(rows, open("gpurun_out/vit_gemm_bn.json", "w"), indent=1)
-
-if "--epi" in sys.argv:
-    # epilogue warps of the GELU GEMM (option gemm_epi_warps: 8 = two per TMEM lane quarter, 12 = three), interleaved
-    f_gelu = lambda: L.gemm(x, fc1_f[0], act=L.ACT_GELU, out=hid, ctas=2, ln=(stats, fc1_f[1], fc1_f[2]))
-    ref = None
-    t = {8: [], 12: []}
-    outs = {}
-    for _ in range(10):
-        for ew in (8, 12):
-            L.set_option("gemm_epi_warps", ew)
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record(); f_gelu(); e.record(); torch.cuda.synchronize(); t[ew].append(s.elapsed_time(e))
-            outs[ew] = hid.clone()
-    L.set_option("gemm_epi_warps", 12)
-    row = {"shape": "fc1_6144x1408_lnfold_gelu", **{f"ew{k}_ms": round(min(v), 4) for k, v in t.items()},
-           **{f"ew{k}_tflops": round(flops[2] / min(v) / 1e9, 1) for k, v in t.items()},
-           "bit_identical": bool(torch.equal(outs[8], outs[12]))}
-    print(json.dumps(row), flush=True)
-    os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(row, open("gpurun_out/vit_gemm_epi.json", "w"), indent=1)
