@@ -54,8 +54,9 @@ __device__ __forceinline__ void dot8(const uint4& w, const uint4& x, float& acc)
   }
 }
 
-// U: 16-byte vectors per weight row a lane keeps in flight (4 = 128 bytes per lane; 8 for the short-N projections
-// whose few warps cannot cover the HBM latency otherwise).  CTAs are 256 or 128 threads (nw warps).
+// U: 16-byte vectors per weight row a lane keeps in flight (4 = 128 bytes per lane).  Measured and dropped (r02,
+// profiles/r02_decode_ab.json): U = 8 on 128-thread CTAs for the short-N projections (4.98 -> 5.37 ms/token) and a cap on
+// the CTAs per SM so that the next kernel of the programmatic-launch chain is co-resident early (5.08 / 6.13 ms/token).
 template <int M, int MODE, bool NORM, int U>
 __global__ void __launch_bounds__(256)
 gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long long ldw, __half* __restrict__ out,
@@ -227,10 +228,6 @@ int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* resid
   SB_REQUIRE(smem <= 200 * 1024, "gemv: activation rows do not fit shared memory (M=%d K=%d)", M, K);
   const int n_tasks = mode == 1 ? N / 2 : (N + 1) / 2;
   const int force_split = get_option("gemv_ksplit");
-  // option gemv_deep: row-pair count below which the 8-vectors-in-flight / 128-thread form is used (0 = never):
-  // o_proj / down_proj of the decode step have 2560 pairs for ~2400 resident warps, one dependent chain of 128-byte
-  // loads per lane each
-  const bool deep = M <= 2 && get_option("gemv_deep") > 0 && n_tasks <= get_option("gemv_deep");
   const __half* xp = static_cast<const __half*>(x);
   const __half* wp = static_cast<const __half*>(W);
   const __half* rp = static_cast<const __half*>(residual);
@@ -239,7 +236,7 @@ int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* resid
 #define SB_GEMV_LAUNCH(M_, MD_, NM_, U_)                                                                   \
   {                                                                                                        \
     auto kern = gemv_kernel<M_, MD_, NM_, U_>;                                                             \
-    const int threads = (U_ == 8) ? 128 : 256;                                                             \
+    const int threads = 256;                                                                               \
     static size_t attr_smem_dev[SB_MAX_DEVICES] = {};   /* per device: cudaFuncSetAttribute is */          \
     const int dev_ = cur_device();                                                                         \
     size_t& attr_smem = attr_smem_dev[dev_];                                                               \
@@ -257,10 +254,7 @@ int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* resid
       occ_smem = smem;                                                                                     \
       if (occ < 1) occ = 1;                                                                                \
     }                                                                                                      \
-    /* option gemv_occupancy: cap the CTAs per SM so that the next kernel of a programmatic-launch chain */   \
-    /* finds room to become resident (and prefetch its first weight batch) while this one is streaming */    \
-    const int occ_cap = get_option("gemv_occupancy");                                                      \
-    const int resident = num_sms() * ((occ_cap > 0 && occ_cap < occ) ? occ_cap : occ);                     \
+    const int resident = num_sms() * occ;                                                                  \
     /* K can be split over 2 or 4 warps per row pair (option gemv_ksplit); measured on the 13B decode step it  */ \
     /* loses (5.19 ms/token unsplit, 5.44 / 5.62 with 2 / 4 slices), so the default stays one warp per pair */ \
     int ksplit = 1;                                                                                        \
@@ -280,10 +274,6 @@ int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* resid
   }
 #define SB_GEMV(M_, MD_)                                                                                   \
   if (M == M_ && mode == MD_) {                                                                            \
-    if (deep) {                                                                                            \
-      if (norm_w != nullptr) SB_GEMV_LAUNCH(M_, MD_, true, 8)                                              \
-      SB_GEMV_LAUNCH(M_, MD_, false, 8)                                                                    \
-    }                                                                                                      \
     if (norm_w != nullptr) SB_GEMV_LAUNCH(M_, MD_, true, 4)                                                \
     SB_GEMV_LAUNCH(M_, MD_, false, 4)                                                                      \
   }

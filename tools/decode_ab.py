@@ -1,4 +1,5 @@
-"""A/B of the decode-step options on the 13B cached decode forward (eager launches through the C handle, programmatic
+"""(historical: the gemv_occupancy / gemv_deep options it sweeps were removed after this A/B; the fused-attention rows still run)
+A/B of the decode-step options on the 13B cached decode forward (eager launches through the C handle, programmatic
 dependent launches on): fused RoPE+append+attention, GEMV CTAs-per-SM cap, deep-load GEMV for the short-N projections.
 Writes gpurun_out/decode_ab.json.  `python tools/decode_ab.py [7b]`"""
 import sys, os, json, itertools
@@ -23,7 +24,12 @@ bytes_per_token = 2.0 * (nl * (4 * h * h + 3 * h * ffn) + V * h) + 2.0 * nl * 2 
 
 def run(tag, **opts):
     for k, v in opts.items():
-        L.set_option(k, v)
+        try:
+            L.set_option(k, v)
+        except RuntimeError:
+            if v != 0:
+                print(json.dumps({"tag": tag, "skipped": f"option {k} no longer exists"}), flush=True)
+                return {"tag": tag, "skipped": k}
     for i in range(4):
         llm.forward(input_ids=nxt, inputs_embeds=None, position_ids=None, past_len=256 + i, last_only=True)
     torch.cuda.synchronize()
