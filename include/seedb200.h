@@ -71,6 +71,7 @@ void seedb200_reset_launch_count(void);
  * "gemm_tail": 1 (default) = a ragged last column of tiles runs at its own width, 0 = as a full tile.
  * "decode_fused_attention": 1 (default) = the cached decode step runs RoPE + KV append + attention as one kernel per
  * layer when max_seq <= 2048 (seedb200_decode_attention_rope), 0 = rope_kv_append + split-KV decode attention.
+ * "gemv_no_allocate": 1 (default) = the decode GEMVs stream their weights with ld.global.nc.L1::no_allocate, 0 = ld.global.nc.
  * "gemm_sched": 1 (default) = a GEMM with a single row of tiles (M <= 256: a short LLaMA prompt) picks its tile width
  * from a busy-SM model (seedb200_gemm_plan), 0 = the fixed heuristics, 2 = balanced-tail tile order with an explicit
  * bn (A/B runs: measured equal to the rotated round robin, tools/llama_gemm_ab.py).

@@ -57,7 +57,23 @@ __device__ __forceinline__ void dot8(const uint4& w, const uint4& x, float& acc)
 // U: 16-byte vectors per weight row a lane keeps in flight (4 = 128 bytes per lane).  Measured and dropped (r02,
 // profiles/r02_decode_ab.json): U = 8 on 128-thread CTAs for the short-N projections (4.98 -> 5.37 ms/token) and a cap on
 // the CTAs per SM so that the next kernel of the programmatic-launch chain is co-resident early (5.08 / 6.13 ms/token).
-template <int M, int MODE, bool NORM, int U>
+// NA: the weight stream is loaded with ld.global.nc.L1::no_allocate -- every weight byte is used exactly once, so it should
+// not displace anything in L1 on its way through (13B decode step 4.87 -> 4.80 ms/token; an added L2::256B prefetch-size hint
+// and 256-bit ld.global.v8.b32 loads measured equal or slower, profiles/r02_gemv_load_policy_ab.txt)
+template <bool NA>
+__device__ __forceinline__ uint4 gemv_ldw(const uint4* p) {
+  if constexpr (!NA) {
+    return __ldg(p);
+  } else {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+  }
+}
+
+template <int M, int MODE, bool NORM, int U, bool NA>
 __global__ void __launch_bounds__(256)
 gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long long ldw, __half* __restrict__ out,
             const __half* __restrict__ residual, const __half* __restrict__ norm_w, float eps, int N, int K,
@@ -93,7 +109,7 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int vi = v0 + lane + u * 32;
-      if (vi < v1) { wa[u] = __ldg(w0 + vi); wb[u] = __ldg(w1 + vi); }
+      if (vi < v1) { wa[u] = gemv_ldw<NA>(w0 + vi); wb[u] = gemv_ldw<NA>(w1 + vi); }
     }
     // ... and the next pf_lines 128-byte lines of both rows go to L2: with programmatic dependent launch this CTA is
     // resident long before its predecessor has finished, and the dependency wait + activation staging below would
@@ -158,7 +174,7 @@ gemv_kernel(const __half* __restrict__ x, const __half* __restrict__ W, long lon
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const int vi = v + u * 32;
-            if (vi < v1) { wa[u] = __ldg(w0 + vi); wb[u] = __ldg(w1 + vi); }
+            if (vi < v1) { wa[u] = gemv_ldw<NA>(w0 + vi); wb[u] = gemv_ldw<NA>(w1 + vi); }
           }
         }
 #pragma unroll
@@ -228,14 +244,15 @@ int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* resid
   SB_REQUIRE(smem <= 200 * 1024, "gemv: activation rows do not fit shared memory (M=%d K=%d)", M, K);
   const int n_tasks = mode == 1 ? N / 2 : (N + 1) / 2;
   const int force_split = get_option("gemv_ksplit");
+  const bool no_alloc = get_option("gemv_no_allocate") != 0;
   const __half* xp = static_cast<const __half*>(x);
   const __half* wp = static_cast<const __half*>(W);
   const __half* rp = static_cast<const __half*>(residual);
   const __half* np = static_cast<const __half*>(norm_w);
   __half* op = static_cast<__half*>(out);
-#define SB_GEMV_LAUNCH(M_, MD_, NM_, U_)                                                                   \
+#define SB_GEMV_LAUNCH(M_, MD_, NM_, U_, NA_)                                                              \
   {                                                                                                        \
-    auto kern = gemv_kernel<M_, MD_, NM_, U_>;                                                             \
+    auto kern = gemv_kernel<M_, MD_, NM_, U_, NA_>;                                                        \
     const int threads = 256;                                                                               \
     static size_t attr_smem_dev[SB_MAX_DEVICES] = {};   /* per device: cudaFuncSetAttribute is */          \
     const int dev_ = cur_device();                                                                         \
@@ -274,8 +291,12 @@ int gemv(const void* x, const void* W, int64_t ldw, void* out, const void* resid
   }
 #define SB_GEMV(M_, MD_)                                                                                   \
   if (M == M_ && mode == MD_) {                                                                            \
-    if (norm_w != nullptr) SB_GEMV_LAUNCH(M_, MD_, true, 4)                                                \
-    SB_GEMV_LAUNCH(M_, MD_, false, 4)                                                                      \
+    if (no_alloc) {                                                                                        \
+      if (norm_w != nullptr) SB_GEMV_LAUNCH(M_, MD_, true, 4, true)                                        \
+      SB_GEMV_LAUNCH(M_, MD_, false, 4, true)                                                              \
+    }                                                                                                      \
+    if (norm_w != nullptr) SB_GEMV_LAUNCH(M_, MD_, true, 4, false)                                         \
+    SB_GEMV_LAUNCH(M_, MD_, false, 4, false)                                                               \
   }
   SB_GEMV(1, 0) SB_GEMV(2, 0) SB_GEMV(3, 0) SB_GEMV(4, 0)
   SB_GEMV(1, 1) SB_GEMV(2, 1) SB_GEMV(3, 1) SB_GEMV(4, 1)
